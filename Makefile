@@ -1,0 +1,73 @@
+# Top-level build.  Knob names follow the reference Makefile (/root/reference/Makefile:24-41):
+#   STATES=DNA  NUM_ACCELERATORS=9  INPUT_SRC=mem|gen  PLIO_LAYOUT=Comb|Sep  WINDOW_SIZE=8192
+#   NO_PRERUN_CHECK / NO_CORRECTNESS_CHECK / NO_INTERMEDIATE_RESULTS  (Makefile:145-161)
+# and its run-time parameters DEVICE, ALIGNMENTS, PLF_CALLS, INSTANCES_USED (Makefile:14-18).
+#
+#   make lib      libb200plf.so            (CUDA kernels + C ABI, sm_100a only)
+#   make host     host_mem.exe host_gen.exe (C++ host drop-ins on top of the C ABI)
+#   make oracle   oracle/liboracle.so (+ oracle/_ref when /root/reference is present)
+#   make run      ./host_<INPUT_SRC>.exe <config> <DEVICE> <ALIGNMENTS> <PLF_CALLS> <INSTANCES_USED>
+
+PKG      := amd-versal-phylogenetic-likelihood-function_b200
+NVCC     ?= nvcc
+CXX      ?= g++
+ARCH     := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS  := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC
+CUDA_HOME ?= /usr/local/cuda
+
+STATES ?= DNA
+AIE_TYPE ?= window
+WINDOW_SIZE ?= 8192
+PLIO_LAYOUT ?= Comb
+NUM_ACCELERATORS ?= 9
+INPUT_SRC ?= mem
+
+DEVICE ?= 0
+ALIGNMENTS ?= 100
+PLF_CALLS ?= 1
+INSTANCES_USED ?= 1
+
+NO_PRERUN_CHECK ?= 1
+NO_CORRECTNESS_CHECK ?= 0
+NO_INTERMEDIATE_RESULTS ?= 0
+
+ifeq ($(AIE_TYPE), stream)
+AIE_COMS_METHOD := $(AIE_TYPE)
+else
+AIE_COMS_METHOD := $(AIE_TYPE)$(WINDOW_SIZE)
+endif
+# Same artefact naming as the reference (Makefile:37-39); the host parses the knobs back out of it.
+CONFIG := plf_128x$(NUM_ACCELERATORS)$(STATES)$(AIE_COMS_METHOD)$(PLIO_LAYOUT)_$(INPUT_SRC)$(STATES)$(AIE_TYPE)$(PLIO_LAYOUT)
+
+LIB  := $(PKG)/libb200plf.so
+HOSTDEFS := -DNO_PRERUN_CHECK=$(NO_PRERUN_CHECK) -DNO_CORRECTNESS_CHECK=$(NO_CORRECTNESS_CHECK) \
+            -DNO_INTERMEDIATE_RESULTS=$(NO_INTERMEDIATE_RESULTS)
+HOSTFLAGS := -O2 -g -Wall -std=c++17 -ffp-contract=off -pthread -Iinclude $(HOSTDEFS)
+
+all: lib host oracle
+
+lib: $(LIB)
+
+$(LIB): $(PKG)/csrc/plf_capi.cu $(PKG)/csrc/plf_kernels.cuh include/b200plf.h
+	$(NVCC) $(NVFLAGS) -shared -o $@ $(PKG)/csrc/plf_capi.cu
+
+host: $(PKG)/host_mem.exe $(PKG)/host_gen.exe
+
+$(PKG)/host_mem.exe: $(PKG)/host/host_mem.cpp $(PKG)/host/golden_plf.cpp $(wildcard $(PKG)/host/*.h) $(LIB)
+	$(CXX) $(HOSTFLAGS) -o $@ $(PKG)/host/host_mem.cpp $(PKG)/host/golden_plf.cpp \
+	    -L$(PKG) -lb200plf -Wl,-rpath,'$$ORIGIN'
+
+$(PKG)/host_gen.exe: $(PKG)/host/host_gen.cpp $(wildcard $(PKG)/host/*.h) $(LIB)
+	$(CXX) $(HOSTFLAGS) -o $@ $(PKG)/host/host_gen.cpp -L$(PKG) -lb200plf -Wl,-rpath,'$$ORIGIN'
+
+oracle:
+	$(MAKE) -C oracle all
+
+run: host
+	./$(PKG)/host_$(INPUT_SRC).exe $(CONFIG) $(DEVICE) $(ALIGNMENTS) $(PLF_CALLS) $(INSTANCES_USED)
+
+clean:
+	rm -f $(LIB) $(PKG)/host_mem.exe $(PKG)/host_gen.exe
+	$(MAKE) -C oracle clean
+
+.PHONY: all lib host oracle run clean

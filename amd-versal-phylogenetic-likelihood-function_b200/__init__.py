@@ -1,0 +1,451 @@
+"""B200-native Phylogenetic Likelihood Function (PLF) "newview" path.
+
+Python face of ``libb200plf.so`` (C ABI: ``include/b200plf.h``).  It mirrors the operator
+surface of the reference host program (GeertRoks/AMD-Versal-phylogenetic-likelihood-function,
+``app/src/host_mem.cpp``): open device -> allocate per-instance buffers -> write packed
+``[EV|P|CLV]`` inputs -> run -> read CLV + scaler bytes -> verify.  All arithmetic happens in
+hand-written sm_100a CUDA kernels; this module only marshals pointers.  There is no CPU
+fallback: if the shared library is missing or no GPU is present, calls raise ``PlfError``.
+
+The directory name of this package is not a Python identifier; import it with
+``importlib`` (see ``tests/conftest.py::load_pkg``) -- it registers itself as ``plf_b200``.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import os
+import subprocess
+from dataclasses import dataclass
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+LIB_PATH = os.path.join(HERE, "libb200plf.so")
+HEADER_PATH = os.path.join(ROOT, "include", "b200plf.h")
+
+SITE_FLOATS = 16
+HEADER_COMB = 80
+HEADER_SEP = 64
+LAYOUT_COMB, LAYOUT_SEP = 0, 1
+INPUT_MEM, INPUT_GEN = 0, 1
+MATH_STRICT, MATH_FMA = 0, 1
+GEN_WRITE, GEN_DISCARD = 0, 1
+MARK_BEGIN, MARK_T1, MARK_T2, MARK_END = 0, 1, 2, 3
+
+# Algorithmic HBM bytes per site: read 64 (x1) + 64 (x2), write 64 (x3) + 1 scaler byte.
+BYTES_PER_SITE = 193
+
+
+class PlfError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"b200plf error {code}: {msg}")
+        self.code = code
+
+
+class LaunchOpts(ctypes.Structure):
+    _fields_ = [("math_mode", ctypes.c_int), ("variant", ctypes.c_int),
+                ("threads_per_block", ctypes.c_int), ("blocks_per_sm", ctypes.c_int),
+                ("ev_per_category", ctypes.c_int)]
+
+
+_vp = ctypes.c_void_p
+_sz = ctypes.c_size_t
+_u = ctypes.c_uint
+_i = ctypes.c_int
+
+# name -> (restype, argtypes): every symbol include/b200plf.h declares.
+PROTOTYPES = {
+    "plf_device_count": (_i, [ctypes.POINTER(_i)]),
+    "plf_device_info": (_i, [_i, ctypes.c_char_p, _sz, ctypes.c_char_p, _sz]),
+    "plf_device_from_string": (_i, [ctypes.c_char_p, ctypes.POINTER(_i)]),
+    "plf_ctx_create": (_i, [ctypes.POINTER(_vp), _i, _u, _i, _i]),
+    "plf_ctx_destroy": (_i, [_vp]),
+    "plf_last_error": (ctypes.c_char_p, [_vp]),
+    "plf_ctx_set_math": (_i, [_vp, _i]),
+    "plf_ctx_set_gen_sink": (_i, [_vp, _i]),
+    "plf_ctx_set_tuning": (_i, [_vp, _i, _i, _i]),
+    "plf_ctx_instances": (_u, [_vp]),
+    "plf_instance_alloc": (_i, [_vp, _u, _sz]),
+    "plf_instance_free": (_i, [_vp, _u]),
+    "plf_write_left": (_i, [_vp, _u, _vp, _sz, _sz]),
+    "plf_write_right": (_i, [_vp, _u, _vp, _sz, _sz]),
+    "plf_write_wgt": (_i, [_vp, _u, _vp, _sz]),
+    "plf_run_async": (_i, [_vp, _u, _sz]),
+    "plf_wait": (_i, [_vp, _u]),
+    "plf_read_out": (_i, [_vp, _u, _vp, _sz, _sz]),
+    "plf_read_scaler": (_i, [_vp, _u, _vp, _sz, _sz]),
+    "plf_scaler_increment": (_i, [_vp, _u, ctypes.POINTER(ctypes.c_longlong)]),
+    "plf_gen_checksum": (_i, [_vp, _u, ctypes.POINTER(ctypes.c_double)]),
+    "plf_mark": (_i, [_vp, _u, _i]),
+    "plf_elapsed_ms": (_i, [_vp, _u, _i, _i, ctypes.POINTER(ctypes.c_float)]),
+    "plf_instance_device_ptrs": (_i, [_vp, _u] + [ctypes.POINTER(_vp)] * 4),
+    "plf_instance_stream": (_i, [_vp, _u, ctypes.POINTER(_vp)]),
+    "plf_host_alloc": (_i, [ctypes.POINTER(_vp), _sz]),
+    "plf_host_free": (_i, [_vp]),
+    "plf_host_register": (_i, [_vp, _sz]),
+    "plf_host_unregister": (_i, [_vp]),
+    "plf_newview_device": (_i, [_vp] * 8 + [_sz, _vp, ctypes.POINTER(LaunchOpts), _vp]),
+    "plf_newview_gen_device": (_i, [_vp, _vp, _sz, _vp, _vp, _i, ctypes.POINTER(LaunchOpts), _vp]),
+    "plf_gen_pattern": (_i, [_vp] * 5),
+    "plf_generate_device": (_i, [_vp, _vp, _sz, _sz, ctypes.c_uint64, _vp]),
+    "plf_generate_host": (_i, [_vp, _vp, _sz, _sz, ctypes.c_uint64]),
+    "plf_kernel_info": (_i, [_i, _i] + [ctypes.POINTER(_i)] * 4),
+    "plf_launch_count": (ctypes.c_ulonglong, []),
+}
+
+_lib = None
+
+
+def build(force: bool = False, quiet: bool = True) -> str:
+    """Compile libb200plf.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    if force and os.path.exists(LIB_PATH):
+        os.remove(LIB_PATH)
+    subprocess.run(["make", "-C", ROOT, "lib"], check=True,
+                   stdout=subprocess.DEVNULL if quiet else None)
+    return LIB_PATH
+
+
+def load():
+    """dlopen libb200plf.so and bind every prototype.  Raises if the library is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PlfError(-2, f"{LIB_PATH} is not built (run `make lib`); there is no CPU fallback")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)      # AttributeError if the header and the library disagree
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _check(rc: int, ctx=None):
+    if rc != 0:
+        msg = load().plf_last_error(ctx)
+        raise PlfError(rc, msg.decode() if msg else "unknown error")
+
+
+def device_count() -> int:
+    n = _i(0)
+    rc = load().plf_device_count(ctypes.byref(n))
+    return n.value if rc == 0 else 0
+
+
+def device_info(device: int = 0):
+    name = ctypes.create_string_buffer(256)
+    bdf = ctypes.create_string_buffer(32)
+    _check(load().plf_device_info(device, name, 256, bdf, 32))
+    return name.value.decode(), bdf.value.decode()
+
+
+def launch_count() -> int:
+    return int(load().plf_launch_count())
+
+
+def _ptr(a):
+    """numpy array / int / None -> void* value."""
+    if a is None:
+        return None
+    if isinstance(a, (int, np.integer)):
+        return int(a)
+    return a.ctypes.data
+
+
+# ------------------------------------------------------------------------------------------
+# Host-side size / partition math of the reference test bench (app/src/include.h:150-268),
+# with 64-bit sizes (the reference's `unsigned int` byte counts wrap at 4 GiB).
+# ------------------------------------------------------------------------------------------
+@dataclass
+class TestbenchInfo:
+    __test__ = False  # not a pytest class
+    alignment_sites: int
+    parallel_instances: int = 1
+    plf_calls: int = 1
+    window_size: int = 8192
+    layout: int = LAYOUT_COMB
+    elements_per_alignment: int = SITE_FLOATS
+    word_size: int = 4
+
+    def alignments_per_instance(self, instance: int | None = None) -> int:
+        """ceil(n / instances); the last instance takes the remainder (include.h:181-192)."""
+        per = math.ceil(self.alignment_sites / self.parallel_instances)
+        if instance is None:
+            return per
+        if instance == self.parallel_instances - 1:
+            return per - self.alignments_padding()
+        return per
+
+    def alignments_padding(self) -> int:
+        return self.alignments_per_instance() * self.parallel_instances - self.alignment_sites
+
+    def instance_offset(self, instance: int) -> int:
+        """First site of an instance: k * alignments_per_instance(0) (host_mem.cpp:229,290)."""
+        return instance * self.alignments_per_instance()
+
+    def header_left(self) -> int:
+        return HEADER_COMB
+
+    def header_right(self) -> int:
+        return HEADER_COMB if self.layout == LAYOUT_COMB else HEADER_SEP
+
+    def instance_active_elements_left(self, instance: int) -> int:
+        return self.alignments_per_instance(instance) * self.elements_per_alignment + self.header_left()
+
+    def instance_active_elements_right(self, instance: int) -> int:
+        return self.alignments_per_instance(instance) * self.elements_per_alignment + self.header_right()
+
+    def elements_per_plf(self) -> int:
+        return self.alignment_sites * self.elements_per_alignment
+
+    def data_size(self) -> int:
+        """Bytes of result CLV over all calls -- what timing.h:101-103 divides by time."""
+        return self.elements_per_plf() * self.word_size * self.plf_calls
+
+    def valid(self) -> bool:
+        """Every instance must own at least one site (the reference silently underflows)."""
+        return (self.alignment_sites > 0 and self.parallel_instances > 0 and
+                self.alignments_per_instance(self.parallel_instances - 1) > 0)
+
+
+def partition_sites(n: int, parts: int):
+    """[(first_site, count)] per part with the reference rule (include.h:181-192).  Parts that
+    would be empty or negative under that rule are returned with count 0."""
+    per = math.ceil(n / parts) if parts > 0 else 0
+    out = []
+    for k in range(parts):
+        lo = min(k * per, n)
+        out.append((lo, max(0, min(per, n - lo))))
+    return out
+
+
+def pack_left(ev, p_left, x1):
+    """[EV16 | P_left64 | CLV] (host_mem.cpp:231-233)."""
+    return np.concatenate([np.asarray(ev, np.float32).reshape(16),
+                           np.asarray(p_left, np.float32).reshape(64),
+                           np.asarray(x1, np.float32).reshape(-1)])
+
+
+def pack_right(ev, p_right, x2, layout: int = LAYOUT_COMB):
+    """Comb: [EV16 | P_right64 | CLV]; Sep: [P_right64 | CLV] (host_mem.cpp:234-241)."""
+    parts = [np.asarray(p_right, np.float32).reshape(64), np.asarray(x2, np.float32).reshape(-1)]
+    if layout == LAYOUT_COMB:
+        parts.insert(0, np.asarray(ev, np.float32).reshape(16))
+    return np.concatenate(parts)
+
+
+class Context:
+    """One GPU with NUM_ACCELERATORS independent PLF instances (CUDA streams).
+
+    Mirrors the XRT objects the reference host holds: acap_info + per-instance kernels, buffer
+    objects and run handles (host_mem.cpp:108-157)."""
+
+    def __init__(self, device: int = 0, n_instances: int = 1, layout: int = LAYOUT_COMB,
+                 input_src: int = INPUT_MEM):
+        self.lib = load()
+        self._ctx = _vp()
+        _check(self.lib.plf_ctx_create(ctypes.byref(self._ctx), device, n_instances, layout, input_src))
+        self.device = device
+        self.n_instances = n_instances
+        self.layout = layout
+        self.input_src = input_src
+
+    def close(self):
+        if self._ctx:
+            self.lib.plf_ctx_destroy(self._ctx)
+            self._ctx = _vp()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        _check(rc, self._ctx)
+
+    def set_math(self, mode: int):
+        self._ck(self.lib.plf_ctx_set_math(self._ctx, mode))
+
+    def set_gen_sink(self, sink: int):
+        self._ck(self.lib.plf_ctx_set_gen_sink(self._ctx, sink))
+
+    def set_tuning(self, variant: int = 0, threads: int = 0, blocks_per_sm: int = 0):
+        self._ck(self.lib.plf_ctx_set_tuning(self._ctx, variant, threads, blocks_per_sm))
+
+    def instance_alloc(self, inst: int, max_sites: int):
+        self._ck(self.lib.plf_instance_alloc(self._ctx, inst, max_sites))
+
+    def instance_free(self, inst: int):
+        self._ck(self.lib.plf_instance_free(self._ctx, inst))
+
+    def write_left(self, inst: int, packed, nbytes: int | None = None, offset: int = 0):
+        nbytes = packed.nbytes if nbytes is None else nbytes
+        self._ck(self.lib.plf_write_left(self._ctx, inst, _ptr(packed), nbytes, offset))
+
+    def write_right(self, inst: int, packed, nbytes: int | None = None, offset: int = 0):
+        nbytes = packed.nbytes if nbytes is None else nbytes
+        self._ck(self.lib.plf_write_right(self._ctx, inst, _ptr(packed), nbytes, offset))
+
+    def write_wgt(self, inst: int, wgt):
+        if wgt is None:
+            self._ck(self.lib.plf_write_wgt(self._ctx, inst, None, 0))
+        else:
+            assert wgt.dtype == np.int32 and wgt.flags.c_contiguous
+            self._ck(self.lib.plf_write_wgt(self._ctx, inst, _ptr(wgt), wgt.size))
+
+    def run_async(self, inst: int, sites: int):
+        self._ck(self.lib.plf_run_async(self._ctx, inst, sites))
+
+    def wait(self, inst: int):
+        self._ck(self.lib.plf_wait(self._ctx, inst))
+
+    def read_out(self, inst: int, dst, nbytes: int | None = None, offset: int = 0):
+        nbytes = dst.nbytes if nbytes is None else nbytes
+        self._ck(self.lib.plf_read_out(self._ctx, inst, _ptr(dst), nbytes, offset))
+
+    def read_scaler(self, inst: int, dst, nbytes: int | None = None, offset: int = 0):
+        nbytes = dst.nbytes if nbytes is None else nbytes
+        self._ck(self.lib.plf_read_scaler(self._ctx, inst, _ptr(dst), nbytes, offset))
+
+    def scaler_increment(self, inst: int) -> int:
+        v = ctypes.c_longlong(0)
+        self._ck(self.lib.plf_scaler_increment(self._ctx, inst, ctypes.byref(v)))
+        return v.value
+
+    def gen_checksum(self, inst: int) -> float:
+        v = ctypes.c_double(0)
+        self._ck(self.lib.plf_gen_checksum(self._ctx, inst, ctypes.byref(v)))
+        return v.value
+
+    def mark(self, inst: int, mark_id: int):
+        self._ck(self.lib.plf_mark(self._ctx, inst, mark_id))
+
+    def elapsed_ms(self, inst: int, a: int, b: int) -> float:
+        v = ctypes.c_float(0)
+        self._ck(self.lib.plf_elapsed_ms(self._ctx, inst, a, b, ctypes.byref(v)))
+        return v.value
+
+    def device_ptrs(self, inst: int):
+        p = [_vp() for _ in range(4)]
+        self._ck(self.lib.plf_instance_device_ptrs(self._ctx, inst, *[ctypes.byref(x) for x in p]))
+        return tuple(x.value for x in p)
+
+    def stream(self, inst: int) -> int:
+        s = _vp()
+        self._ck(self.lib.plf_instance_stream(self._ctx, inst, ctypes.byref(s)))
+        return s.value or 0
+
+    # -- the reference host's per-call sequence (host_mem.cpp:287-325) for numpy inputs --------
+    def newview(self, ev, p_left, p_right, x1, x2, wgt=None, instances: int | None = None,
+                timings: bool = False):
+        """Packs [EV|P|CLV] per instance, writes, runs, reads back.  Returns
+        (x3[n,16] f32, scaler[n] u8, scaler_increment)."""
+        if self.input_src != INPUT_MEM:
+            raise PlfError(-4, "Context.newview needs INPUT_SRC=mem")
+        x1 = np.ascontiguousarray(x1, np.float32).reshape(-1, 16)
+        x2 = np.ascontiguousarray(x2, np.float32).reshape(-1, 16)
+        n = x1.shape[0]
+        k_inst = self.n_instances if instances is None else instances
+        tb = TestbenchInfo(n, k_inst, layout=self.layout)
+        if n and not tb.valid():
+            raise PlfError(-1, f"{n} sites cannot be split over {k_inst} instances "
+                               "(last instance would be empty)")
+        out = np.empty((n, 16), np.float32)
+        sc = np.empty(n, np.uint8)
+        if wgt is not None:
+            wgt = np.ascontiguousarray(wgt, np.int32)
+        keep = []
+        total = 0
+        if n == 0:
+            return out, sc, 0
+        for k in range(k_inst):
+            lo, cnt = tb.instance_offset(k), tb.alignments_per_instance(k)
+            lb = pack_left(ev, p_left, x1[lo:lo + cnt])
+            rb = pack_right(ev, p_right, x2[lo:lo + cnt], self.layout)
+            keep += [lb, rb]
+            self.instance_alloc(k, cnt)
+            self.mark(k, MARK_BEGIN)
+            self.write_left(k, lb, tb.instance_active_elements_left(k) * 4)
+            self.write_right(k, rb, tb.instance_active_elements_right(k) * 4)
+            self.write_wgt(k, None if wgt is None else wgt[lo:lo + cnt])
+            self.mark(k, MARK_T1)
+            self.run_async(k, cnt)
+            self.mark(k, MARK_T2)
+            self.read_out(k, out[lo:lo + cnt])
+            self.read_scaler(k, sc[lo:lo + cnt])
+            self.mark(k, MARK_END)
+        for k in range(k_inst):
+            self.wait(k)
+            total += self.scaler_increment(k)
+        if timings:
+            t = [(self.elapsed_ms(k, MARK_BEGIN, MARK_T1), self.elapsed_ms(k, MARK_T1, MARK_T2),
+                  self.elapsed_ms(k, MARK_T2, MARK_END)) for k in range(k_inst)]
+            return out, sc, total, t
+        return out, sc, total
+
+
+def make_opts(math_mode: int = MATH_STRICT, variant: int = 0, threads: int = 0,
+              blocks_per_sm: int = 0, ev_per_category: int = 0) -> LaunchOpts:
+    return LaunchOpts(math_mode, variant, threads, blocks_per_sm, ev_per_category)
+
+
+def newview_device(x1, x2, x3, scaler, ev, p_left, p_right, wgt, n: int, scaler_sum,
+                   opts: LaunchOpts | None = None, stream: int = 0):
+    """Fused newview on caller-owned DEVICE memory; every pointer is an int (e.g. tensor.data_ptr())."""
+    _check(load().plf_newview_device(x1, x2, x3, scaler, ev, p_left, p_right, wgt, n, scaler_sum,
+                                     ctypes.byref(opts) if opts is not None else None, stream or None))
+
+
+def newview_gen_device(x3, scaler, n: int, scaler_sum, checksum, sink: int = GEN_WRITE,
+                       opts: LaunchOpts | None = None, stream: int = 0):
+    _check(load().plf_newview_gen_device(x3, scaler, n, scaler_sum, checksum, sink,
+                                         ctypes.byref(opts) if opts is not None else None,
+                                         stream or None))
+
+
+def gen_pattern():
+    """(x1[16], x2[16], ev4[64], p_left[64], p_right[64]) of the INPUT_SRC=gen movers."""
+    arrs = [np.empty(k, np.float32) for k in (16, 16, 64, 64, 64)]
+    _check(load().plf_gen_pattern(*[_ptr(a) for a in arrs]))
+    return tuple(arrs)
+
+
+def generate_device(x1, x2, first_site: int, n: int, seed: int, stream: int = 0):
+    _check(load().plf_generate_device(x1, x2, first_site, n, seed, stream or None))
+
+
+def generate_host(first_site: int, n: int, seed: int):
+    x1 = np.empty((n, 16), np.float32)
+    x2 = np.empty((n, 16), np.float32)
+    _check(load().plf_generate_host(_ptr(x1), _ptr(x2), first_site, n, seed))
+    return x1, x2
+
+
+def kernel_info(variant: int = 0, math_mode: int = MATH_STRICT, threads: int = 0):
+    regs, thr, bps, sms = _i(0), _i(threads), _i(0), _i(0)
+    _check(load().plf_kernel_info(variant, math_mode, ctypes.byref(regs), ctypes.byref(thr),
+                                  ctypes.byref(bps), ctypes.byref(sms)))
+    return {"regs": regs.value, "threads": thr.value, "blocks_per_sm": bps.value, "sms": sms.value}
+
+
+def host_alloc(nbytes: int, dtype=np.uint8):
+    """Pinned host memory as a numpy array (freed with host_free(arr))."""
+    p = _vp()
+    _check(load().plf_host_alloc(ctypes.byref(p), nbytes))
+    buf = (ctypes.c_ubyte * nbytes).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=np.uint8).view(dtype)
+    return arr, p.value
+
+
+def host_free(ptr: int):
+    _check(load().plf_host_free(ptr))

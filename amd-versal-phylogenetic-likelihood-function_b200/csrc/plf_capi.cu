@@ -1,0 +1,940 @@
+// csrc/plf_capi.cu -- the C ABI of include/b200plf.h over the CUDA runtime.
+//
+// Replaces the XRT control code of the reference host (app/src/include.h:28-147 acap_info,
+// app/src/host_mem.cpp:108-164,249-325): device open, device-only buffers, async write / run /
+// read on per-instance queues.  Here an "instance" (NUM_ACCELERATORS, Makefile:29) is a set of
+// device buffers plus one CUDA stream; the three PL kernels + AIE graph are one fused kernel.
+//
+// No exception leaves this file and there is no CPU fallback: every failure is a status code.
+#include "../../include/b200plf.h"
+#include "plf_kernels.cuh"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_last_error = "";
+std::atomic<unsigned long long> g_launches{0};
+
+struct Instance {
+    bool allocated = false;
+    size_t max_sites = 0;
+    float *d_left = nullptr;
+    float *d_right = nullptr;
+    float *d_out = nullptr;
+    unsigned char *d_scaler = nullptr;
+    int *d_wgt = nullptr;
+    bool use_wgt = false;
+    unsigned long long *d_sum = nullptr;    // [0] scaler sum of the last run
+    double *d_check = nullptr;              // gen-discard checksum of the last run
+    unsigned long long *h_sum = nullptr;    // pinned mirrors, filled after each run
+    double *h_check = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t marks[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool mark_set[4] = {false, false, false, false};
+    std::string error;
+};
+
+}  // namespace
+
+struct plf_ctx {
+    int device = 0;
+    int layout = PLF_LAYOUT_COMB;
+    int input_src = PLF_INPUT_MEM;
+    int math = PLF_MATH_STRICT;
+    int gen_sink = PLF_GEN_WRITE;
+    int variant = 0, threads = 0, blocks_per_sm = 0;
+    int num_sms = 0;
+    float *d_gen = nullptr;                 // gen pattern: x1[16] x2[16] ev4[64] pl[64] pr[64]
+    std::vector<Instance> inst;
+    std::mutex err_mu;
+    std::string error;
+};
+
+namespace {
+
+int fail(plf_ctx *ctx, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) {
+        std::lock_guard<std::mutex> g(ctx->err_mu);
+        ctx->error = buf;
+    }
+    g_last_error = buf;
+    return code;
+}
+
+#define PLF_CUDA(ctx, expr)                                                                     \
+    do {                                                                                        \
+        cudaError_t e__ = (expr);                                                               \
+        if (e__ != cudaSuccess)                                                                 \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? PLF_ERR_NOMEM : PLF_ERR_CUDA,   \
+                        "%s failed: %s", #expr, cudaGetErrorString(e__));                       \
+    } while (0)
+
+// ---- kernel variant registry -------------------------------------------------------------------
+// variant = 1000*B + 100*D + 10*K + U
+//   U : 128-bit loads per child per thread per tile (1, 2 or 4)
+//   K : 0 = "ldg" register-staged kernel with streaming load/store policy
+//       1 = "ldg" with plain (cached) loads/stores
+//       2 = "tma" bulk-copy / mbarrier ring kernel
+//   D : tma only: ring depth in stages (0 -> 4)
+//   B : minimum resident blocks per SM given to __launch_bounds__ (0 -> 1); caps registers/thread
+// threads_per_block is the number of COMPUTE threads (tma adds one producer warp).
+// variant 0 selects kDefaultVariant.
+constexpr int kDefaultVariant = 2422;
+constexpr int kDefaultThreads = 256;
+
+using NewviewFn = void (*)(const float4 *, const float4 *, float4 *, unsigned char *, const float *,
+                           const float *, const float *, const int *, size_t, unsigned long long *,
+                           int);
+
+struct KernelSel {
+    NewviewFn fn = nullptr;
+    int threads = 0;            // launch block size
+    size_t smem = 0;            // dynamic shared memory
+    int sites_per_block_iter = 0;
+};
+
+template <class M, int U, bool STREAM, int MINB>
+KernelSel sel_ldg(int threads)
+{
+    KernelSel k;
+    switch (threads) {
+    case 128: k.fn = plf::plf_newview_ldg<M, U, STREAM, 128, MINB>; break;
+    case 256: k.fn = plf::plf_newview_ldg<M, U, STREAM, 256, MINB>; break;
+    case 512: if (MINB <= 2) k.fn = plf::plf_newview_ldg<M, U, STREAM, 512, (MINB <= 2 ? MINB : 1)>; break;
+    default: break;
+    }
+    k.threads = threads;
+    k.sites_per_block_iter = (threads / 32) * 8 * U;
+    return k;
+}
+
+template <class M, int U>
+KernelSel sel_ldg_u(int kind, int b, int threads)
+{
+    if (kind == 1) return b <= 1 ? sel_ldg<M, U, false, 1>(threads) : KernelSel{};
+    switch (b) {
+    case 0: case 1: return sel_ldg<M, U, true, 1>(threads);
+    case 2: return sel_ldg<M, U, true, 2>(threads);
+    case 3: return sel_ldg<M, U, true, 3>(threads);
+    case 4: return sel_ldg<M, U, true, 4>(threads);
+    default: return KernelSel{};
+    }
+}
+
+template <class M, int U, int WARPS, int DEPTH, int MINB>
+KernelSel sel_tma_one()
+{
+    KernelSel k;
+    k.smem = plf::tma_smem_bytes<U, WARPS, DEPTH>();
+    if (k.smem * MINB > 227u * 1024u) return KernelSel{};
+    k.fn = plf::plf_newview_tma<M, U, WARPS, DEPTH, MINB>;
+    k.threads = (WARPS + 1) * 32;
+    k.sites_per_block_iter = WARPS * 8 * U;
+    return k;
+}
+
+template <class M, int U, int WARPS, int MINB>
+KernelSel sel_tma_d(int d)
+{
+    switch (d) {
+    case 2: return sel_tma_one<M, U, WARPS, 2, MINB>();
+    case 3: return sel_tma_one<M, U, WARPS, 3, MINB>();
+    case 0: case 4: return sel_tma_one<M, U, WARPS, 4, MINB>();
+    case 6: return sel_tma_one<M, U, WARPS, 6, MINB>();
+    case 8: return sel_tma_one<M, U, WARPS, 8, MINB>();
+    default: return KernelSel{};
+    }
+}
+
+// consumer warps 4 / 8 / 16 with the launch bounds that still fit 2048 threads per SM
+template <class M, int U>
+KernelSel sel_tma_u(int b, int d, int threads)
+{
+    if (b == 0) b = 1;
+    switch (threads) {
+    case 128:
+        switch (b) {
+        case 1: return sel_tma_d<M, U, 4, 1>(d);
+        case 2: return sel_tma_d<M, U, 4, 2>(d);
+        case 3: return sel_tma_d<M, U, 4, 3>(d);
+        case 4: return sel_tma_d<M, U, 4, 4>(d);
+        default: return KernelSel{};
+        }
+    case 256:
+        switch (b) {
+        case 1: return sel_tma_d<M, U, 8, 1>(d);
+        case 2: return sel_tma_d<M, U, 8, 2>(d);
+        case 3: return sel_tma_d<M, U, 8, 3>(d);
+        default: return KernelSel{};
+        }
+    case 512:
+        switch (b) {
+        case 1: return sel_tma_d<M, U, 16, 1>(d);
+        default: return KernelSel{};
+        }
+    default: return KernelSel{};
+    }
+}
+
+template <class M>
+KernelSel sel_math(int variant, int threads)
+{
+    const int u = variant % 10, kind = (variant / 10) % 10, d = (variant / 100) % 10, b = variant / 1000;
+    if (kind == 2) {
+        switch (u) {
+        case 1: return sel_tma_u<M, 1>(b, d, threads);
+        case 2: return sel_tma_u<M, 2>(b, d, threads);
+        case 4: return sel_tma_u<M, 4>(b, d, threads);
+        default: return KernelSel{};
+        }
+    }
+    if ((kind == 0 || kind == 1) && d == 0) {
+        switch (u) {
+        case 1: return sel_ldg_u<M, 1>(kind, b, threads);
+        case 2: return sel_ldg_u<M, 2>(kind, b, threads);
+        case 4: return sel_ldg_u<M, 4>(kind, b, threads);
+        default: return KernelSel{};
+        }
+    }
+    return KernelSel{};
+}
+
+KernelSel pick_kernel(int math, int variant, int threads)
+{
+    if (variant < 0 || variant > 9999) return KernelSel{};
+    return math == PLF_MATH_FMA ? sel_math<plf::MathFma>(variant, threads)
+                                : sel_math<plf::MathStrict>(variant, threads);
+}
+
+int device_sms(int *sms)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    if (cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    return 0;
+}
+
+// Opt in to > 48 KB of dynamic shared memory once per kernel and device.
+int prepare_kernel(plf_ctx *ctx, const KernelSel &k)
+{
+    if (k.smem > 48u * 1024u)
+        PLF_CUDA(ctx, cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.smem));
+    return PLF_OK;
+}
+
+// Resolves defaults and the persistent grid size: SMs x resident blocks per SM, capped by the
+// amount of work so that small inputs do not launch idle blocks.
+int resolve_launch(plf_ctx *ctx, const plf_launch_opts *opts, size_t n, KernelSel *sel, int *grid)
+{
+    int math = opts ? opts->math_mode : PLF_MATH_STRICT;
+    int variant = opts && opts->variant ? opts->variant : kDefaultVariant;
+    int thr = opts && opts->threads_per_block ? opts->threads_per_block : kDefaultThreads;
+    int bps = opts ? opts->blocks_per_sm : 0;
+    if (math != PLF_MATH_STRICT && math != PLF_MATH_FMA)
+        return fail(ctx, PLF_ERR_INVALID, "unknown math mode %d", math);
+    KernelSel k = pick_kernel(math, variant, thr);
+    if (!k.fn)
+        return fail(ctx, PLF_ERR_INVALID, "unknown kernel variant %d / threads %d", variant, thr);
+    int sms = 0;
+    if (device_sms(&sms) != 0) return fail(ctx, PLF_ERR_CUDA, "no CUDA device");
+    int rc = prepare_kernel(ctx, k);
+    if (rc != PLF_OK) return rc;
+    if (bps <= 0) {
+        int occ = 0;
+        PLF_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k.fn, k.threads, k.smem));
+        bps = occ > 0 ? occ : 1;
+    }
+    const size_t per_iter = (size_t)k.sites_per_block_iter;
+    const size_t blocks_needed = (n + per_iter - 1) / per_iter;
+    size_t g = (size_t)sms * (size_t)bps;
+    if (g > blocks_needed) g = blocks_needed;
+    if (g == 0) g = 1;
+    *sel = k;
+    *grid = (int)g;
+    return PLF_OK;
+}
+
+int launch_newview(plf_ctx *ctx, const float *x1, const float *x2, float *x3, unsigned char *scaler,
+                   const float *ev, const float *pl, const float *pr, const int *wgt, size_t n,
+                   unsigned long long *sum, const plf_launch_opts *opts, cudaStream_t stream)
+{
+    if (n == 0) return PLF_OK;
+    if (!x1 || !x2 || !x3 || !ev || !pl || !pr)
+        return fail(ctx, PLF_ERR_INVALID, "newview: NULL device pointer");
+    if (((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)x3 | (uintptr_t)ev | (uintptr_t)pl |
+         (uintptr_t)pr) & 15u)
+        return fail(ctx, PLF_ERR_INVALID, "newview: CLV / matrix pointers must be 16-byte aligned");
+    KernelSel k;
+    int grid = 0;
+    int rc = resolve_launch(ctx, opts, n, &k, &grid);
+    if (rc != PLF_OK) return rc;
+    k.fn<<<grid, k.threads, k.smem, stream>>>(reinterpret_cast<const float4 *>(x1),
+                                              reinterpret_cast<const float4 *>(x2),
+                                              reinterpret_cast<float4 *>(x3), scaler, ev, pl, pr, wgt, n,
+                                              sum, opts ? opts->ev_per_category : 0);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    PLF_CUDA(ctx, cudaGetLastError());
+    return PLF_OK;
+}
+
+// Constant site patterns of the gen movers (values are data: mm2sleft_genDNAwindowComb.cpp:44-49,
+// mm2sright_genDNAwindowComb.cpp:45-50) and the header each AIE lane derives from them: in gen
+// mode the 2 EV beats and the 4 branch beats in front of every window carry the same 128-bit
+// word as the site beats (mm2sleft_genDNAwindowComb.cpp:70-84), so lane j sees
+//   EV_j rows 0,1 = left[4j..4j+3], rows 2,3 = right[4j..4j+3]   (combine.cpp:17-19)
+//   P^T rows = left[4j..4j+3]  =>  P_left[j][k][l] = left[4j+k]   (mmul_branch.cpp:27-29)
+const float kGenLeft[16] = {0.2135f, 0.1427f, 0.4139f, 0.8301f, 0.2021f, 0.9124f, 0.6542f, 0.1235f,
+                            0.4856f, 0.2242f, 0.1322f, 0.5223f, 0.8223f, 0.7741f, 0.9855f, 0.2024f};
+const float kGenRight[16] = {0.123456f, 0.234567f, 0.345678f, 0.789543f, 0.456789f, 0.567890f,
+                             0.678901f, 0.789012f, 0.890123f, 0.901234f, 0.012345f, 0.023456f,
+                             0.034567f, 0.045678f, 0.056789f, 0.067890f};
+
+void build_gen_pattern(float *x1, float *x2, float *ev4, float *pl, float *pr)
+{
+    for (int e = 0; e < 16; ++e) {
+        x1[e] = kGenLeft[e];
+        x2[e] = kGenRight[e];
+    }
+    for (int j = 0; j < 4; ++j)
+        for (int k = 0; k < 4; ++k)
+            for (int l = 0; l < 4; ++l) {
+                ev4[16 * j + 4 * k + l] = (k < 2) ? kGenLeft[4 * j + l] : kGenRight[4 * j + l];
+                pl[16 * j + 4 * k + l] = kGenLeft[4 * j + k];
+                pr[16 * j + 4 * k + l] = kGenRight[4 * j + k];
+            }
+}
+
+template <class M, bool DISCARD>
+int launch_gen_t(plf_ctx *ctx, float *x3, unsigned char *scaler, const float *d_gen, size_t n,
+                 unsigned long long *sum, double *checksum, int bps_opt, cudaStream_t stream)
+{
+    constexpr int U = 2, THREADS = 256;
+    auto fn = plf::plf_newview_gen<M, U, DISCARD, THREADS, 1>;
+    int sms = 0;
+    if (device_sms(&sms) != 0) return fail(ctx, PLF_ERR_CUDA, "no CUDA device");
+    int bps = bps_opt;
+    if (bps <= 0) {
+        PLF_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, THREADS, 0));
+        if (bps <= 0) bps = 1;
+    }
+    const size_t tiles = (n + 8 * U - 1) / (8 * U);
+    const size_t need = (tiles + THREADS / 32 - 1) / (THREADS / 32);
+    size_t g = (size_t)sms * bps;
+    if (g > need) g = need;
+    if (g == 0) g = 1;
+    fn<<<(int)g, THREADS, 0, stream>>>(reinterpret_cast<float4 *>(x3), scaler, d_gen, d_gen + 16,
+                                       d_gen + 32, d_gen + 96, d_gen + 160, n, sum, checksum);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    PLF_CUDA(ctx, cudaGetLastError());
+    return PLF_OK;
+}
+
+int launch_gen(plf_ctx *ctx, float *x3, unsigned char *scaler, const float *d_gen, size_t n,
+               unsigned long long *sum, double *checksum, int sink, const plf_launch_opts *opts,
+               cudaStream_t stream)
+{
+    if (n == 0) return PLF_OK;
+    const int math = opts ? opts->math_mode : PLF_MATH_STRICT;
+    const int bps = opts ? opts->blocks_per_sm : 0;
+    if (sink == PLF_GEN_WRITE) {
+        if (!x3 || ((uintptr_t)x3 & 15u))
+            return fail(ctx, PLF_ERR_INVALID, "gen: x3 must be a 16-byte aligned device pointer");
+        return math == PLF_MATH_FMA
+                   ? launch_gen_t<plf::MathFma, false>(ctx, x3, scaler, d_gen, n, sum, checksum, bps, stream)
+                   : launch_gen_t<plf::MathStrict, false>(ctx, x3, scaler, d_gen, n, sum, checksum, bps, stream);
+    }
+    if (sink == PLF_GEN_DISCARD)
+        return math == PLF_MATH_FMA
+                   ? launch_gen_t<plf::MathFma, true>(ctx, x3, scaler, d_gen, n, sum, checksum, bps, stream)
+                   : launch_gen_t<plf::MathStrict, true>(ctx, x3, scaler, d_gen, n, sum, checksum, bps, stream);
+    return fail(ctx, PLF_ERR_INVALID, "gen: unknown sink %d", sink);
+}
+
+// One device-resident copy of the gen pattern per device, for the ctx-less entry point.
+std::mutex g_gen_mu;
+float *g_gen_dev[64] = {nullptr};
+
+int gen_pattern_device(plf_ctx *ctx, float **out)
+{
+    int dev = 0;
+    PLF_CUDA(ctx, cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(ctx, PLF_ERR_INVALID, "device ordinal %d out of range", dev);
+    std::lock_guard<std::mutex> g(g_gen_mu);
+    if (!g_gen_dev[dev]) {
+        float h[224];
+        build_gen_pattern(h, h + 16, h + 32, h + 96, h + 160);
+        float *d = nullptr;
+        PLF_CUDA(ctx, cudaMalloc(&d, sizeof h));
+        PLF_CUDA(ctx, cudaMemcpy(d, h, sizeof h, cudaMemcpyHostToDevice));
+        g_gen_dev[dev] = d;
+    }
+    *out = g_gen_dev[dev];
+    return PLF_OK;
+}
+
+int check_inst(plf_ctx *ctx, unsigned inst, bool need_alloc, Instance **out)
+{
+    if (!ctx) return fail(nullptr, PLF_ERR_INVALID, "NULL context");
+    if (inst >= ctx->inst.size())
+        return fail(ctx, PLF_ERR_INVALID, "instance %u out of range (context has %zu)", inst,
+                    ctx->inst.size());
+    Instance *I = &ctx->inst[inst];
+    if (need_alloc && !I->allocated)
+        return fail(ctx, PLF_ERR_STATE, "instance %u has no buffers (call plf_instance_alloc)", inst);
+    *out = I;
+    return PLF_OK;
+}
+
+size_t right_header(const plf_ctx *ctx)
+{
+    return ctx->layout == PLF_LAYOUT_COMB ? PLF_HEADER_COMB : PLF_HEADER_SEP;
+}
+
+void free_instance(Instance &I)
+{
+    cudaFree(I.d_left);
+    cudaFree(I.d_right);
+    cudaFree(I.d_out);
+    cudaFree(I.d_scaler);
+    cudaFree(I.d_wgt);
+    I.d_left = I.d_right = I.d_out = nullptr;
+    I.d_scaler = nullptr;
+    I.d_wgt = nullptr;
+    I.use_wgt = false;
+    I.allocated = false;
+    I.max_sites = 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *plf_last_error(const plf_ctx *ctx)
+{
+    if (ctx) {
+        plf_ctx *c = const_cast<plf_ctx *>(ctx);
+        std::lock_guard<std::mutex> g(c->err_mu);
+        g_last_error = c->error;
+    }
+    return g_last_error.c_str();
+}
+
+unsigned long long plf_launch_count(void) { return g_launches.load(); }
+
+int plf_device_count(int *count)
+{
+    if (!count) return fail(nullptr, PLF_ERR_INVALID, "NULL count");
+    *count = 0;
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        *count = 0;
+        cudaGetLastError();
+        return fail(nullptr, PLF_ERR_CUDA, "cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+    }
+    return PLF_OK;
+}
+
+int plf_device_info(int device, char *name, size_t name_len, char *bdf, size_t bdf_len)
+{
+    cudaDeviceProp prop;
+    PLF_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
+    if (name && name_len) snprintf(name, name_len, "%s", prop.name);
+    if (bdf && bdf_len) {
+        char tmp[32];
+        PLF_CUDA(nullptr, cudaDeviceGetPCIBusId(tmp, sizeof tmp, device));
+        snprintf(bdf, bdf_len, "%s", tmp);
+    }
+    return PLF_OK;
+}
+
+int plf_device_from_string(const char *s, int *device)
+{
+    if (!s || !device) return fail(nullptr, PLF_ERR_INVALID, "NULL argument");
+    if (strchr(s, ':')) {
+        PLF_CUDA(nullptr, cudaDeviceGetByPCIBusId(device, s));
+        return PLF_OK;
+    }
+    char *end = nullptr;
+    long v = strtol(s, &end, 10);
+    if (end == s || *end != '\0' || v < 0)
+        return fail(nullptr, PLF_ERR_INVALID, "'%s' is neither a PCI BDF nor a device ordinal", s);
+    int count = 0;
+    int rc = plf_device_count(&count);
+    if (rc != PLF_OK) return rc;
+    if (v >= count) return fail(nullptr, PLF_ERR_INVALID, "device %ld not present (%d devices)", v, count);
+    *device = (int)v;
+    return PLF_OK;
+}
+
+int plf_ctx_create(plf_ctx **out, int device, unsigned n_instances, int layout, int input_src)
+{
+    if (!out) return fail(nullptr, PLF_ERR_INVALID, "NULL ctx out-pointer");
+    *out = nullptr;
+    if (n_instances == 0 || n_instances > 1024)
+        return fail(nullptr, PLF_ERR_INVALID, "n_instances must be in 1..1024 (got %u)", n_instances);
+    if (layout != PLF_LAYOUT_COMB && layout != PLF_LAYOUT_SEP)
+        return fail(nullptr, PLF_ERR_INVALID, "unknown layout %d", layout);
+    if (input_src != PLF_INPUT_MEM && input_src != PLF_INPUT_GEN)
+        return fail(nullptr, PLF_ERR_INVALID, "unknown input source %d", input_src);
+    int count = 0;
+    int rc = plf_device_count(&count);
+    if (rc != PLF_OK) return rc;
+    if (count == 0) return fail(nullptr, PLF_ERR_CUDA, "no CUDA device present (no CPU fallback)");
+    if (device < 0 || device >= count)
+        return fail(nullptr, PLF_ERR_INVALID, "device %d not present (%d devices)", device, count);
+    PLF_CUDA(nullptr, cudaSetDevice(device));
+    plf_ctx *ctx = new (std::nothrow) plf_ctx;
+    if (!ctx) return fail(nullptr, PLF_ERR_NOMEM, "out of host memory");
+    ctx->device = device;
+    ctx->layout = layout;
+    ctx->input_src = input_src;
+    cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
+    ctx->inst.resize(n_instances);
+    for (auto &I : ctx->inst) {
+        cudaError_t e = cudaStreamCreateWithFlags(&I.stream, cudaStreamNonBlocking);
+        for (int m = 0; m < 4 && e == cudaSuccess; ++m) e = cudaEventCreate(&I.marks[m]);
+        if (e == cudaSuccess) e = cudaMalloc(&I.d_sum, sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaMalloc(&I.d_check, sizeof(double));
+        if (e == cudaSuccess) e = cudaMallocHost(&I.h_sum, sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaMallocHost(&I.h_check, sizeof(double));
+        if (e != cudaSuccess) {
+            fail(nullptr, PLF_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(e));
+            plf_ctx_destroy(ctx);
+            return PLF_ERR_CUDA;
+        }
+        *I.h_sum = 0;
+        *I.h_check = 0.0;
+    }
+    if (input_src == PLF_INPUT_GEN) {
+        rc = gen_pattern_device(nullptr, &ctx->d_gen);
+        if (rc != PLF_OK) {
+            plf_ctx_destroy(ctx);
+            return rc;
+        }
+    }
+    *out = ctx;
+    return PLF_OK;
+}
+
+int plf_ctx_destroy(plf_ctx *ctx)
+{
+    if (!ctx) return PLF_OK;
+    cudaSetDevice(ctx->device);
+    for (auto &I : ctx->inst) {
+        if (I.stream) cudaStreamSynchronize(I.stream);
+        free_instance(I);
+        cudaFree(I.d_sum);
+        cudaFree(I.d_check);
+        if (I.h_sum) cudaFreeHost(I.h_sum);
+        if (I.h_check) cudaFreeHost(I.h_check);
+        for (auto &m : I.marks)
+            if (m) cudaEventDestroy(m);
+        if (I.stream) cudaStreamDestroy(I.stream);
+    }
+    delete ctx;
+    return PLF_OK;
+}
+
+int plf_ctx_set_math(plf_ctx *ctx, int math_mode)
+{
+    if (!ctx) return fail(nullptr, PLF_ERR_INVALID, "NULL context");
+    if (math_mode != PLF_MATH_STRICT && math_mode != PLF_MATH_FMA)
+        return fail(ctx, PLF_ERR_INVALID, "unknown math mode %d", math_mode);
+    ctx->math = math_mode;
+    return PLF_OK;
+}
+
+int plf_ctx_set_gen_sink(plf_ctx *ctx, int sink)
+{
+    if (!ctx) return fail(nullptr, PLF_ERR_INVALID, "NULL context");
+    if (sink != PLF_GEN_WRITE && sink != PLF_GEN_DISCARD)
+        return fail(ctx, PLF_ERR_INVALID, "unknown gen sink %d", sink);
+    ctx->gen_sink = sink;
+    return PLF_OK;
+}
+
+int plf_ctx_set_tuning(plf_ctx *ctx, int variant, int threads_per_block, int blocks_per_sm)
+{
+    if (!ctx) return fail(nullptr, PLF_ERR_INVALID, "NULL context");
+    const int v = variant ? variant : kDefaultVariant;
+    const int t = threads_per_block ? threads_per_block : kDefaultThreads;
+    if (!pick_kernel(PLF_MATH_STRICT, v, t).fn)
+        return fail(ctx, PLF_ERR_INVALID, "unknown kernel variant %d / threads %d", variant,
+                    threads_per_block);
+    if (blocks_per_sm < 0 || blocks_per_sm > 32)
+        return fail(ctx, PLF_ERR_INVALID, "blocks_per_sm %d out of range", blocks_per_sm);
+    ctx->variant = variant;
+    ctx->threads = threads_per_block;
+    ctx->blocks_per_sm = blocks_per_sm;
+    return PLF_OK;
+}
+
+unsigned plf_ctx_instances(const plf_ctx *ctx) { return ctx ? (unsigned)ctx->inst.size() : 0u; }
+
+int plf_instance_alloc(plf_ctx *ctx, unsigned inst, size_t max_sites)
+{
+    Instance *I = nullptr;
+    int rc = check_inst(ctx, inst, false, &I);
+    if (rc != PLF_OK) return rc;
+    if (max_sites == 0) return fail(ctx, PLF_ERR_INVALID, "max_sites must be > 0");
+    if (max_sites > (SIZE_MAX / 64) - 2) return fail(ctx, PLF_ERR_INVALID, "max_sites too large");
+    PLF_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (I->allocated) {
+        PLF_CUDA(ctx, cudaStreamSynchronize(I->stream));
+        free_instance(*I);
+    }
+    const size_t clv = max_sites * PLF_SITE_FLOATS * sizeof(float);
+    cudaError_t e = cudaSuccess;
+    if (ctx->input_src == PLF_INPUT_MEM) {
+        e = cudaMalloc(&I->d_left, PLF_HEADER_COMB * sizeof(float) + clv);
+        if (e == cudaSuccess) e = cudaMalloc(&I->d_right, right_header(ctx) * sizeof(float) + clv);
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&I->d_out, clv);
+    if (e == cudaSuccess) e = cudaMalloc(&I->d_scaler, max_sites);
+    if (e != cudaSuccess) {
+        free_instance(*I);
+        cudaGetLastError();
+        return fail(ctx, e == cudaErrorMemoryAllocation ? PLF_ERR_NOMEM : PLF_ERR_CUDA,
+                    "instance %u: device allocation for %zu sites failed: %s", inst, max_sites,
+                    cudaGetErrorString(e));
+    }
+    I->max_sites = max_sites;
+    I->allocated = true;
+    return PLF_OK;
+}
+
+int plf_instance_free(plf_ctx *ctx, unsigned inst)
+{
+    Instance *I = nullptr;
+    int rc = check_inst(ctx, inst, false, &I);
+    if (rc != PLF_OK) return rc;
+    PLF_CUDA(ctx, cudaSetDevice(ctx->device));
+    PLF_CUDA(ctx, cudaStreamSynchronize(I->stream));
+    free_instance(*I);
+    return PLF_OK;
+}
+
+static int write_packed(plf_ctx *ctx, unsigned inst, bool left, const float *src, size_t bytes,
+                        size_t offset)
+{
+    Instance *I = nullptr;
+    int rc = check_inst(ctx, inst, true, &I);
+    if (rc != PLF_OK) return rc;
+    if (ctx->input_src != PLF_INPUT_MEM)
+        return fail(ctx, PLF_ERR_STATE, "INPUT_SRC=gen instances have no input buffers");
+    if (bytes == 0) return PLF_OK;
+    if (!src) return fail(ctx, PLF_ERR_INVALID, "NULL host buffer");
+    const size_t header = left ? PLF_HEADER_COMB : right_header(ctx);
+    const size_t cap = (header + I->max_sites * PLF_SITE_FLOATS) * sizeof(float);
+    if (offset > cap || bytes > cap - offset)
+        return fail(ctx, PLF_ERR_INVALID, "write of %zu bytes at offset %zu exceeds the %s buffer (%zu bytes)",
+                    bytes, offset, left ? "left" : "right", cap);
+    PLF_CUDA(ctx, cudaSetDevice(ctx->device));
+    char *dst = reinterpret_cast<char *>(left ? I->d_left : I->d_right) + offset;
+    PLF_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, I->stream));
+    return PLF_OK;
+}
+
+int plf_write_left(plf_ctx *ctx, unsigned inst, const float *packed, size_t bytes, size_t offset)
+{
+    return write_packed(ctx, inst, true, packed, bytes, offset);
+}
+
+int plf_write_right(plf_ctx *ctx, unsigned inst, const float *packed, size_t bytes, size_t offset)
+{
+    return write_packed(ctx, inst, false, packed, bytes, offset);
+}
+
+int plf_write_wgt(plf_ctx *ctx, unsigned inst, const int *wgt, size_t count)
+{
+    Instance *I = nullptr;
+    int rc = check_inst(ctx, inst, true, &I);
+    if (rc != PLF_OK) return rc;
+    if (!wgt) {
+        I->use_wgt = false;
+        return PLF_OK;
+    }
+    if (count > I->max_sites)
+        return fail(ctx, PLF_ERR_INVALID, "%zu weights exceed the instance capacity of %zu sites", count,
+                    I->max_sites);
+    PLF_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!I->d_wgt) PLF_CUDA(ctx, cudaMalloc(&I->d_wgt, I->max_sites * sizeof(int)));
+    PLF_CUDA(ctx, cudaMemcpyAsync(I->d_wgt, wgt, count * sizeof(int), cudaMemcpyHostToDevice, I->stream));
+    I->use_wgt = true;
+    return PLF_OK;
+}
+
+int plf_run_async(plf_ctx *ctx, unsigned inst, size_t sites)
+{
+    Instance *I = nullptr;
+    int rc = check_inst(ctx, inst, true, &I);
+    if (rc != PLF_OK) return rc;
+    if (sites > I->max_sites)
+        return fail(ctx, PLF_ERR_INVALID, "run of %zu sites exceeds the instance capacity of %zu", sites,
+                    I->max_sites);
+    PLF_CUDA(ctx, cudaSetDevice(ctx->device));
+    PLF_CUDA(ctx, cudaMemsetAsync(I->d_sum, 0, sizeof(unsigned long long), I->stream));
+    plf_launch_opts opts;
+    opts.math_mode = ctx->math;
+    opts.variant = ctx->variant;
+    opts.threads_per_block = ctx->threads;
+    opts.blocks_per_sm = ctx->blocks_per_sm;
+    opts.ev_per_category = 0;
+    if (ctx->input_src == PLF_INPUT_MEM) {
+        const float *ev = I->d_left;                                   // mem[0]
+        const float *pl = I->d_left + PLF_EV_FLOATS;                   // mem[1..4]
+        const float *x1 = I->d_left + PLF_HEADER_COMB;                 // mem[5+i]
+        const float *pr = ctx->layout == PLF_LAYOUT_COMB ? I->d_right + PLF_EV_FLOATS : I->d_right;
+        const float *x2 = I->d_right + right_header(ctx);
+        rc = launch_newview(ctx, x1, x2, I->d_out, I->d_scaler, ev, pl, pr,
+                            I->use_wgt ? I->d_wgt : nullptr, sites, I->d_sum, &opts, I->stream);
+    } else {
+        PLF_CUDA(ctx, cudaMemsetAsync(I->d_check, 0, sizeof(double), I->stream));
+        rc = launch_gen(ctx, I->d_out, I->d_scaler, ctx->d_gen, sites, I->d_sum, I->d_check,
+                        ctx->gen_sink, &opts, I->stream);
+        if (rc == PLF_OK)
+            PLF_CUDA(ctx, cudaMemcpyAsync(I->h_check, I->d_check, sizeof(double), cudaMemcpyDeviceToHost,
+                                          I->stream));
+    }
+    if (rc != PLF_OK) return rc;
+    PLF_CUDA(ctx, cudaMemcpyAsync(I->h_sum, I->d_sum, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                  I->stream));
+    return PLF_OK;
+}
+
+int plf_wait(plf_ctx *ctx, unsigned inst)
+{
+    Instance *I = nullptr;
+    int rc = check_inst(ctx, inst, false, &I);
+    if (rc != PLF_OK) return rc;
+    PLF_CUDA(ctx, cudaSetDevice(ctx->device));
+    PLF_CUDA(ctx, cudaStreamSynchronize(I->stream));
+    return PLF_OK;
+}
+
+int plf_read_out(plf_ctx *ctx, unsigned inst, float *dst, size_t bytes, size_t offset)
+{
+    Instance *I = nullptr;
+    int rc = check_inst(ctx, inst, true, &I);
+    if (rc != PLF_OK) return rc;
+    if (bytes == 0) return PLF_OK;
+    if (!dst) return fail(ctx, PLF_ERR_INVALID, "NULL host buffer");
+    const size_t cap = I->max_sites * PLF_SITE_FLOATS * sizeof(float);
+    if (offset > cap || bytes > cap - offset)
+        return fail(ctx, PLF_ERR_INVALID, "read of %zu bytes at offset %zu exceeds the out buffer (%zu bytes)",
+                    bytes, offset, cap);
+    PLF_CUDA(ctx, cudaSetDevice(ctx->device));
+    PLF_CUDA(ctx, cudaMemcpyAsync(dst, reinterpret_cast<char *>(I->d_out) + offset, bytes,
+                                  cudaMemcpyDeviceToHost, I->stream));
+    return PLF_OK;
+}
+
+int plf_read_scaler(plf_ctx *ctx, unsigned inst, char *dst, size_t bytes, size_t offset)
+{
+    Instance *I = nullptr;
+    int rc = check_inst(ctx, inst, true, &I);
+    if (rc != PLF_OK) return rc;
+    if (bytes == 0) return PLF_OK;
+    if (!dst) return fail(ctx, PLF_ERR_INVALID, "NULL host buffer");
+    if (offset > I->max_sites || bytes > I->max_sites - offset)
+        return fail(ctx, PLF_ERR_INVALID, "read of %zu bytes at offset %zu exceeds the scaler buffer (%zu bytes)",
+                    bytes, offset, I->max_sites);
+    PLF_CUDA(ctx, cudaSetDevice(ctx->device));
+    PLF_CUDA(ctx, cudaMemcpyAsync(dst, I->d_scaler + offset, bytes, cudaMemcpyDeviceToHost, I->stream));
+    return PLF_OK;
+}
+
+int plf_scaler_increment(plf_ctx *ctx, unsigned inst, long long *increment)
+{
+    Instance *I = nullptr;
+    int rc = check_inst(ctx, inst, false, &I);
+    if (rc != PLF_OK) return rc;
+    if (!increment) return fail(ctx, PLF_ERR_INVALID, "NULL increment");
+    rc = plf_wait(ctx, inst);
+    if (rc != PLF_OK) return rc;
+    *increment = (long long)*I->h_sum;
+    return PLF_OK;
+}
+
+int plf_gen_checksum(plf_ctx *ctx, unsigned inst, double *checksum)
+{
+    Instance *I = nullptr;
+    int rc = check_inst(ctx, inst, false, &I);
+    if (rc != PLF_OK) return rc;
+    if (!checksum) return fail(ctx, PLF_ERR_INVALID, "NULL checksum");
+    rc = plf_wait(ctx, inst);
+    if (rc != PLF_OK) return rc;
+    *checksum = *I->h_check;
+    return PLF_OK;
+}
+
+int plf_mark(plf_ctx *ctx, unsigned inst, int mark_id)
+{
+    Instance *I = nullptr;
+    int rc = check_inst(ctx, inst, false, &I);
+    if (rc != PLF_OK) return rc;
+    if (mark_id < 0 || mark_id > 3) return fail(ctx, PLF_ERR_INVALID, "mark id %d out of range", mark_id);
+    PLF_CUDA(ctx, cudaSetDevice(ctx->device));
+    PLF_CUDA(ctx, cudaEventRecord(I->marks[mark_id], I->stream));
+    I->mark_set[mark_id] = true;
+    return PLF_OK;
+}
+
+int plf_elapsed_ms(plf_ctx *ctx, unsigned inst, int from_mark, int to_mark, float *ms)
+{
+    Instance *I = nullptr;
+    int rc = check_inst(ctx, inst, false, &I);
+    if (rc != PLF_OK) return rc;
+    if (from_mark < 0 || from_mark > 3 || to_mark < 0 || to_mark > 3 || !ms)
+        return fail(ctx, PLF_ERR_INVALID, "bad mark ids %d..%d", from_mark, to_mark);
+    if (!I->mark_set[from_mark] || !I->mark_set[to_mark])
+        return fail(ctx, PLF_ERR_STATE, "mark %d or %d was never recorded", from_mark, to_mark);
+    PLF_CUDA(ctx, cudaSetDevice(ctx->device));
+    PLF_CUDA(ctx, cudaEventSynchronize(I->marks[to_mark]));
+    PLF_CUDA(ctx, cudaEventElapsedTime(ms, I->marks[from_mark], I->marks[to_mark]));
+    return PLF_OK;
+}
+
+int plf_instance_device_ptrs(plf_ctx *ctx, unsigned inst, float **left, float **right, float **out,
+                             unsigned char **scaler)
+{
+    Instance *I = nullptr;
+    int rc = check_inst(ctx, inst, true, &I);
+    if (rc != PLF_OK) return rc;
+    if (left) *left = I->d_left;
+    if (right) *right = I->d_right;
+    if (out) *out = I->d_out;
+    if (scaler) *scaler = I->d_scaler;
+    return PLF_OK;
+}
+
+int plf_instance_stream(plf_ctx *ctx, unsigned inst, void **stream)
+{
+    Instance *I = nullptr;
+    int rc = check_inst(ctx, inst, false, &I);
+    if (rc != PLF_OK) return rc;
+    if (!stream) return fail(ctx, PLF_ERR_INVALID, "NULL stream out-pointer");
+    *stream = I->stream;
+    return PLF_OK;
+}
+
+int plf_host_alloc(void **ptr, size_t bytes)
+{
+    if (!ptr) return fail(nullptr, PLF_ERR_INVALID, "NULL out-pointer");
+    *ptr = nullptr;
+    cudaError_t e = cudaMallocHost(ptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, PLF_ERR_NOMEM, "cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    }
+    return PLF_OK;
+}
+
+int plf_host_free(void *ptr)
+{
+    if (!ptr) return PLF_OK;
+    PLF_CUDA(nullptr, cudaFreeHost(ptr));
+    return PLF_OK;
+}
+
+int plf_host_register(void *ptr, size_t bytes)
+{
+    if (!ptr || !bytes) return fail(nullptr, PLF_ERR_INVALID, "NULL or empty range");
+    PLF_CUDA(nullptr, cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+    return PLF_OK;
+}
+
+int plf_host_unregister(void *ptr)
+{
+    if (!ptr) return PLF_OK;
+    PLF_CUDA(nullptr, cudaHostUnregister(ptr));
+    return PLF_OK;
+}
+
+int plf_newview_device(const float *x1, const float *x2, float *x3, unsigned char *scaler,
+                       const float *ev, const float *p_left, const float *p_right, const int *wgt,
+                       size_t n, unsigned long long *scaler_sum, const plf_launch_opts *opts,
+                       void *stream)
+{
+    return launch_newview(nullptr, x1, x2, x3, scaler, ev, p_left, p_right, wgt, n, scaler_sum, opts,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int plf_newview_gen_device(float *x3, unsigned char *scaler, size_t n, unsigned long long *scaler_sum,
+                           double *checksum, int sink, const plf_launch_opts *opts, void *stream)
+{
+    float *d_gen = nullptr;
+    int rc = gen_pattern_device(nullptr, &d_gen);
+    if (rc != PLF_OK) return rc;
+    return launch_gen(nullptr, x3, scaler, d_gen, n, scaler_sum, checksum, sink, opts,
+                      static_cast<cudaStream_t>(stream));
+}
+
+int plf_gen_pattern(float *x1, float *x2, float *ev4, float *p_left, float *p_right)
+{
+    if (!x1 || !x2 || !ev4 || !p_left || !p_right) return fail(nullptr, PLF_ERR_INVALID, "NULL argument");
+    build_gen_pattern(x1, x2, ev4, p_left, p_right);
+    return PLF_OK;
+}
+
+int plf_generate_device(float *x1, float *x2, size_t first_site, size_t n, uint64_t seed, void *stream)
+{
+    if (n == 0) return PLF_OK;
+    if (!x1 || !x2 || (((uintptr_t)x1 | (uintptr_t)x2) & 15u))
+        return fail(nullptr, PLF_ERR_INVALID, "generate: x1/x2 must be 16-byte aligned device pointers");
+    int sms = 0;
+    if (device_sms(&sms) != 0) return fail(nullptr, PLF_ERR_CUDA, "no CUDA device");
+    const size_t n_vec4 = n * 4;
+    size_t grid = (n_vec4 + 255) / 256;
+    if (grid > (size_t)sms * 8) grid = (size_t)sms * 8;
+    plf::plf_generate_kernel<<<(int)grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<float4 *>(x1), reinterpret_cast<float4 *>(x2), (uint64_t)first_site * 16u,
+        n_vec4, seed);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    PLF_CUDA(nullptr, cudaGetLastError());
+    return PLF_OK;
+}
+
+int plf_generate_host(float *x1, float *x2, size_t first_site, size_t n, uint64_t seed)
+{
+    if (!x1 || !x2) return fail(nullptr, PLF_ERR_INVALID, "NULL argument");
+    for (size_t e = 0; e < n * 16; ++e)
+        plf::gen_pair(seed, (uint64_t)first_site * 16u + e, x1[e], x2[e]);
+    return PLF_OK;
+}
+
+int plf_kernel_info(int variant, int math_mode, int *regs_per_thread, int *threads_per_block,
+                    int *blocks_per_sm, int *num_sms)
+{
+    const int v = variant ? variant : kDefaultVariant;
+    const int t = threads_per_block && *threads_per_block ? *threads_per_block : kDefaultThreads;
+    KernelSel k = pick_kernel(math_mode, v, t);
+    if (!k.fn) return fail(nullptr, PLF_ERR_INVALID, "unknown kernel variant %d / threads %d", variant, t);
+    cudaFuncAttributes attr;
+    PLF_CUDA(nullptr, cudaFuncGetAttributes(&attr, k.fn));
+    int rc = prepare_kernel(nullptr, k);
+    if (rc != PLF_OK) return rc;
+    if (regs_per_thread) *regs_per_thread = attr.numRegs;
+    if (threads_per_block) *threads_per_block = k.threads;
+    if (blocks_per_sm)
+        PLF_CUDA(nullptr, cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k.fn, k.threads, k.smem));
+    if (num_sms && device_sms(num_sms) != 0) return fail(nullptr, PLF_ERR_CUDA, "no CUDA device");
+    return PLF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,528 @@
+// csrc/plf_kernels.cuh -- the fused PLF "newview" kernels for sm_100a (B200).
+//
+// One kernel replaces the reference's whole device pipeline
+//   mm2sleft / mm2sright  (hls/src/mm2s{left,right}_memDNAwindowComb.cpp:16-100)  DDR -> 4 lanes
+//   transpose             (hls/src/transpose.cpp:6-24)                            P -> P^T
+//   mmul_branch x8        (aie/src/128x9DNAwindow8192Comb/kernels/mmul_branch.cpp:6-41)
+//   combine x4            (.../kernels/combine.cpp:4-39)
+//   ev x4                 (.../kernels/ev.cpp:4-27)
+//   s2mm                  (hls/src/s2mm_memDNAwindowComb.cpp:20-101)              rescale + scaler byte
+//   host scaler reduction (app/src/host_mem.cpp:384-388)
+// and computes exactly what the CPU golden plf() computes (app/src/plf.cpp:19-65).
+//
+// Mapping: one thread per (site, rate category) -- the reference's "lane" (one 128-bit PLIO stream
+// per category, mm2sleft_memDNAwindowComb.cpp:88-96).  A warp covers 8 consecutive sites per
+// 128-bit load instruction, so every warp-level request is 512 contiguous bytes.  The category's
+// two 4x4 P matrices and its EV matrix (48 floats) live in registers for the whole kernel.
+// The kernel is HBM-bound (193 B and ~400 flop per site): tensor cores are deliberately unused.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace plf {
+
+constexpr float kMinLikelihood = 0x1p-32f;   // plf.cpp:5-6 (exact in fp32)
+constexpr float kTwoToThe32 = 0x1p+32f;      // plf.cpp:5
+
+// ---------------------------------------------------------------------------------------------
+// Arithmetic policies.
+// STRICT reproduces the reference's rounding: each product and each sum is rounded to fp32
+// separately, sums run left to right from +0.0f (plf.cpp:32-39, 45-50).  __fmul_rn/__fadd_rn are
+// never contracted into FMA by nvcc.  FMA is the contracted variant (<= 1e-5 relative).
+// ---------------------------------------------------------------------------------------------
+struct MathStrict {
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    // ((((+0 + a0*b0) + a1*b1) + a2*b2) + a3*b3)
+    static __device__ __forceinline__ float dot4(float a0, float a1, float a2, float a3,
+                                                 float b0, float b1, float b2, float b3)
+    {
+        float acc = __fadd_rn(0.0f, __fmul_rn(a0, b0));   // keeps -0.0 -> +0.0 of the reference
+        acc = __fadd_rn(acc, __fmul_rn(a1, b1));
+        acc = __fadd_rn(acc, __fmul_rn(a2, b2));
+        acc = __fadd_rn(acc, __fmul_rn(a3, b3));
+        return acc;
+    }
+};
+
+struct MathFma {
+    static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
+    static __device__ __forceinline__ float dot4(float a0, float a1, float a2, float a3,
+                                                 float b0, float b1, float b2, float b3)
+    {
+        float acc = a0 * b0;
+        acc = __fmaf_rn(a1, b1, acc);
+        acc = __fmaf_rn(a2, b2, acc);
+        acc = __fmaf_rn(a3, b3, acc);
+        return acc;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Memory access policies: streaming 128-bit loads/stores.  CLVs are touched exactly once, so
+// loads bypass L1 allocation and stores are marked streaming.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld_stream(const float4 *p)
+{
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream(float4 *p, const float4 &v)
+{
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 ld_plain(const float4 *p) { return *p; }
+__device__ __forceinline__ void st_plain(float4 *p, const float4 &v) { *p = v; }
+
+// The 48 per-category constants: P_left[j], P_right[j] as [k][l], EV (or EV4[j]) as [k][l].
+struct CatConst {
+    float L[16];
+    float R[16];
+    float E[16];
+};
+
+__device__ __forceinline__ void load_cat_const(CatConst &c, const float *__restrict__ ev,
+                                               const float *__restrict__ pl,
+                                               const float *__restrict__ pr, int cat,
+                                               int ev_per_category)
+{
+    const float4 *l4 = reinterpret_cast<const float4 *>(pl) + 4 * cat;
+    const float4 *r4 = reinterpret_cast<const float4 *>(pr) + 4 * cat;
+    const float4 *e4 = reinterpret_cast<const float4 *>(ev) + (ev_per_category ? 4 * cat : 0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float4 a = __ldg(l4 + k), b = __ldg(r4 + k), e = __ldg(e4 + k);
+        c.L[4 * k + 0] = a.x; c.L[4 * k + 1] = a.y; c.L[4 * k + 2] = a.z; c.L[4 * k + 3] = a.w;
+        c.R[4 * k + 0] = b.x; c.R[4 * k + 1] = b.y; c.R[4 * k + 2] = b.z; c.R[4 * k + 3] = b.w;
+        c.E[4 * k + 0] = e.x; c.E[4 * k + 1] = e.y; c.E[4 * k + 2] = e.z; c.E[4 * k + 3] = e.w;
+    }
+}
+
+// One (site, category): a = P_l x1, b = P_r x2 (plf.cpp:29-39), p = a.b (:41),
+// x3[l] = sum_k p[k] EV[k][l] (:45-50).  Returns true when all four |x3| < 2^-32 (:53-56).
+template <class M>
+__device__ __forceinline__ bool category_newview(const CatConst &c, const float4 &u, const float4 &v,
+                                                 float4 &o)
+{
+    float p[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float a = M::dot4(u.x, u.y, u.z, u.w, c.L[4 * k], c.L[4 * k + 1], c.L[4 * k + 2], c.L[4 * k + 3]);
+        float b = M::dot4(v.x, v.y, v.z, v.w, c.R[4 * k], c.R[4 * k + 1], c.R[4 * k + 2], c.R[4 * k + 3]);
+        p[k] = M::mul(a, b);
+    }
+    o.x = M::dot4(p[0], p[1], p[2], p[3], c.E[0], c.E[4], c.E[8], c.E[12]);
+    o.y = M::dot4(p[0], p[1], p[2], p[3], c.E[1], c.E[5], c.E[9], c.E[13]);
+    o.z = M::dot4(p[0], p[1], p[2], p[3], c.E[2], c.E[6], c.E[10], c.E[14]);
+    o.w = M::dot4(p[0], p[1], p[2], p[3], c.E[3], c.E[7], c.E[11], c.E[15]);
+    // NaN compares false, exactly like ABS(x) < minlikelihood on the CPU.
+    return (fabsf(o.x) < kMinLikelihood) & (fabsf(o.y) < kMinLikelihood) &
+           (fabsf(o.z) < kMinLikelihood) & (fabsf(o.w) < kMinLikelihood);
+}
+
+__device__ __forceinline__ void rescale(float4 &o)
+{
+    o.x = __fmul_rn(o.x, kTwoToThe32);   // exact: power-of-two scale of a value < 2^-32
+    o.y = __fmul_rn(o.y, kTwoToThe32);
+    o.z = __fmul_rn(o.z, kTwoToThe32);
+    o.w = __fmul_rn(o.w, kTwoToThe32);
+}
+
+// Site s of a warp tile occupies lanes 4s..4s+3: the site rescales when its whole nibble is set.
+__device__ __forceinline__ bool nibble_all(unsigned ballot, int site_in_warp)
+{
+    return ((ballot >> (4 * site_in_warp)) & 0xFu) == 0xFu;
+}
+
+// Block-wide sum of per-thread counters -> one atomic per block (host_mem.cpp:384-388 fused).
+template <int THREADS>
+__device__ __forceinline__ void block_add_u64(unsigned long long v, unsigned long long *dst)
+{
+    __shared__ unsigned long long warp_sums[THREADS / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        unsigned long long t = threadIdx.x < THREADS / 32 ? warp_sums[threadIdx.x] : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0 && t != 0ull) atomicAdd(dst, t);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Variant 1 ("ldg"): persistent grid-stride kernel, register-staged.
+//   U      : 128-bit loads per child per thread per tile; a warp tile is 8*U sites.
+//   STREAM : use the streaming load/store policies above.
+// Per tile each thread issues 2*U independent 128-bit loads before the first use (memory-level
+// parallelism), computes U (site,category) results, votes per site with one ballot per load
+// row, stores U 128-bit results and lanes 0..8U-1 store one scaler byte each (one contiguous
+// 8U-byte run per warp).
+// ---------------------------------------------------------------------------------------------
+template <class M, int U, bool STREAM, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+plf_newview_ldg(const float4 *__restrict__ x1, const float4 *__restrict__ x2,
+                float4 *__restrict__ x3, unsigned char *__restrict__ scaler,
+                const float *__restrict__ ev, const float *__restrict__ pl,
+                const float *__restrict__ pr, const int *__restrict__ wgt, size_t n,
+                unsigned long long *__restrict__ scaler_sum, int ev_per_category)
+{
+    constexpr int TILE = 8 * U;                       // sites per warp tile
+    const int lane = threadIdx.x & 31;
+    const int cat = lane & 3;
+    const int site_in_row = lane >> 2;                // 0..7
+
+    CatConst c;
+    load_cat_const(c, ev, pl, pr, cat, ev_per_category);
+
+    const size_t warps_total = (size_t)gridDim.x * (THREADS / 32);
+    const size_t warp_id = (size_t)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
+    const size_t n_tiles = (n + TILE - 1) / TILE;
+    unsigned long long my_sum = 0;
+
+    for (size_t tile = warp_id; tile < n_tiles; tile += warps_total) {
+        const size_t s0 = tile * TILE;
+        const bool full = s0 + TILE <= n;
+        float4 a[U], b[U], o[U];
+        unsigned ballots[U];
+
+        if (full) {
+            const float4 *p1 = x1 + s0 * 4 + lane;
+            const float4 *p2 = x2 + s0 * 4 + lane;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                a[u] = STREAM ? ld_stream(p1 + 32 * u) : ld_plain(p1 + 32 * u);
+                b[u] = STREAM ? ld_stream(p2 + 32 * u) : ld_plain(p2 + 32 * u);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                bool small = category_newview<M>(c, a[u], b[u], o[u]);
+                ballots[u] = __ballot_sync(0xffffffffu, small);
+                if (nibble_all(ballots[u], site_in_row)) rescale(o[u]);
+            }
+            float4 *p3 = x3 + s0 * 4 + lane;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (STREAM) st_stream(p3 + 32 * u, o[u]); else st_plain(p3 + 32 * u, o[u]);
+            }
+        } else {
+            // ragged last tile: same code, predicated per load row
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const size_t s = s0 + 8 * u + site_in_row;
+                const bool live = s < n;
+                a[u] = live ? x1[s * 4 + cat] : make_float4(1.f, 1.f, 1.f, 1.f);
+                b[u] = live ? x2[s * 4 + cat] : make_float4(1.f, 1.f, 1.f, 1.f);
+                bool small = category_newview<M>(c, a[u], b[u], o[u]);
+                ballots[u] = __ballot_sync(0xffffffffu, small && live);
+                if (nibble_all(ballots[u], site_in_row)) rescale(o[u]);
+                if (live) x3[s * 4 + cat] = o[u];
+            }
+        }
+
+        // scaler bytes + weighted count: lane L owns site s0+L of the tile
+        if (lane < TILE) {
+            unsigned bal = ballots[0];
+#pragma unroll
+            for (int u = 1; u < U; ++u) bal = (lane >> 3) == u ? ballots[u] : bal;
+            const bool scaled = nibble_all(bal, lane & 7);
+            const size_t s = s0 + lane;
+            if (s < n) {
+                if (scaler) scaler[s] = scaled ? 1 : 0;
+                if (scaled) my_sum += wgt ? (unsigned long long)(long long)wgt[s] : 1ull;
+            }
+        }
+    }
+    if (scaler_sum) block_add_u64<THREADS>(my_sum, scaler_sum);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Variant 2 ("tma"): warp-specialised, shared-memory staged with the bulk-copy engine.
+//
+//   producer warp (1 elected lane): cp.async.bulk global -> shared (TMA bulk copy, SASS UBLKCP)
+//       of one STAGE = WARPS*8*U consecutive sites of x1 and of x2, completion counted on an
+//       mbarrier (complete_tx::bytes); DEPTH stages form a ring, so up to DEPTH*STAGE*128 bytes
+//       are in flight per CTA without holding a single register.
+//   consumer warps: wait on the stage's "full" mbarrier, read their float4 with conflict-free
+//       LDS.128 (lane i reads bytes 16i..16i+15 of a 512-byte row), compute, vote, rescale and
+//       store x3 / scaler bytes straight to global memory with 128-bit streaming stores, then
+//       release the stage through its "empty" mbarrier.
+// The ring decouples memory-level parallelism from occupancy: the 48 matrix constants per thread
+// cost registers, not bytes in flight.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}"
+        :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy; bytes must be a multiple of 16, both addresses 16-byte aligned.
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes,
+                                         uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <class M, int U, int WARPS, int DEPTH, int MINB>
+__global__ void __launch_bounds__((WARPS + 1) * 32, MINB)
+plf_newview_tma(const float4 *__restrict__ x1, const float4 *__restrict__ x2,
+                float4 *__restrict__ x3, unsigned char *__restrict__ scaler,
+                const float *__restrict__ ev, const float *__restrict__ pl,
+                const float *__restrict__ pr, const int *__restrict__ wgt, size_t n,
+                unsigned long long *__restrict__ scaler_sum, int ev_per_category)
+{
+    constexpr int THREADS = (WARPS + 1) * 32;
+    constexpr int TILE = 8 * U;                 // sites per consumer warp per stage
+    constexpr int STAGE = WARPS * TILE;         // sites per stage
+    constexpr int STAGE_F4 = STAGE * 4;         // float4 per child per stage
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4 *s1 = reinterpret_cast<float4 *>(smem_raw);                 // [DEPTH][STAGE_F4]
+    float4 *s2 = s1 + (size_t)DEPTH * STAGE_F4;                        // [DEPTH][STAGE_F4]
+    uint64_t *full = reinterpret_cast<uint64_t *>(s2 + (size_t)DEPTH * STAGE_F4);
+    uint64_t *empty = full + DEPTH;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const size_t n_stages = (n + STAGE - 1) / STAGE;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int d = 0; d < DEPTH; ++d) {
+            mbar_init(&full[d], 1);             // one arrive.expect_tx by the producer
+            mbar_init(&empty[d], WARPS);        // one arrive per consumer warp
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    unsigned long long my_sum = 0;
+
+    if (warp == WARPS) {
+        // ===== producer =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (size_t st = blockIdx.x; st < n_stages; st += gridDim.x, ++it) {
+                const uint32_t slot = it % DEPTH;
+                const uint32_t phase = (it / DEPTH) & 1u;
+                mbar_wait(&empty[slot], phase ^ 1u);
+                const size_t s0 = st * STAGE;
+                const size_t left = n - s0;
+                const uint32_t bytes = (uint32_t)(left < (size_t)STAGE ? left : (size_t)STAGE) * 64u;
+                mbar_arrive_expect_tx(&full[slot], 2u * bytes);
+                bulk_g2s(s1 + (size_t)slot * STAGE_F4, x1 + s0 * 4, bytes, &full[slot]);
+                bulk_g2s(s2 + (size_t)slot * STAGE_F4, x2 + s0 * 4, bytes, &full[slot]);
+            }
+        }
+    } else {
+        // ===== consumers =====
+        const int cat = lane & 3;
+        const int site_in_row = lane >> 2;
+        CatConst c;
+        load_cat_const(c, ev, pl, pr, cat, ev_per_category);
+
+        uint32_t it = 0;
+        for (size_t st = blockIdx.x; st < n_stages; st += gridDim.x, ++it) {
+            const uint32_t slot = it % DEPTH;
+            const uint32_t phase = (it / DEPTH) & 1u;
+            const size_t s0 = st * STAGE + (size_t)warp * TILE;     // first site of this warp's tile
+            const float4 *t1 = s1 + (size_t)slot * STAGE_F4 + warp * (TILE * 4) + lane;
+            const float4 *t2 = s2 + (size_t)slot * STAGE_F4 + warp * (TILE * 4) + lane;
+
+            mbar_wait(&full[slot], phase);
+            float4 a[U], b[U], o[U];
+            unsigned ballots[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                a[u] = t1[32 * u];
+                b[u] = t2[32 * u];
+            }
+            // all of this warp's reads of the slot are done once the values are in registers
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[slot]);
+
+            const bool full_tile = s0 + TILE <= n;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const size_t s = s0 + 8 * u + site_in_row;
+                const bool live = full_tile || s < n;
+                bool small = category_newview<M>(c, a[u], b[u], o[u]);
+                ballots[u] = __ballot_sync(0xffffffffu, small && live);
+                if (nibble_all(ballots[u], site_in_row)) rescale(o[u]);
+                if (live) st_stream(x3 + s * 4 + cat, o[u]);
+            }
+            if (lane < TILE) {
+                unsigned bal = ballots[0];
+#pragma unroll
+                for (int u = 1; u < U; ++u) bal = (lane >> 3) == u ? ballots[u] : bal;
+                const bool scaled = nibble_all(bal, lane & 7);
+                const size_t s = s0 + lane;
+                if (s < n) {
+                    if (scaler) scaler[s] = scaled ? 1 : 0;
+                    if (scaled) my_sum += wgt ? (unsigned long long)(long long)wgt[s] : 1ull;
+                }
+            }
+        }
+    }
+    if (scaler_sum) block_add_u64<THREADS>(my_sum, scaler_sum);
+}
+
+template <int U, int WARPS, int DEPTH>
+constexpr size_t tma_smem_bytes()
+{
+    return (size_t)DEPTH * (WARPS * 8 * U) * 64 * 2 + (size_t)DEPTH * 2 * sizeof(uint64_t);
+}
+
+// ---------------------------------------------------------------------------------------------
+// INPUT_SRC=gen analogue: no CLV is read.  Every lane holds its category's slice of the constant
+// site pattern (mm2sleft_genDNAwindowComb.cpp:44-49 / mm2sright_...:45-50); an opaque register
+// move per site keeps the compiler from hoisting the (site-invariant) arithmetic out of the loop,
+// so the full per-site work is issued exactly as in the MEM kernel.
+//   DISCARD = false : write CLV + scaler (cfg4a)      DISCARD = true : checksum only (cfg4b,
+//   the sink of s2mm_genDNAwindowComb.cpp:15-53 reads the streams and drops them).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void opaque(float4 &v)
+{
+    asm volatile("" : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w));
+}
+
+template <class M, int U, bool DISCARD, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+plf_newview_gen(float4 *__restrict__ x3, unsigned char *__restrict__ scaler,
+                const float *__restrict__ pat_x1, const float *__restrict__ pat_x2,
+                const float *__restrict__ ev4, const float *__restrict__ pl,
+                const float *__restrict__ pr, size_t n,
+                unsigned long long *__restrict__ scaler_sum, double *__restrict__ checksum)
+{
+    constexpr int TILE = 8 * U;
+    const int lane = threadIdx.x & 31;
+    const int cat = lane & 3;
+    const int site_in_row = lane >> 2;
+
+    CatConst c;
+    load_cat_const(c, ev4, pl, pr, cat, 1);
+    float4 g1 = __ldg(reinterpret_cast<const float4 *>(pat_x1) + cat);
+    float4 g2 = __ldg(reinterpret_cast<const float4 *>(pat_x2) + cat);
+
+    const size_t warps_total = (size_t)gridDim.x * (THREADS / 32);
+    const size_t warp_id = (size_t)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
+    const size_t n_tiles = (n + TILE - 1) / TILE;
+    unsigned long long my_sum = 0;
+    double my_check = 0.0;
+
+    for (size_t tile = warp_id; tile < n_tiles; tile += warps_total) {
+        const size_t s0 = tile * TILE;
+        unsigned ballots[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const size_t s = s0 + 8 * u + site_in_row;
+            const bool live = s < n;
+            float4 a = g1, b = g2, o;
+            opaque(a);
+            opaque(b);
+            bool small = category_newview<M>(c, a, b, o);
+            ballots[u] = __ballot_sync(0xffffffffu, small && live);
+            if (nibble_all(ballots[u], site_in_row)) rescale(o);
+            if (DISCARD) {
+                if (live) my_check += (double)((o.x + o.y) + (o.z + o.w));
+            } else if (live) {
+                st_stream(x3 + s * 4 + cat, o);
+            }
+        }
+        if (lane < TILE) {
+            unsigned bal = ballots[0];
+#pragma unroll
+            for (int u = 1; u < U; ++u) bal = (lane >> 3) == u ? ballots[u] : bal;
+            const bool scaled = nibble_all(bal, lane & 7);
+            const size_t s = s0 + lane;
+            if (s < n) {
+                if (!DISCARD && scaler) scaler[s] = scaled ? 1 : 0;
+                if (scaled) my_sum += 1ull;
+            }
+        }
+    }
+    if (scaler_sum) block_add_u64<THREADS>(my_sum, scaler_sum);
+    if (DISCARD && checksum) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) my_check += __shfl_xor_sync(0xffffffffu, my_check, o);
+        if (lane == 0 && my_check != 0.0) atomicAdd(checksum, my_check);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Synthetic stimulus on the device (bench / INPUT generation for GB-scale configs).
+// Counter-based: element e of x1/x2 is a pure function of (seed, global element index), so any
+// site range can be produced independently on any GPU and re-derived on the host for checks.
+// Distribution follows host_mem.cpp:198-204: U(0,1), left CLV of every 4th site times 1e-12f.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x)
+{
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+// 24 random bits -> (0,1): (k + 0.5) / 2^24, exactly representable, never 0 or 1.
+__host__ __device__ __forceinline__ float u01_from_bits(uint32_t r)
+{
+    return ((float)(r >> 8) + 0.5f) * (1.0f / 16777216.0f);
+}
+__host__ __device__ __forceinline__ void gen_pair(uint64_t seed, uint64_t elem, float &l, float &r)
+{
+    const uint64_t h = splitmix64(seed ^ splitmix64(elem));
+    l = u01_from_bits((uint32_t)h);
+    r = u01_from_bits((uint32_t)(h >> 32));
+    if ((elem & 63u) < 16u) l = l * 1.0e-12f;     // j % 64 < 16  (host_mem.cpp:200-202)
+}
+
+__global__ void __launch_bounds__(256)
+plf_generate_kernel(float4 *__restrict__ x1, float4 *__restrict__ x2, uint64_t first_elem,
+                    size_t n_vec4, uint64_t seed)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_vec4; v += stride) {
+        float4 a, b;
+        const uint64_t e = first_elem + 4 * (uint64_t)v;
+        gen_pair(seed, e + 0, a.x, b.x);
+        gen_pair(seed, e + 1, a.y, b.y);
+        gen_pair(seed, e + 2, a.z, b.z);
+        gen_pair(seed, e + 3, a.w, b.w);
+        x1[v] = a;
+        x2[v] = b;
+    }
+}
+
+}  // namespace plf

@@ -1,0 +1,47 @@
+"""Multi-GPU plumbing for the PLF path: site-range sharding and the one optional collective.
+
+Sites are independent, so the path shards with NO steady-state inter-GPU traffic: rank r of W
+owns a contiguous site range chosen by the reference's instance-split rule
+(app/src/include.h:181-192: ceil(n/W) each, the last takes the remainder).  The only exchange is
+the final sum of the per-rank scaler increments (host_mem.cpp:384-388 is the single-device
+version), an all-reduce of one int64 over NCCL (NVLink/NVSwitch) -- or gloo in the CPU tests.
+"""
+from __future__ import annotations
+
+import math
+
+
+def shard_for_rank(n_sites: int, rank: int, world: int):
+    """(first_site, count) of `rank`; count may be 0 when n_sites < world."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    per = math.ceil(n_sites / world)
+    lo = min(rank * per, n_sites)
+    return lo, max(0, min(per, n_sites - lo))
+
+
+def all_shards(n_sites: int, world: int):
+    return [shard_for_rank(n_sites, r, world) for r in range(world)]
+
+
+def reduce_scaler_increment(local_increment: int, device=None, group=None) -> int:
+    """Sum of the per-rank scaler increments.  One int64 all-reduce; identity when
+    torch.distributed is not initialised (single process)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return int(local_increment)
+    t = torch.tensor([int(local_increment)], dtype=torch.int64, device=device or "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return int(t.item())
+
+
+def max_over_ranks(value: float, device=None, group=None) -> float:
+    """Max of a per-rank scalar (device timings are reported as the max over ranks)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device or "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t.item())

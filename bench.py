@@ -1,0 +1,466 @@
+#!/usr/bin/env python
+"""bench.py -- PLF newview throughput on B200 (sites/s, HBM GB/s), next to the reference's CPU path.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm  (N>1: launched by torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU plf()
+
+Workload (config.workload): BASELINE.json configs[2] -- "DNA with 4 rate categories, 64M sites,
+site-partitioned across 1/2/4/8 B200": 64 Mi sites TOTAL, split over the ranks with the reference's
+instance rule (ceil(n/N), last takes the remainder), so scaling is "strong".  A step is one pass
+of the fused newview kernel over the rank's whole site range (one launch).  Inputs (12 GiB/N per
+rank) are far larger than L2, so no flush is needed between steps.
+
+value      device-resident throughput: CUDA events on the launching stream, max over ranks.
+e2e        the same sites through the reference-facing host API (plf_write_left/right -> plf_run_async
+           -> plf_read_out/plf_read_scaler on NUM_ACCELERATORS=9 instances) from PINNED HOST buffers,
+           H2D and D2H copies inside the timed region.
+roofline   193 algorithmic bytes/site x sites per launch / mean launch time, against the measured
+           HBM copy bandwidth in MEASURED_PEAKS.json.
+cpu_baseline  oracle/_ref (the reference's plf.cpp compiled in place) on all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib.util
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+PKG_DIR = os.path.join(ROOT, "amd-versal-phylogenetic-likelihood-function_b200")
+
+TOTAL_SITES = {"cfg3": 64 << 20, "cfg2": 1 << 20}
+WORKLOAD_NAME = {
+    "cfg3": "BASELINE.json configs[2]: DNA, 4 rate categories, 64Mi sites, site-partitioned over N GPUs",
+    "cfg2": "BASELINE.json configs[1]: single PLF instance, DNA, 1Mi sites, 1 GPU",
+}
+BYTES_PER_SITE = 193
+NOMINAL_HBM_GBS = 8000.0
+FALLBACK_HBM_GBS = 6650.0
+SEED = 42
+
+
+def load_pkg():
+    name = "plf_b200"
+    if name in sys.modules:
+        return sys.modules[name]
+    spec = importlib.util.spec_from_file_location(name, os.path.join(PKG_DIR, "__init__.py"),
+                                                  submodule_search_locations=[PKG_DIR])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[name] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU plf() (oracle/_ref), all host threads
+# ---------------------------------------------------------------------------------------------
+def host_inputs_tiled(n_sites: int):
+    """host_mem.cpp:179-209 stimulus for a 1 Mi-site block, tiled to n_sites (content repeats;
+    the CPU path's cost does not depend on it)."""
+    import oracle
+    block = min(n_sites, 1 << 20)
+    ev, left, right, b1, b2, _ = oracle.host_mem_inputs(block, seed=SEED)
+    x1 = np.empty((n_sites, 16), np.float32)
+    x2 = np.empty((n_sites, 16), np.float32)
+    for lo in range(0, n_sites, block):
+        c = min(block, n_sites - lo)
+        x1[lo:lo + c] = b1[:c]
+        x2[lo:lo + c] = b2[:c]
+    return ev, left, right, x1, x2, np.ones(n_sites, np.int32)
+
+
+def cpu_reference_rate(n_sites: int, repeats: int, threads: int):
+    """Best-of-`repeats` sites/s of the reference plf() over n_sites with `threads` threads."""
+    import oracle
+    if oracle.RefOracle.available():
+        ref, kind = oracle.RefOracle(), "reference"
+    else:
+        ref, kind = None, "port"
+        co = oracle.COracle()
+    ev, left, right, x1, x2, wgt = host_inputs_tiled(n_sites)
+    out = np.empty((n_sites, 16), np.float32)
+    times, inc = [], None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        if ref is not None:
+            _, inc = ref.newview(x1, x2, ev, left, right, wgt, nthreads=threads, out=out)
+        else:
+            _, _, inc = co.newview(x1, x2, ev, left, right, wgt, nthreads=threads)
+        times.append(time.perf_counter() - t0)
+    assert inc == (n_sites + 3) // 4, "CPU reference produced an unexpected scaler increment"
+    return kind, times
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = min(TOTAL_SITES[args.workload], 16 << 20)
+    import oracle
+    ref = oracle.RefOracle() if oracle.RefOracle.available() else None
+    kind = "reference" if ref is not None else "port"
+    co = None if ref is not None else oracle.COracle()
+    ev, left, right, x1, x2, wgt = host_inputs_tiled(sample)
+    out = np.empty((sample, 16), np.float32)
+
+    def one_step(m):
+        if ref is not None:
+            ref.newview(x1[:m], x2[:m], ev, left, right, wgt[:m], nthreads=cores, out=out)
+        else:
+            co.newview(x1[:m], x2[:m], ev, left, right, wgt[:m], nthreads=cores)
+
+    for _ in range(args.warmup):
+        one_step(min(sample, 2 << 20))          # warm-up on a prefix: page-in, thread start-up
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        one_step(sample)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    desc = (f"{sample} sites/step of the {TOTAL_SITES[args.workload]}-site workload "
+            f"(host_mem.cpp stimulus, 1Mi-site block tiled), {cores} threads, "
+            f"{'/root/reference/app/src/plf.cpp compiled in place (-O2 -ffp-contract=off)' if kind == 'reference' else 'oracle/plf_oracle.c port'}")
+    line = {
+        "impl": "reference", "metric": "plf_sites_per_s", "value": value, "unit": "sites/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD_NAME[args.workload], "total_sites": TOTAL_SITES[args.workload],
+                   "sample_sites_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": "sites/s", "cores": cores, "kind": kind, "sample": desc},
+        "e2e": {"value": value, "unit": "sites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "hbm_equiv_gbs": value * BYTES_PER_SITE / 1e9,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    pkg = load_pkg()
+    from plf_b200 import sharding
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the PLF path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    if args.gpus != world and rank == 0:
+        print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; using {world}", file=sys.stderr)
+
+    total_sites = args.sites or TOTAL_SITES[args.workload]
+    first, n = sharding.shard_for_rank(total_sites, rank, world)
+    K, W = args.steps, max(args.warmup, 3)
+    math_mode = pkg.MATH_FMA if args.math == "fma" else pkg.MATH_STRICT
+    opts = pkg.make_opts(math_mode, args.variant, args.threads, args.blocks_per_sm)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident leg ("value") ------------------------------------------------------
+    import oracle  # checker only: spot check below + cpu_baseline leg
+    ev, left, right, *_ = oracle.host_mem_inputs(1, seed=SEED)
+    d_ev = torch.from_numpy(ev).to(device)
+    d_pl = torch.from_numpy(left).to(device)
+    d_pr = torch.from_numpy(right).to(device)
+    # cfg2's 192 MiB working set is only ~1.5x L2: rotate buffer sets so every step reads cold data
+    sets = args.buffer_sets if args.buffer_sets > 0 else (1 if n * 128 >= (1 << 30) else 6)
+    x1 = [torch.empty((n, 16), device=device) for _ in range(sets)]
+    x2 = [torch.empty((n, 16), device=device) for _ in range(sets)]
+    x3 = [torch.empty((n, 16), device=device) for _ in range(sets)]
+    sc = [torch.empty(n, dtype=torch.uint8, device=device) for _ in range(sets)]
+    sums = torch.zeros(K + W, dtype=torch.int64, device=device)
+    stream = torch.cuda.current_stream().cuda_stream
+    for s in range(sets):
+        pkg.generate_device(x1[s].data_ptr(), x2[s].data_ptr(), first, n, SEED, stream)
+
+    def step(i):
+        s = i % sets
+        pkg.newview_device(x1[s].data_ptr(), x2[s].data_ptr(), x3[s].data_ptr(), sc[s].data_ptr(),
+                           d_ev.data_ptr(), d_pl.data_ptr(), d_pr.data_ptr(), None, n,
+                           sums[i:].data_ptr(), opts, stream)
+
+    for i in range(W):
+        step(i)
+    barrier()
+    launches0 = pkg.launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    evs[0].record()
+    for i in range(K):
+        step(W + i)
+        evs[i + 1].record()
+    barrier()
+    launches = pkg.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    elapsed_ms = evs[0].elapsed_time(evs[K])
+    per_launch_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(K)]
+    t_max_ms = sharding.max_over_ranks(elapsed_ms, device)
+    launches_all = sharding.reduce_scaler_increment(launches, device)
+
+    # correctness of what was timed: every step produced the designed scaler count, the
+    # NCCL-reduced total matches, and a slice is bit-identical to the oracle.
+    sums_h = sums.cpu().numpy()
+    lo_scaled = (first + 3) // 4
+    expect = (first + n + 3) // 4 - lo_scaled
+    assert (sums_h == expect).all(), f"rank {rank}: scaler sums {sums_h[:4]} != {expect}"
+    total_inc = sharding.reduce_scaler_increment(int(sums_h[-1]), device)
+    assert total_inc == (total_sites + 3) // 4
+    chk = min(n, 2048)
+    h1, h2 = pkg.generate_host(first, chk, SEED)
+    o3, osc, _ = oracle.COracle().newview(h1, h2, ev, left, right)
+    g3 = x3[(W + K - 1) % sets][:chk].cpu().numpy()
+    if math_mode == pkg.MATH_STRICT:
+        assert np.array_equal(g3.view(np.uint32), o3.view(np.uint32)), "bench output != oracle"
+    else:
+        assert np.allclose(g3, o3, rtol=1e-5, atol=0)
+
+    value = total_sites * K / (t_max_ms * 1e-3)
+    mean_launch_ms = statistics.fmean(per_launch_ms)
+    peak, peak_src = measured_peak()
+    achieved = BYTES_PER_SITE * n / (mean_launch_ms * 1e-3) / 1e9
+    traffic = ncu_traffic()
+    info = pkg.kernel_info(args.variant, math_mode, args.threads)
+
+    # ---- end-to-end leg through the host API with pinned host buffers -------------------------
+    del x1, x2, x3, sc
+    torch.cuda.empty_cache()
+    e2e = run_e2e(pkg, torch, args, local_rank, first, n, total_sites, world, math_mode, barrier,
+                  sharding, device, ev, left, right)
+
+    # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        sample = min(total_sites, 16 << 20)
+        kind, times = cpu_reference_rate(sample, 3, cores)
+        _, t1 = cpu_reference_rate(1 << 20, 2, 1)
+        cpu = {"value": sample / min(times), "unit": "sites/s", "cores": cores, "kind": kind,
+               "sample": f"{sample} sites of the workload's stimulus recipe, best of 3, {cores} threads "
+                         "each running the unmodified plf() on a contiguous site range "
+                         "(-O2 -ffp-contract=off)",
+               "single_thread_sites_per_s": (1 << 20) / min(t1)}
+
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        line = {
+            "metric": "plf_sites_per_s", "value": value, "unit": "sites/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": t_max_ms / K, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD_NAME[args.workload], "total_sites": total_sites,
+                       "sites_per_gpu": n, "partition": "contiguous site ranges, ceil(n/N) rule",
+                       "math": args.math, "kernel": info | {"variant": args.variant},
+                       "l2": f"inputs {2 * n * 64 * sets >> 20} MiB per GPU >> 126 MB L2, "
+                             f"{sets} rotating buffer set(s), no flush needed",
+                       "bytes_per_site": BYTES_PER_SITE},
+            "hbm_gbs": value * BYTES_PER_SITE / 1e9,
+            "hbm_gbs_per_gpu": value * BYTES_PER_SITE / 1e9 / world,
+            "frac_of_8TBs_per_gpu": value * BYTES_PER_SITE / 1e9 / world / NOMINAL_HBM_GBS,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+                         "peak_source": peak_src, "launch_ms_mean": mean_launch_ms,
+                         "launch_ms_min": min(per_launch_ms), "launch_ms_max": max(per_launch_ms),
+                         "algorithmic_bytes_per_launch": BYTES_PER_SITE * n,
+                         "traffic_note": (traffic or {}).get("note")},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_all, "clocks": clocks,
+            "scaler_increment": total_inc,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(pkg, torch, args, local_rank, first, n, total_sites, world, math_mode, barrier, sharding,
+            device, ev, left, right):
+    """Host buffers -> plf_write_* -> plf_run_async -> plf_read_* on NUM_ACCELERATORS instances."""
+    inst = args.instances
+    tb = pkg.TestbenchInfo(n, inst)
+    if not tb.valid():
+        inst, tb = 1, pkg.TestbenchInfo(n, 1)
+    e2e_steps = max(2, min(args.steps, args.e2e_steps))
+    bufs, frees = [], []
+
+    def pinned(nbytes, dtype):
+        a, p = pkg.host_alloc(nbytes, dtype)
+        frees.append(p)
+        return a
+
+    ctx = pkg.Context(local_rank, inst, pkg.LAYOUT_COMB, pkg.INPUT_MEM)
+    ctx.set_math(math_mode)
+    ctx.set_tuning(args.variant, args.threads, args.blocks_per_sm)
+    stream0 = torch.cuda.current_stream().cuda_stream
+    header = np.concatenate([ev, left]).astype(np.float32), np.concatenate([ev, right]).astype(np.float32)
+    h2d = d2h = 0
+    for k in range(inst):
+        cnt, lo = tb.alignments_per_instance(k), first + tb.instance_offset(k)
+        lb = pinned((80 + 16 * cnt) * 4, np.float32)
+        rb = pinned((80 + 16 * cnt) * 4, np.float32)
+        out = pinned(16 * cnt * 4, np.float32)
+        scb = pinned(cnt, np.uint8)
+        # stimulus: generated on the device once, copied to the pinned host buffers (setup, untimed)
+        t1 = torch.empty((cnt, 16), device=device)
+        t2 = torch.empty((cnt, 16), device=device)
+        pkg.generate_device(t1.data_ptr(), t2.data_ptr(), lo, cnt, SEED, stream0)
+        torch.cuda.synchronize()
+        lb[:80], rb[:80] = header
+        torch.from_numpy(lb[80:]).copy_(t1.view(-1))
+        torch.from_numpy(rb[80:]).copy_(t2.view(-1))
+        del t1, t2
+        ctx.instance_alloc(k, cnt)
+        bufs.append((cnt, lb, rb, out, scb))
+        h2d += lb.nbytes + rb.nbytes
+        d2h += out.nbytes + scb.nbytes + 8
+    torch.cuda.empty_cache()
+
+    def one_call():
+        for k, (cnt, lb, rb, out, scb) in enumerate(bufs):
+            ctx.write_left(k, lb)
+            ctx.write_right(k, rb)
+            ctx.run_async(k, cnt)
+            ctx.read_out(k, out)
+            ctx.read_scaler(k, scb)
+        total = 0
+        for k in range(len(bufs)):
+            total += ctx.scaler_increment(k)       # waits for the instance
+        return total
+
+    one_call()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        inc = one_call()
+    barrier()
+    dt = time.perf_counter() - t0
+    dt = sharding.max_over_ranks(dt, device)
+    lo_scaled = (first + 3) // 4
+    assert inc == (first + n + 3) // 4 - lo_scaled, "e2e scaler increment mismatch"
+    assert int(bufs[0][4][:8].sum()) == sum(1 for s in range(first, first + min(8, n)) if s % 4 == 0)
+    ctx.close()
+    for p in frees:
+        pkg.host_free(p)
+    return {"value": total_sites * e2e_steps / dt, "unit": "sites/s",
+            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+            "instances": inst, "ms_per_step": dt / e2e_steps * 1e3,
+            "timing": "host wall clock around plf_write/run/read/wait, barrier + device sync on both sides, max over ranks",
+            "pcie_gbs_per_gpu": (h2d + d2h) * e2e_steps / dt / 1e9}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=list(TOTAL_SITES))
+    ap.add_argument("--sites", type=int, default=0, help="override total site count")
+    ap.add_argument("--math", default="strict", choices=["strict", "fma"])
+    ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--blocks-per-sm", type=int, default=0)
+    ap.add_argument("--buffer-sets", type=int, default=0, help="0 = auto")
+    ap.add_argument("--instances", type=int, default=9, help="NUM_ACCELERATORS for the e2e leg")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,203 @@
+/*
+ * include/b200plf.h -- C ABI of the B200-native PLF "newview" path (libb200plf.so).
+ *
+ * This is the drop-in boundary.  The reference (GeertRoks/AMD-Versal-phylogenetic-likelihood-
+ * function) has no FFI layer of its own: its host program drives the accelerator through the
+ * XRT C++ API.  Each entry point below replaces one XRT use in the reference host and cites
+ * it (paths relative to /root/reference/).  Plain pointers and sizes only; no exceptions cross
+ * this boundary; every call returns PLF_OK (0) or a negative plf_status, and the message is
+ * available from plf_last_error().
+ *
+ * Threading: a plf_ctx belongs to one GPU.  Distinct instances of one ctx may be driven from
+ * distinct host threads (the reference drives each instance from its own xrt::queue workers,
+ * app/src/host_mem.cpp:249-260); one instance must not be driven from two threads at once.
+ *
+ * There is NO CPU fallback anywhere behind this header: without a CUDA device every compute
+ * entry point fails with PLF_ERR_CUDA.
+ */
+#ifndef B200PLF_H
+#define B200PLF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200PLF_VERSION 100
+
+/* Sizes fixed by STATES=DNA (Makefile:31): 4 rate categories x 4 states. */
+#define PLF_SITE_FLOATS 16u      /* one site of a CLV: [category j][state l]  (plf.cpp:21-23)   */
+#define PLF_EV_FLOATS 16u        /* EV[k][l]                                  (plf.cpp:47)      */
+#define PLF_BRANCH_FLOATS 64u    /* P[j][k][l]                                (plf.cpp:37-38)   */
+#define PLF_HEADER_COMB 80u      /* floats in front of the CLV: [EV16|P64]    (host_mem.cpp:231-233) */
+#define PLF_HEADER_SEP 64u       /* Sep right buffer: [P64]                   (host_mem.cpp:239-240) */
+
+typedef enum plf_status {
+    PLF_OK = 0,
+    PLF_ERR_INVALID = -1,   /* bad argument (index, size, alignment, NULL)            */
+    PLF_ERR_CUDA = -2,      /* CUDA runtime / no device / kernel launch failure      */
+    PLF_ERR_NOMEM = -3,     /* device or pinned-host allocation failed                */
+    PLF_ERR_STATE = -4      /* call order violated (e.g. run before alloc)            */
+} plf_status;
+
+/* PLIO_LAYOUT knob (Makefile:28): how the right-child buffer is packed.
+ *   COMB: left = right-format = [EV16|P64|CLV]   SEP: right = [P64|CLV]
+ * (host_mem.cpp:234-241; mm2sright_memDNAwindowComb.cpp:32-42 vs ...windowSep.cpp:37-40).   */
+typedef enum plf_layout { PLF_LAYOUT_COMB = 0, PLF_LAYOUT_SEP = 1 } plf_layout;
+
+/* INPUT_SRC knob (Makefile:30).  MEM: CLVs are read from the instance buffers.
+ * GEN: the kernel synthesises the constant site pattern of hls/src/mm2s{left,right}_gen*.cpp
+ * in registers and reads no CLV; used to isolate kernel throughput (host_gen.cpp).            */
+typedef enum plf_input_src { PLF_INPUT_MEM = 0, PLF_INPUT_GEN = 1 } plf_input_src;
+
+/* Arithmetic mode of the fused kernel.
+ *   STRICT: separately rounded fp32 multiplies and adds in the order of plf.cpp:29-52
+ *           -> bit-identical to the reference's CPU plf() (the default).
+ *   FMA:    contracted multiply-adds; CLVs agree to <= 1e-5 relative, scaler decisions can
+ *           differ only for sites whose max |x3| is within that distance of 2^-32.          */
+typedef enum plf_math { PLF_MATH_STRICT = 0, PLF_MATH_FMA = 1 } plf_math;
+
+/* GEN sink behaviour (cfg4a / cfg4b of SURVEY.md section 8d). */
+typedef enum plf_gen_sink {
+    PLF_GEN_WRITE = 0,      /* write CLV + scaler bytes (65 B/site)                      */
+    PLF_GEN_DISCARD = 1     /* fold outputs into a checksum, write nothing (s2mm_gen*)    */
+} plf_gen_sink;
+
+/* Timestamps the reference host takes around each call (host_mem.cpp:294,302,309,318). */
+typedef enum plf_mark_id { PLF_MARK_BEGIN = 0, PLF_MARK_T1 = 1, PLF_MARK_T2 = 2, PLF_MARK_END = 3 } plf_mark_id;
+
+typedef struct plf_ctx plf_ctx;
+
+/* ---- device / context ------------------------------------------------------------------ */
+
+/* Number of CUDA devices (0 and PLF_ERR_CUDA when there is none). */
+int plf_device_count(int *count);
+/* Device name and PCI bus id, the analogue of xrt::info::device::{name,bdf} (host_mem.cpp:88-89). */
+int plf_device_info(int device, char *name, size_t name_len, char *bdf, size_t bdf_len);
+/* Resolve "0000:5e:00.0"-style BDF (argv[2] of the reference host) or a decimal ordinal. */
+int plf_device_from_string(const char *bdf_or_ordinal, int *device);
+
+/* Replaces acap_info(xclbin, BDF): open device, "load" the accelerator (include.h:30-36,85-102).
+ * n_instances is NUM_ACCELERATORS (Makefile:29): independent PLF instances, each with its own
+ * CUDA stream.  Fails (PLF_ERR_CUDA) instead of throwing.                                     */
+int plf_ctx_create(plf_ctx **ctx, int device, unsigned n_instances, int layout, int input_src);
+int plf_ctx_destroy(plf_ctx *ctx);
+/* Last error message of this ctx (or of ctx-less calls when ctx == NULL).  Never NULL. */
+const char *plf_last_error(const plf_ctx *ctx);
+
+int plf_ctx_set_math(plf_ctx *ctx, int math_mode);          /* plf_math; default STRICT       */
+int plf_ctx_set_gen_sink(plf_ctx *ctx, int sink);           /* plf_gen_sink; default WRITE    */
+/* Kernel tuning: variant id and launch shape; 0 = library default.  See DESIGN.md.           */
+int plf_ctx_set_tuning(plf_ctx *ctx, int variant, int threads_per_block, int blocks_per_sm);
+unsigned plf_ctx_instances(const plf_ctx *ctx);
+
+/* ---- instance buffers: xrt::bo x4 per instance (host_mem.cpp:123-133) --------------------- */
+
+/* Allocates left, right, out and scaler device buffers for up to max_sites sites:
+ * left (80+16*max_sites) floats, right (80|64 + 16*max_sites) floats, out 16*max_sites floats,
+ * scaler max_sites bytes (tb.instance_size_*, include.h:173-179,222-239 -- in size_t here).   */
+int plf_instance_alloc(plf_ctx *ctx, unsigned inst, size_t max_sites);
+int plf_instance_free(plf_ctx *ctx, unsigned inst);
+
+/* bo.write(host_ptr, bytes, 0) (host_mem.cpp:297-298): enqueue a host->device copy of `bytes`
+ * bytes of the packed buffer at byte offset `offset` on the instance's stream.  The host buffer
+ * must stay valid until plf_wait(); it is copied asynchronously when it is pinned
+ * (plf_host_alloc / plf_host_register).                                                      */
+int plf_write_left(plf_ctx *ctx, unsigned inst, const float *packed, size_t bytes, size_t offset);
+int plf_write_right(plf_ctx *ctx, unsigned inst, const float *packed, size_t bytes, size_t offset);
+/* Per-site integer weights (plf.cpp:63; host_mem.cpp:206-209 uses all ones).  wgt == NULL
+ * restores the all-ones default (no weight traffic in the kernel).                          */
+int plf_write_wgt(plf_ctx *ctx, unsigned inst, const int *wgt, size_t count);
+
+/* run.set_arg(sites) + s2mm.start(); mm2sleft.start(); mm2sright.start() (host_mem.cpp:142-156,
+ * 305): enqueue ONE fused kernel for `sites` sites on the instance's stream.                  */
+int plf_run_async(plf_ctx *ctx, unsigned inst, size_t sites);
+/* run.wait() x3 / instance_done[k].wait() (host_mem.cpp:305,323-325): block until everything
+ * enqueued on the instance has finished; reports asynchronous CUDA errors.                   */
+int plf_wait(plf_ctx *ctx, unsigned inst);
+
+/* bo.read (host_mem.cpp:313-314): enqueue device->host copies of the result CLV (16 floats per
+ * site) and of the per-site scaler bytes (0/1) (s2mm_memDNAwindowComb.cpp:96-97).             */
+int plf_read_out(plf_ctx *ctx, unsigned inst, float *dst, size_t bytes, size_t offset);
+int plf_read_scaler(plf_ctx *ctx, unsigned inst, char *dst, size_t bytes, size_t offset);
+/* sum_j scaler[j]*wgt[j] (host_mem.cpp:384-388), accumulated inside the kernel.  Waits for the
+ * instance, then returns the value of the LAST run.                                          */
+int plf_scaler_increment(plf_ctx *ctx, unsigned inst, long long *increment);
+/* GEN + DISCARD sink: checksum (sum of all outputs, fp32 accumulated in fp64) of the last run. */
+int plf_gen_checksum(plf_ctx *ctx, unsigned inst, double *checksum);
+
+/* Enqueue a timestamp on the instance's stream / read the time between two of them (ms), the
+ * device-side analogue of timing_data{begin,t1,t2,end} (timing.h:25-52).                     */
+int plf_mark(plf_ctx *ctx, unsigned inst, int mark_id);
+int plf_elapsed_ms(plf_ctx *ctx, unsigned inst, int from_mark, int to_mark, float *ms);
+
+/* Raw handles for callers that keep data on the device (next newview of a tree, benchmarks).
+ * Any pointer argument may be NULL.  stream is a cudaStream_t.                                */
+int plf_instance_device_ptrs(plf_ctx *ctx, unsigned inst, float **left, float **right,
+                             float **out, unsigned char **scaler);
+int plf_instance_stream(plf_ctx *ctx, unsigned inst, void **stream);
+
+/* ---- pinned host memory -------------------------------------------------------------------- */
+int plf_host_alloc(void **ptr, size_t bytes);
+int plf_host_free(void *ptr);
+int plf_host_register(void *ptr, size_t bytes);
+int plf_host_unregister(void *ptr);
+
+/* ---- the fused kernel on caller-owned device memory ---------------------------------------- */
+
+typedef struct plf_launch_opts {
+    int math_mode;          /* plf_math                                                          */
+    int variant;            /* kernel variant, 0 = default                           */
+    int threads_per_block;  /* 0 = default                                                       */
+    int blocks_per_sm;      /* 0 = default (persistent grid = SMs x blocks_per_sm)               */
+    int ev_per_category;    /* 0: ev is EV[16]; 1: ev is EV4[4][16], one matrix per category     */
+} plf_launch_opts;
+
+/* Newview of n sites.  ALL pointers are device pointers on `device`'s current context:
+ *   x1,x2,x3 : 16 floats per site, 16-byte aligned; x3 may alias neither input
+ *   scaler   : n bytes (0/1) or NULL
+ *   ev,p_left,p_right : 16 / 64 / 64 floats (layouts of plf.cpp:37-38,47)
+ *   wgt      : n ints or NULL (all ones)
+ *   scaler_sum: one unsigned 64-bit counter the kernel ADDS sum(wgt over rescaled sites) to,
+ *              or NULL.  The caller zeroes it.
+ * opts may be NULL (defaults).  stream is a cudaStream_t (NULL = default stream).
+ * Replaces plf() (plf.h:1-5) for device-resident data.                                        */
+int plf_newview_device(const float *x1, const float *x2, float *x3, unsigned char *scaler,
+                       const float *ev, const float *p_left, const float *p_right,
+                       const int *wgt, size_t n, unsigned long long *scaler_sum,
+                       const plf_launch_opts *opts, void *stream);
+
+/* INPUT_SRC=gen analogue on caller-owned memory: no CLV is read; x3/scaler may be NULL when
+ * sink == PLF_GEN_DISCARD, in which case the fp64 sum of all outputs is ADDED to *checksum
+ * (device pointer, may be NULL).                                                             */
+int plf_newview_gen_device(float *x3, unsigned char *scaler, size_t n,
+                           unsigned long long *scaler_sum, double *checksum, int sink,
+                           const plf_launch_opts *opts, void *stream);
+
+/* The constant 16-float site patterns and the per-lane header the gen movers emit
+ * (mm2sleft_genDNAwindowComb.cpp:44-49, mm2sright_genDNAwindowComb.cpp:45-50), as host arrays:
+ * x1[16], x2[16], ev4[64], p_left[64], p_right[64] -- what a MEM run must be fed to reproduce
+ * a GEN run.                                                                                 */
+int plf_gen_pattern(float *x1, float *x2, float *ev4, float *p_left, float *p_right);
+
+/* Synthetic stimulus generated on the device with a counter-based hash: the value
+ * distribution of host_mem.cpp:198-204 (uniform(0,1); the left CLV of every 4th site times
+ * 1e-12f).  Element e of x1/x2 depends only on (seed, first_site*16 + e), so any site range
+ * can be generated independently on any GPU.                                                  */
+int plf_generate_device(float *x1, float *x2, size_t first_site, size_t n, uint64_t seed,
+                        void *stream);
+/* The same generator evaluated on the host for a site range (for verification of slices). */
+int plf_generate_host(float *x1, float *x2, size_t first_site, size_t n, uint64_t seed);
+
+/* Largest tile the library was compiled for, number of SMs etc. -- introspection for benches. */
+int plf_kernel_info(int variant, int math_mode, int *regs_per_thread, int *threads_per_block,
+                    int *blocks_per_sm, int *num_sms);
+/* Number of kernel launches this library has issued in this process (all contexts). */
+unsigned long long plf_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200PLF_H */
