@@ -28,16 +28,34 @@ constexpr float kTwoToThe32 = 0x1p+32f;      // plf.cpp:5
 // ---------------------------------------------------------------------------------------------
 // Arithmetic policies.
 // STRICT reproduces the reference's rounding: each product and each sum is rounded to fp32
-// separately, sums run left to right from +0.0f (plf.cpp:32-39, 45-50).  __fmul_rn/__fadd_rn are
-// never contracted into FMA by nvcc.  FMA is the contracted variant (<= 1e-5 relative).
+// separately and sums run left to right (plf.cpp:32-39, 45-50).  __fmul_rn/__fadd_rn are never
+// contracted into FMA by nvcc.  FMA is the contracted variant (<= 1e-5 relative).
+//
+// The reference starts every sum from +0.0f.  In round-to-nearest "+0 + q0" differs from q0 only
+// for q0 == -0, and by induction the whole sum differs only when ALL four products are -0 (result
+// -0 instead of +0).  A zero a[k] or b[k] with the wrong sign can only flip the sign of zero
+// products further down, and those matter only when an output element is exactly zero -- in
+// which case the reference output is +0 (a sum that started from +0 is never -0).  So the leading
+// add is dropped from the two branch mat-vecs (dot4_inner) and kept in the final EV mat-vec
+// (dot4_final), which canonicalises any -0 to +0: outputs stay bit-identical to plf() at 92
+// instead of 100 fp32 operations per (site, category).
 // ---------------------------------------------------------------------------------------------
 struct MathStrict {
     static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
-    // ((((+0 + a0*b0) + a1*b1) + a2*b2) + a3*b3)
-    static __device__ __forceinline__ float dot4(float a0, float a1, float a2, float a3,
-                                                 float b0, float b1, float b2, float b3)
+    // ((a0*b0 + a1*b1) + a2*b2) + a3*b3
+    static __device__ __forceinline__ float dot4_inner(float a0, float a1, float a2, float a3,
+                                                       float b0, float b1, float b2, float b3)
     {
-        float acc = __fadd_rn(0.0f, __fmul_rn(a0, b0));   // keeps -0.0 -> +0.0 of the reference
+        float acc = __fadd_rn(__fmul_rn(a0, b0), __fmul_rn(a1, b1));
+        acc = __fadd_rn(acc, __fmul_rn(a2, b2));
+        acc = __fadd_rn(acc, __fmul_rn(a3, b3));
+        return acc;
+    }
+    // ((((+0 + a0*b0) + a1*b1) + a2*b2) + a3*b3)
+    static __device__ __forceinline__ float dot4_final(float a0, float a1, float a2, float a3,
+                                                       float b0, float b1, float b2, float b3)
+    {
+        float acc = __fadd_rn(0.0f, __fmul_rn(a0, b0));
         acc = __fadd_rn(acc, __fmul_rn(a1, b1));
         acc = __fadd_rn(acc, __fmul_rn(a2, b2));
         acc = __fadd_rn(acc, __fmul_rn(a3, b3));
@@ -47,14 +65,19 @@ struct MathStrict {
 
 struct MathFma {
     static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
-    static __device__ __forceinline__ float dot4(float a0, float a1, float a2, float a3,
-                                                 float b0, float b1, float b2, float b3)
+    static __device__ __forceinline__ float dot4_inner(float a0, float a1, float a2, float a3,
+                                                       float b0, float b1, float b2, float b3)
     {
         float acc = a0 * b0;
         acc = __fmaf_rn(a1, b1, acc);
         acc = __fmaf_rn(a2, b2, acc);
         acc = __fmaf_rn(a3, b3, acc);
         return acc;
+    }
+    static __device__ __forceinline__ float dot4_final(float a0, float a1, float a2, float a3,
+                                                       float b0, float b1, float b2, float b3)
+    {
+        return dot4_inner(a0, a1, a2, a3, b0, b1, b2, b3);
     }
 };
 
@@ -110,14 +133,14 @@ __device__ __forceinline__ bool category_newview(const CatConst &c, const float4
     float p[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        float a = M::dot4(u.x, u.y, u.z, u.w, c.L[4 * k], c.L[4 * k + 1], c.L[4 * k + 2], c.L[4 * k + 3]);
-        float b = M::dot4(v.x, v.y, v.z, v.w, c.R[4 * k], c.R[4 * k + 1], c.R[4 * k + 2], c.R[4 * k + 3]);
+        float a = M::dot4_inner(u.x, u.y, u.z, u.w, c.L[4 * k], c.L[4 * k + 1], c.L[4 * k + 2], c.L[4 * k + 3]);
+        float b = M::dot4_inner(v.x, v.y, v.z, v.w, c.R[4 * k], c.R[4 * k + 1], c.R[4 * k + 2], c.R[4 * k + 3]);
         p[k] = M::mul(a, b);
     }
-    o.x = M::dot4(p[0], p[1], p[2], p[3], c.E[0], c.E[4], c.E[8], c.E[12]);
-    o.y = M::dot4(p[0], p[1], p[2], p[3], c.E[1], c.E[5], c.E[9], c.E[13]);
-    o.z = M::dot4(p[0], p[1], p[2], p[3], c.E[2], c.E[6], c.E[10], c.E[14]);
-    o.w = M::dot4(p[0], p[1], p[2], p[3], c.E[3], c.E[7], c.E[11], c.E[15]);
+    o.x = M::dot4_final(p[0], p[1], p[2], p[3], c.E[0], c.E[4], c.E[8], c.E[12]);
+    o.y = M::dot4_final(p[0], p[1], p[2], p[3], c.E[1], c.E[5], c.E[9], c.E[13]);
+    o.z = M::dot4_final(p[0], p[1], p[2], p[3], c.E[2], c.E[6], c.E[10], c.E[14]);
+    o.w = M::dot4_final(p[0], p[1], p[2], p[3], c.E[3], c.E[7], c.E[11], c.E[15]);
     // NaN compares false, exactly like ABS(x) < minlikelihood on the CPU.
     return (fabsf(o.x) < kMinLikelihood) & (fabsf(o.y) < kMinLikelihood) &
            (fabsf(o.z) < kMinLikelihood) & (fabsf(o.w) < kMinLikelihood);
@@ -334,17 +357,19 @@ plf_newview_tma(const float4 *__restrict__ x1, const float4 *__restrict__ x2,
     if (warp == WARPS) {
         // ===== producer =====
         if (lane == 0) {
-            uint32_t it = 0;
-            for (size_t st = blockIdx.x; st < n_stages; st += gridDim.x, ++it) {
-                const uint32_t slot = it % DEPTH;
-                const uint32_t phase = (it / DEPTH) & 1u;
+            uint32_t slot = 0, phase = 0;
+            for (size_t st = blockIdx.x; st < n_stages; st += gridDim.x) {
                 mbar_wait(&empty[slot], phase ^ 1u);
                 const size_t s0 = st * STAGE;
                 const size_t left = n - s0;
                 const uint32_t bytes = (uint32_t)(left < (size_t)STAGE ? left : (size_t)STAGE) * 64u;
                 mbar_arrive_expect_tx(&full[slot], 2u * bytes);
-                bulk_g2s(s1 + (size_t)slot * STAGE_F4, x1 + s0 * 4, bytes, &full[slot]);
-                bulk_g2s(s2 + (size_t)slot * STAGE_F4, x2 + s0 * 4, bytes, &full[slot]);
+                bulk_g2s(s1 + slot * STAGE_F4, x1 + s0 * 4, bytes, &full[slot]);
+                bulk_g2s(s2 + slot * STAGE_F4, x2 + s0 * 4, bytes, &full[slot]);
+                if (++slot == DEPTH) {
+                    slot = 0;
+                    phase ^= 1u;
+                }
             }
         }
     } else {
@@ -354,14 +379,18 @@ plf_newview_tma(const float4 *__restrict__ x1, const float4 *__restrict__ x2,
         CatConst c;
         load_cat_const(c, ev, pl, pr, cat, ev_per_category);
 
-        uint32_t it = 0;
-        for (size_t st = blockIdx.x; st < n_stages; st += gridDim.x, ++it) {
-            const uint32_t slot = it % DEPTH;
-            const uint32_t phase = (it / DEPTH) & 1u;
-            const size_t s0 = st * STAGE + (size_t)warp * TILE;     // first site of this warp's tile
-            const float4 *t1 = s1 + (size_t)slot * STAGE_F4 + warp * (TILE * 4) + lane;
-            const float4 *t2 = s2 + (size_t)slot * STAGE_F4 + warp * (TILE * 4) + lane;
+        const size_t last_full = n / STAGE;                 // stages [0, last_full) are complete
+        const size_t stride_f4 = (size_t)gridDim.x * STAGE_F4;
+        // this lane's output slot in the CTA's first stage; advanced by one grid stride per iteration
+        float4 *out = x3 + ((size_t)blockIdx.x * STAGE + (size_t)warp * TILE) * 4 + lane;
+        unsigned char *sc_out = scaler ? scaler + (size_t)blockIdx.x * STAGE + warp * TILE + lane : nullptr;
+        const int *w_in = wgt ? wgt + (size_t)blockIdx.x * STAGE + warp * TILE + lane : nullptr;
+        const uint32_t tile_off = warp * (TILE * 4) + lane;
 
+        uint32_t slot = 0, phase = 0;
+        for (size_t st = blockIdx.x; st < n_stages; st += gridDim.x) {
+            const float4 *t1 = s1 + slot * STAGE_F4 + tile_off;
+            const float4 *t2 = s2 + slot * STAGE_F4 + tile_off;
             mbar_wait(&full[slot], phase);
             float4 a[U], b[U], o[U];
             unsigned ballots[U];
@@ -373,28 +402,51 @@ plf_newview_tma(const float4 *__restrict__ x1, const float4 *__restrict__ x2,
             // all of this warp's reads of the slot are done once the values are in registers
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[slot]);
-
-            const bool full_tile = s0 + TILE <= n;
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const size_t s = s0 + 8 * u + site_in_row;
-                const bool live = full_tile || s < n;
-                bool small = category_newview<M>(c, a[u], b[u], o[u]);
-                ballots[u] = __ballot_sync(0xffffffffu, small && live);
-                if (nibble_all(ballots[u], site_in_row)) rescale(o[u]);
-                if (live) st_stream(x3 + s * 4 + cat, o[u]);
+            if (++slot == DEPTH) {
+                slot = 0;
+                phase ^= 1u;
             }
-            if (lane < TILE) {
-                unsigned bal = ballots[0];
+
+            if (st < last_full) {
+                // complete stage: no bounds predicates anywhere
 #pragma unroll
-                for (int u = 1; u < U; ++u) bal = (lane >> 3) == u ? ballots[u] : bal;
-                const bool scaled = nibble_all(bal, lane & 7);
-                const size_t s = s0 + lane;
-                if (s < n) {
-                    if (scaler) scaler[s] = scaled ? 1 : 0;
-                    if (scaled) my_sum += wgt ? (unsigned long long)(long long)wgt[s] : 1ull;
+                for (int u = 0; u < U; ++u) {
+                    bool small = category_newview<M>(c, a[u], b[u], o[u]);
+                    ballots[u] = __ballot_sync(0xffffffffu, small);
+                    if (nibble_all(ballots[u], site_in_row)) rescale(o[u]);
+                    st_stream(out + 32 * u, o[u]);
+                }
+                if (lane < TILE) {
+                    unsigned bal = ballots[0];
+#pragma unroll
+                    for (int u = 1; u < U; ++u) bal = (lane >> 3) == u ? ballots[u] : bal;
+                    const bool scaled = nibble_all(bal, lane & 7);
+                    if (sc_out) *sc_out = scaled ? 1 : 0;
+                    if (scaled) my_sum += w_in ? (unsigned long long)(long long)*w_in : 1ull;
+                }
+            } else {
+                // the single ragged stage at the end of the site range
+                const size_t s0 = st * STAGE + (size_t)warp * TILE;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const bool live = s0 + 8 * u + site_in_row < n;
+                    bool small = category_newview<M>(c, a[u], b[u], o[u]);
+                    ballots[u] = __ballot_sync(0xffffffffu, small && live);
+                    if (nibble_all(ballots[u], site_in_row)) rescale(o[u]);
+                    if (live) st_stream(out + 32 * u, o[u]);
+                }
+                if (lane < TILE && s0 + lane < n) {
+                    unsigned bal = ballots[0];
+#pragma unroll
+                    for (int u = 1; u < U; ++u) bal = (lane >> 3) == u ? ballots[u] : bal;
+                    const bool scaled = nibble_all(bal, lane & 7);
+                    if (sc_out) *sc_out = scaled ? 1 : 0;
+                    if (scaled) my_sum += w_in ? (unsigned long long)(long long)*w_in : 1ull;
                 }
             }
+            out += stride_f4;
+            if (sc_out) sc_out += (size_t)gridDim.x * STAGE;
+            if (w_in) w_in += (size_t)gridDim.x * STAGE;
         }
     }
     if (scaler_sum) block_add_u64<THREADS>(my_sum, scaler_sum);

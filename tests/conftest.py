@@ -50,5 +50,22 @@ def ref_cases():
 
 
 def bits(a):
-    """Bit pattern view for exact comparisons (NaN-safe, distinguishes -0.0)."""
-    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+    """Bit pattern view for exact comparisons: distinguishes -0.0 from +0.0 and compares NaNs as
+    equal to each other.  NaN payload/sign is the one thing IEEE-754 leaves to the implementation
+    (x86 SSE produces 0xFFC00000 for invalid operations and propagates input payloads; NVIDIA GPUs
+    produce the canonical 0x7FFFFFFF), so every NaN is mapped to one pattern before comparing."""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    b = a.view(np.uint32).copy()
+    b[np.isnan(a)] = 0x7FC00000
+    return b
+
+
+def first_mismatch(got, want):
+    """Human-readable description of the first differing element (for assertion messages)."""
+    g, w = bits(got).reshape(-1), bits(want).reshape(-1)
+    idx = np.nonzero(g != w)[0]
+    if idx.size == 0:
+        return "identical"
+    i = int(idx[0])
+    return (f"{idx.size} of {g.size} elements differ; first at flat index {i} (site {i // 16}, elem {i % 16}): "
+            f"got {np.asarray(got).reshape(-1)[i]!r} (0x{g[i]:08x}) want {np.asarray(want).reshape(-1)[i]!r} (0x{w[i]:08x})")

@@ -15,7 +15,7 @@ import numpy as np
 import pytest
 
 import oracle
-from conftest import GOLDEN, bits
+from conftest import GOLDEN, bits, first_mismatch
 
 pytestmark = pytest.mark.gpu
 
@@ -95,7 +95,7 @@ def test_reference_fixtures_bit_exact_through_host_api(pkg, gpu, ref_cases, name
         x3, sc, inc = ctx.newview(g("ev"), g("left"), g("right"), g("x1"), g("x2"), wgt,
                                   instances=instances)
     assert inc == int(g("inc"))
-    assert np.array_equal(bits(x3), bits(g("x3")))
+    assert np.array_equal(bits(x3), bits(g("x3"))), first_mismatch(x3, g("x3"))
     w = np.ones(n, np.int64) if wgt is None else wgt.astype(np.int64)
     assert int((sc.astype(np.int64) * w).sum()) == inc
 
@@ -122,7 +122,7 @@ def test_variants_strict_bit_exact(pkg, gpu, coracle, variant, threads):
         ev, left, right, x1, x2, wgt = signed_inputs(n, seed=n)
         o3, osc, oinc = coracle.newview(x1, x2, ev, left, right, wgt)
         x3, sc, inc = run_device(pkg, gpu, ev, left, right, x1, x2, wgt, 0, variant, threads)
-        assert np.array_equal(bits(x3), bits(o3)), (variant, n)
+        assert np.array_equal(bits(x3), bits(o3)), (variant, n, first_mismatch(x3, o3))
         assert np.array_equal(sc, osc), (variant, n)
         assert inc == oinc, (variant, n)
         assert 0 < osc.sum() < n or n < 8

@@ -70,6 +70,17 @@ def main():
                          (2622, 256), (1424, 256), (2324, 256), (1422, 512), (1622, 512), (1421, 512), (1821, 512),
                          (4422, 128), (4822, 128), (3421, 128), (4821, 128)):
                 combos.append((v, t, 0, math))
+    elif args.grid == "tma":
+        combos = []
+        for math in (0, 1):
+            for t in (128, 256, 512):
+                for u in (1, 2, 4):
+                    for d in (2, 3, 4, 6, 8):
+                        combos.append((1000 + 100 * d + 20 + u, t, 0, math))
+            for t, b in ((128, 2), (128, 3), (256, 2)):
+                for u in (1, 2):
+                    for d in (2, 3, 4):
+                        combos.append((1000 * b + 100 * d + 20 + u, t, 0, math))
     else:
         combos = []
         for math in (0, 1):
@@ -121,10 +132,29 @@ def main():
             print(f"v={variant:5d} t={threads:3d} bps={row['bps']:2d} math={math} regs={row['regs']:3d} "
                   f"mean={mean:7.4f} ms min={ts[0]:7.4f}  {gbs:7.0f} GB/s  {row['frac_measured']:.3f} of measured  "
                   f"{'ok' if ok else 'MISMATCH'}", flush=True)
+    # INPUT_SRC=gen analogue: cfg4a (write) and cfg4b (discard = pure issue rate, no HBM traffic)
+    gen_rows = []
+    chk = torch.zeros(1, dtype=torch.float64, device=dev)
+    for math in (0, 1):
+        for sink, label in ((pkg.GEN_WRITE, "write"), (pkg.GEN_DISCARD, "discard")):
+            opts = pkg.make_opts(math)
+            a = (x3.data_ptr(), sc.data_ptr(), n, dsum.data_ptr(), chk.data_ptr(), sink, opts, stream)
+            for _ in range(3):
+                pkg.newview_gen_device(*a)
+            e0.record()
+            for _ in range(args.reps):
+                pkg.newview_gen_device(*a)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / args.reps
+            gs = n / (ms * 1e-3) / 1e9
+            gen_rows.append({"math": math, "sink": label, "ms": ms, "gsites": gs,
+                             "gbs_written": (65 * n / (ms * 1e-3) / 1e9) if sink == pkg.GEN_WRITE else 0.0})
+            print(f"gen math={math} sink={label:7s} {ms:7.4f} ms  {gs:6.2f} G sites/s", flush=True)
     if args.out:
         os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
         with open(args.out, "w") as f:
-            json.dump({"sites": n, "reps": args.reps, "copy_gbs": copy_gbs, "peak": peak, "rows": rows}, f, indent=1)
+            json.dump({"sites": n, "reps": args.reps, "copy_gbs": copy_gbs, "peak": peak, "rows": rows, "gen": gen_rows}, f, indent=1)
 
 
 if __name__ == "__main__":
