@@ -46,10 +46,35 @@ HOSTFLAGS := -O2 -g -Wall -std=c++17 -ffp-contract=off -pthread -Iinclude $(HOST
 
 all: lib host oracle
 
-lib: $(LIB)
+lib:
+	@$(MAKE) --no-print-directory -j8 $(LIB)
 
-$(LIB): $(PKG)/csrc/plf_capi.cu $(PKG)/csrc/plf_kernels.cuh include/b200plf.h
-	$(NVCC) $(NVFLAGS) -shared -o $@ $(PKG)/csrc/plf_capi.cu
+CSRC := $(PKG)/csrc
+OBJDIR := $(PKG)/build
+KHDRS := $(CSRC)/plf_kernels.cuh $(CSRC)/plf_registry.h include/b200plf.h
+OBJS := $(OBJDIR)/plf_capi.o $(OBJDIR)/sel_ldg_strict.o $(OBJDIR)/sel_ldg_fma.o \
+        $(OBJDIR)/sel_tma_strict.o $(OBJDIR)/sel_tma_fma.o
+
+$(OBJDIR)/plf_capi.o: $(CSRC)/plf_capi.cu $(KHDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -c -o $@ $<
+
+# the kernel instantiations: one translation unit per (kernel family, arithmetic mode)
+$(OBJDIR)/sel_ldg_strict.o: $(CSRC)/plf_sel_ldg.cu $(KHDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -DPLF_SEL_MATH=MathStrict -DPLF_SEL_NAME=select_ldg_strict -c -o $@ $<
+$(OBJDIR)/sel_ldg_fma.o: $(CSRC)/plf_sel_ldg.cu $(KHDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -DPLF_SEL_MATH=MathFma -DPLF_SEL_NAME=select_ldg_fma -c -o $@ $<
+$(OBJDIR)/sel_tma_strict.o: $(CSRC)/plf_sel_tma.cu $(KHDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -DPLF_SEL_MATH=MathStrict -DPLF_SEL_NAME=select_tma_strict -c -o $@ $<
+$(OBJDIR)/sel_tma_fma.o: $(CSRC)/plf_sel_tma.cu $(KHDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -DPLF_SEL_MATH=MathFma -DPLF_SEL_NAME=select_tma_fma -c -o $@ $<
+
+$(LIB): $(OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS)
 
 host: $(PKG)/host_mem.exe $(PKG)/host_gen.exe
 
@@ -67,7 +92,7 @@ run: host
 	./$(PKG)/host_$(INPUT_SRC).exe $(CONFIG) $(DEVICE) $(ALIGNMENTS) $(PLF_CALLS) $(INSTANCES_USED)
 
 clean:
-	rm -f $(LIB) $(PKG)/host_mem.exe $(PKG)/host_gen.exe
+	rm -rf $(LIB) $(PKG)/build $(PKG)/host_mem.exe $(PKG)/host_gen.exe
 	$(MAKE) -C oracle clean
 
 .PHONY: all lib host oracle run clean

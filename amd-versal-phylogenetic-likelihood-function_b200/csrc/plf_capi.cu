@@ -8,6 +8,7 @@
 // No exception leaves this file and there is no CPU fallback: every failure is a status code.
 #include "../../include/b200plf.h"
 #include "plf_kernels.cuh"
+#include "plf_registry.h"
 
 #include <atomic>
 #include <cstdarg>
@@ -84,141 +85,24 @@ int fail(plf_ctx *ctx, int code, const char *fmt, ...)
                         "%s failed: %s", #expr, cudaGetErrorString(e__));                       \
     } while (0)
 
-// ---- kernel variant registry -------------------------------------------------------------------
-// variant = 1000*B + 100*D + 10*K + U
-//   U : 128-bit loads per child per thread per tile (1, 2 or 4)
-//   K : 0 = "ldg" register-staged kernel with streaming load/store policy
-//       1 = "ldg" with plain (cached) loads/stores
-//       2 = "tma" bulk-copy / mbarrier ring kernel
-//   D : tma only: ring depth in stages (0 -> 4)
-//   B : minimum resident blocks per SM given to __launch_bounds__ (0 -> 1); caps registers/thread
-// threads_per_block is the number of COMPUTE threads (tma adds one producer warp).
-// variant 0 selects kDefaultVariant.
-constexpr int kDefaultVariant = 2422;
-constexpr int kDefaultThreads = 256;
+// ---- kernel variant registry: see plf_registry.h for the variant encoding ----------------------
+// Default: tma ring, 16 consumer warps, U=2 (256-site / 32 KB stages), 3 stages, 1 CTA per SM --
+// the fastest strict configuration in the sweep on B200 (profiles/r01_sweep.md).
+constexpr int kDefaultVariant = 1322;
+constexpr int kDefaultThreads = 512;
 
-using NewviewFn = void (*)(const float4 *, const float4 *, float4 *, unsigned char *, const float *,
-                           const float *, const float *, const int *, size_t, unsigned long long *,
-                           int);
-
-struct KernelSel {
-    NewviewFn fn = nullptr;
-    int threads = 0;            // launch block size
-    size_t smem = 0;            // dynamic shared memory
-    int sites_per_block_iter = 0;
-};
-
-template <class M, int U, bool STREAM, int MINB>
-KernelSel sel_ldg(int threads)
-{
-    KernelSel k;
-    switch (threads) {
-    case 128: k.fn = plf::plf_newview_ldg<M, U, STREAM, 128, MINB>; break;
-    case 256: k.fn = plf::plf_newview_ldg<M, U, STREAM, 256, MINB>; break;
-    case 512: if (MINB <= 2) k.fn = plf::plf_newview_ldg<M, U, STREAM, 512, (MINB <= 2 ? MINB : 1)>; break;
-    default: break;
-    }
-    k.threads = threads;
-    k.sites_per_block_iter = (threads / 32) * 8 * U;
-    return k;
-}
-
-template <class M, int U>
-KernelSel sel_ldg_u(int kind, int b, int threads)
-{
-    if (kind == 1) return b <= 1 ? sel_ldg<M, U, false, 1>(threads) : KernelSel{};
-    switch (b) {
-    case 0: case 1: return sel_ldg<M, U, true, 1>(threads);
-    case 2: return sel_ldg<M, U, true, 2>(threads);
-    case 3: return sel_ldg<M, U, true, 3>(threads);
-    case 4: return sel_ldg<M, U, true, 4>(threads);
-    default: return KernelSel{};
-    }
-}
-
-template <class M, int U, int WARPS, int DEPTH, int MINB>
-KernelSel sel_tma_one()
-{
-    KernelSel k;
-    k.smem = plf::tma_smem_bytes<U, WARPS, DEPTH>();
-    if (k.smem * MINB > 227u * 1024u) return KernelSel{};
-    k.fn = plf::plf_newview_tma<M, U, WARPS, DEPTH, MINB>;
-    k.threads = (WARPS + 1) * 32;
-    k.sites_per_block_iter = WARPS * 8 * U;
-    return k;
-}
-
-template <class M, int U, int WARPS, int MINB>
-KernelSel sel_tma_d(int d)
-{
-    switch (d) {
-    case 2: return sel_tma_one<M, U, WARPS, 2, MINB>();
-    case 3: return sel_tma_one<M, U, WARPS, 3, MINB>();
-    case 0: case 4: return sel_tma_one<M, U, WARPS, 4, MINB>();
-    case 6: return sel_tma_one<M, U, WARPS, 6, MINB>();
-    case 8: return sel_tma_one<M, U, WARPS, 8, MINB>();
-    default: return KernelSel{};
-    }
-}
-
-// consumer warps 4 / 8 / 16 with the launch bounds that still fit 2048 threads per SM
-template <class M, int U>
-KernelSel sel_tma_u(int b, int d, int threads)
-{
-    if (b == 0) b = 1;
-    switch (threads) {
-    case 128:
-        switch (b) {
-        case 1: return sel_tma_d<M, U, 4, 1>(d);
-        case 2: return sel_tma_d<M, U, 4, 2>(d);
-        case 3: return sel_tma_d<M, U, 4, 3>(d);
-        case 4: return sel_tma_d<M, U, 4, 4>(d);
-        default: return KernelSel{};
-        }
-    case 256:
-        switch (b) {
-        case 1: return sel_tma_d<M, U, 8, 1>(d);
-        case 2: return sel_tma_d<M, U, 8, 2>(d);
-        case 3: return sel_tma_d<M, U, 8, 3>(d);
-        default: return KernelSel{};
-        }
-    case 512:
-        switch (b) {
-        case 1: return sel_tma_d<M, U, 16, 1>(d);
-        default: return KernelSel{};
-        }
-    default: return KernelSel{};
-    }
-}
-
-template <class M>
-KernelSel sel_math(int variant, int threads)
-{
-    const int u = variant % 10, kind = (variant / 10) % 10, d = (variant / 100) % 10, b = variant / 1000;
-    if (kind == 2) {
-        switch (u) {
-        case 1: return sel_tma_u<M, 1>(b, d, threads);
-        case 2: return sel_tma_u<M, 2>(b, d, threads);
-        case 4: return sel_tma_u<M, 4>(b, d, threads);
-        default: return KernelSel{};
-        }
-    }
-    if ((kind == 0 || kind == 1) && d == 0) {
-        switch (u) {
-        case 1: return sel_ldg_u<M, 1>(kind, b, threads);
-        case 2: return sel_ldg_u<M, 2>(kind, b, threads);
-        case 4: return sel_ldg_u<M, 4>(kind, b, threads);
-        default: return KernelSel{};
-        }
-    }
-    return KernelSel{};
-}
+using plf::KernelSel;
+using plf::NewviewFn;
 
 KernelSel pick_kernel(int math, int variant, int threads)
 {
     if (variant < 0 || variant > 9999) return KernelSel{};
-    return math == PLF_MATH_FMA ? sel_math<plf::MathFma>(variant, threads)
-                                : sel_math<plf::MathStrict>(variant, threads);
+    const int u = variant % 10, kind = (variant / 10) % 10, d = (variant / 100) % 10, b = variant / 1000;
+    const bool fma = math == PLF_MATH_FMA;
+    if (kind == 2) return fma ? plf::select_tma_fma(u, d, b, threads) : plf::select_tma_strict(u, d, b, threads);
+    if ((kind == 0 || kind == 1) && d == 0)
+        return fma ? plf::select_ldg_fma(u, kind, b, threads) : plf::select_ldg_strict(u, kind, b, threads);
+    return KernelSel{};
 }
 
 int device_sms(int *sms)

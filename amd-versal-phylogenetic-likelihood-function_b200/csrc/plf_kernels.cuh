@@ -560,7 +560,7 @@ __host__ __device__ __forceinline__ void gen_pair(uint64_t seed, uint64_t elem, 
     if ((elem & 63u) < 16u) l = l * 1.0e-12f;     // j % 64 < 16  (host_mem.cpp:200-202)
 }
 
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 plf_generate_kernel(float4 *__restrict__ x1, float4 *__restrict__ x2, uint64_t first_elem,
                     size_t n_vec4, uint64_t seed)
 {

@@ -21,8 +21,8 @@ pytestmark = pytest.mark.gpu
 
 REL_TOL_FMA = 1e-5
 # kernel variants exercised everywhere: (variant id, compute threads per block)
-VARIANTS = [(0, 0), (2, 256), (1, 128), (4, 256), (12, 256), (3002, 256), (2422, 256), (421, 128),
-            (1324, 256), (1622, 512), (2822, 128)]
+VARIANTS = [(0, 0), (2, 256), (1, 128), (4, 256), (12, 256), (3002, 256), (2422, 256), (1421, 128),
+            (1324, 256), (1622, 512), (1322, 512), (3222, 128), (1221, 512)]
 RAGGED = [1, 7, 8, 9, 31, 33, 127, 128, 129, 1000, 4097, 65536 + 5]
 
 

@@ -70,6 +70,13 @@ def main():
                          (2622, 256), (1424, 256), (2324, 256), (1422, 512), (1622, 512), (1421, 512), (1821, 512),
                          (4422, 128), (4822, 128), (3421, 128), (4821, 128)):
                 combos.append((v, t, 0, math))
+    elif args.grid == "cand":
+        combos = []
+        for math in (0, 1):
+            for v, t in ((1322, 512), (1422, 512), (1622, 512), (1222, 512), (1321, 512), (1421, 512), (1621, 512),
+                         (1324, 512), (2322, 128), (3322, 128), (3222, 128), (1324, 256), (2322, 256), (2222, 256),
+                         (1422, 256), (1424, 128), (3002, 256), (2, 256)):
+                combos.append((v, t, 0, math))
     elif args.grid == "tma":
         combos = []
         for math in (0, 1):
