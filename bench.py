@@ -464,10 +464,17 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: route everything libraries print on fd 1 (e.g. NCCL's
+    # version banner) to stderr and restore the real stdout only around our own print.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if args.impl == "reference":
         run_reference_arm(args)
     else:
         run_b200_arm(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":
