@@ -91,6 +91,22 @@ PROTOTYPES = {
     "plf_gen_pattern": (_i, [_vp] * 5),
     "plf_generate_device": (_i, [_vp, _vp, _sz, _sz, ctypes.c_uint64, _vp]),
     "plf_generate_host": (_i, [_vp, _vp, _sz, _sz, ctypes.c_uint64]),
+    "plf_tree_create": (_i, [ctypes.POINTER(_vp), _i, _u, _vp, _vp, _sz]),
+    "plf_tree_destroy": (_i, [_vp]),
+    "plf_tree_last_error": (ctypes.c_char_p, [_vp]),
+    "plf_tree_set_math": (_i, [_vp, _i]),
+    "plf_tree_set_tuning": (_i, [_vp, _i]),
+    "plf_tree_tip_ptr": (_i, [_vp, _u, ctypes.POINTER(_vp)]),
+    "plf_tree_write_tip": (_i, [_vp, _u, _vp, _sz, _sz]),
+    "plf_tree_write_matrices": (_i, [_vp, _vp, _vp, _vp]),
+    "plf_tree_write_wgt": (_i, [_vp, _vp]),
+    "plf_tree_run_async": (_i, [_vp]),
+    "plf_tree_wait": (_i, [_vp]),
+    "plf_tree_read_root": (_i, [_vp, _vp, _vp, _sz, _sz]),
+    "plf_tree_total_scalings": (_i, [_vp, ctypes.POINTER(ctypes.c_longlong)]),
+    "plf_tree_info": (_i, [_vp, ctypes.POINTER(_u), ctypes.POINTER(_u), ctypes.POINTER(_sz),
+                           ctypes.POINTER(_sz)]),
+    "plf_tree_last_ms": (_i, [_vp, ctypes.POINTER(ctypes.c_float)]),
     "plf_kernel_info": (_i, [_i, _i] + [ctypes.POINTER(_i)] * 4),
     "plf_launch_count": (ctypes.c_ulonglong, []),
 }
@@ -449,3 +465,137 @@ def host_alloc(nbytes: int, dtype=np.uint8):
 
 def host_free(ptr: int):
     _check(load().plf_host_free(ptr))
+
+
+# ------------------------------------------------------------------------------------------
+# Chained newview over a tree (plf_tree_* of include/b200plf.h)
+# ------------------------------------------------------------------------------------------
+def balanced_tree(n_tips: int):
+    """(left, right) child arrays of a balanced binary tree over n_tips tips in post-order
+    (level by level: pairs of the previous level's nodes)."""
+    left, right, frontier, nxt = [], [], list(range(n_tips)), n_tips
+    while len(frontier) > 1:
+        new = []
+        for a in range(0, len(frontier) - 1, 2):
+            left.append(frontier[a])
+            right.append(frontier[a + 1])
+            new.append(nxt)
+            nxt += 1
+        if len(frontier) % 2:
+            new.append(frontier[-1])
+        frontier = new
+    return np.asarray(left, np.int32), np.asarray(right, np.int32)
+
+
+def random_tree(n_tips: int, seed: int = 0):
+    """Random rooted binary tree by repeatedly joining two random live nodes (post-order)."""
+    rng = np.random.RandomState(seed)
+    live, left, right, nxt = list(range(n_tips)), [], [], n_tips
+    while len(live) > 1:
+        i, j = sorted(rng.choice(len(live), 2, replace=False))
+        b = live.pop(j)
+        a = live.pop(i)
+        left.append(a)
+        right.append(b)
+        live.append(nxt)
+        nxt += 1
+    return np.asarray(left, np.int32), np.asarray(right, np.int32)
+
+
+class Tree:
+    """Post-order traversal of a rooted binary tree on one GPU: every inner node is one fused
+    newview of its two children; all nodes of one level run in one launch."""
+
+    def __init__(self, left, right, n_sites: int, device: int = 0):
+        self.lib = load()
+        self.left = np.ascontiguousarray(left, np.int32)
+        self.right = np.ascontiguousarray(right, np.int32)
+        self.n_inner = self.left.size
+        self.n_tips = self.n_inner + 1
+        self.n_sites = n_sites
+        self._t = _vp()
+        rc = self.lib.plf_tree_create(ctypes.byref(self._t), device, self.n_tips, _ptr(self.left),
+                                      _ptr(self.right), n_sites)
+        if rc != 0:
+            raise PlfError(rc, self.lib.plf_tree_last_error(None).decode())
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise PlfError(rc, self.lib.plf_tree_last_error(self._t).decode())
+
+    def close(self):
+        if self._t:
+            self.lib.plf_tree_destroy(self._t)
+            self._t = _vp()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_math(self, mode: int):
+        self._ck(self.lib.plf_tree_set_math(self._t, mode))
+
+    def set_tuning(self, u: int):
+        self._ck(self.lib.plf_tree_set_tuning(self._t, u))
+
+    def tip_ptr(self, tip: int) -> int:
+        p = _vp()
+        self._ck(self.lib.plf_tree_tip_ptr(self._t, tip, ctypes.byref(p)))
+        return p.value
+
+    def write_tip(self, tip: int, clv, offset: int = 0):
+        clv = np.ascontiguousarray(clv, np.float32)
+        self._ck(self.lib.plf_tree_write_tip(self._t, tip, _ptr(clv), clv.nbytes, offset))
+        self.wait()     # clv may be a temporary
+
+    def write_matrices(self, ev, p_left, p_right):
+        ev = np.ascontiguousarray(ev, np.float32).reshape(16)
+        pl = np.ascontiguousarray(p_left, np.float32).reshape(self.n_inner, 64)
+        pr = np.ascontiguousarray(p_right, np.float32).reshape(self.n_inner, 64)
+        self._ck(self.lib.plf_tree_write_matrices(self._t, _ptr(ev), _ptr(pl), _ptr(pr)))
+
+    def write_wgt(self, wgt):
+        if wgt is None:
+            self._ck(self.lib.plf_tree_write_wgt(self._t, None))
+        else:
+            wgt = np.ascontiguousarray(wgt, np.int32)
+            assert wgt.size == self.n_sites
+            self._ck(self.lib.plf_tree_write_wgt(self._t, _ptr(wgt)))
+
+    def run_async(self):
+        self._ck(self.lib.plf_tree_run_async(self._t))
+
+    def wait(self):
+        self._ck(self.lib.plf_tree_wait(self._t))
+
+    def read_root(self, first_site: int = 0, n: int | None = None):
+        n = self.n_sites - first_site if n is None else n
+        clv = np.empty((n, 16), np.float32)
+        cnt = np.empty(n, np.int32)
+        self._ck(self.lib.plf_tree_read_root(self._t, _ptr(clv), _ptr(cnt), first_site, n))
+        return clv, cnt
+
+    def total_scalings(self) -> int:
+        v = ctypes.c_longlong(0)
+        self._ck(self.lib.plf_tree_total_scalings(self._t, ctypes.byref(v)))
+        return v.value
+
+    def info(self):
+        lv, sl, db, tb = _u(0), _u(0), _sz(0), _sz(0)
+        self._ck(self.lib.plf_tree_info(self._t, ctypes.byref(lv), ctypes.byref(sl), ctypes.byref(db),
+                                        ctypes.byref(tb)))
+        return {"levels": lv.value, "clv_slots": sl.value, "device_bytes": db.value,
+                "traversal_bytes": tb.value}
+
+    def last_ms(self) -> float:
+        v = ctypes.c_float(0)
+        self._ck(self.lib.plf_tree_last_ms(self._t, ctypes.byref(v)))
+        return v.value

@@ -320,6 +320,12 @@ const char *plf_last_error(const plf_ctx *ctx)
 
 unsigned long long plf_launch_count(void) { return g_launches.load(); }
 
+}  // extern "C"
+
+void plf::count_launches(unsigned long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+extern "C" {
+
 int plf_device_count(int *count)
 {
     if (!count) return fail(nullptr, PLF_ERR_INVALID, "NULL count");

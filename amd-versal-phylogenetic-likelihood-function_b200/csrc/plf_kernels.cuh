@@ -459,6 +459,160 @@ constexpr size_t tma_smem_bytes()
 }
 
 // ---------------------------------------------------------------------------------------------
+// Variant 3 ("batch"): many independent newviews of the same site count in ONE launch, with
+// per-site scaler-COUNT accumulation -- the building block of a chained newview over a tree
+// (all inner nodes of one tree level are independent: BASELINE.json configs[4]).
+//
+// Same producer/consumer ring as plf_newview_tma.  The work list is the concatenation of the
+// stages of all ops; CTA b owns a contiguous run of it, so it changes op (and reloads the 48
+// matrix constants and the op's pointers) only a handful of times.  Per site the op additionally
+// reads the children's int32 scaler counts (NULL = tip = 0) and writes
+//     cnt3[i] = cnt1[i] + cnt2[i] + (site i rescaled ? 1 : 0)
+// which is what RAxML-style codes carry up the tree instead of the single byte of one call
+// (205 B/site/node: 193 + 12).
+// ---------------------------------------------------------------------------------------------
+struct BatchOp {
+    const float4 *x1;
+    const float4 *x2;
+    float4 *x3;
+    const int *cnt1;      // per-site scaler counts of the children; NULL for a tip
+    const int *cnt2;
+    int *cnt3;            // may be NULL
+    unsigned char *scaler;  // this newview's own 0/1 byte per site; may be NULL
+    const float *pl;      // P_left[64], P_right[64], EV[16] of this op
+    const float *pr;
+    const float *ev;
+};
+
+template <class M, int U, int WARPS, int DEPTH, int MINB>
+__global__ void __launch_bounds__((WARPS + 1) * 32, MINB)
+plf_newview_batch(const BatchOp *__restrict__ ops, int n_ops, size_t n,
+                  const int *__restrict__ wgt, unsigned long long *__restrict__ scaler_sum)
+{
+    constexpr int THREADS = (WARPS + 1) * 32;
+    constexpr int TILE = 8 * U;
+    constexpr int STAGE = WARPS * TILE;
+    constexpr int STAGE_F4 = STAGE * 4;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4 *s1 = reinterpret_cast<float4 *>(smem_raw);
+    float4 *s2 = s1 + (size_t)DEPTH * STAGE_F4;
+    uint64_t *full = reinterpret_cast<uint64_t *>(s2 + (size_t)DEPTH * STAGE_F4);
+    uint64_t *empty = full + DEPTH;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const size_t stages_per_op = (n + STAGE - 1) / STAGE;
+    const size_t total = stages_per_op * (size_t)n_ops;
+    const size_t per_cta = (total + gridDim.x - 1) / gridDim.x;
+    const size_t g_begin = (size_t)blockIdx.x * per_cta;
+    const size_t g_end = g_begin + per_cta < total ? g_begin + per_cta : total;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int d = 0; d < DEPTH; ++d) {
+            mbar_init(&full[d], 1);
+            mbar_init(&empty[d], WARPS);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    unsigned long long my_sum = 0;
+    if (g_begin < g_end) {
+        int op = (int)(g_begin / stages_per_op);
+        size_t st = g_begin - (size_t)op * stages_per_op;
+        if (warp == WARPS) {
+            // ===== producer =====
+            if (lane == 0) {
+                uint32_t slot = 0, phase = 0;
+                const float4 *x1 = ops[op].x1, *x2 = ops[op].x2;
+                for (size_t g = g_begin; g < g_end; ++g) {
+                    mbar_wait(&empty[slot], phase ^ 1u);
+                    const size_t s0 = st * STAGE;
+                    const size_t left = n - s0;
+                    const uint32_t bytes = (uint32_t)(left < (size_t)STAGE ? left : (size_t)STAGE) * 64u;
+                    mbar_arrive_expect_tx(&full[slot], 2u * bytes);
+                    bulk_g2s(s1 + slot * STAGE_F4, x1 + s0 * 4, bytes, &full[slot]);
+                    bulk_g2s(s2 + slot * STAGE_F4, x2 + s0 * 4, bytes, &full[slot]);
+                    if (++slot == DEPTH) {
+                        slot = 0;
+                        phase ^= 1u;
+                    }
+                    if (++st == stages_per_op && g + 1 < g_end) {
+                        st = 0;
+                        ++op;
+                        x1 = ops[op].x1;
+                        x2 = ops[op].x2;
+                    }
+                }
+            }
+        } else {
+            // ===== consumers =====
+            const int cat = lane & 3;
+            const int site_in_row = lane >> 2;
+            const uint32_t tile_off = warp * (TILE * 4) + lane;
+            CatConst c;
+            BatchOp o = ops[op];
+            load_cat_const(c, o.ev, o.pl, o.pr, cat, 0);
+            uint32_t slot = 0, phase = 0;
+            for (size_t g = g_begin; g < g_end; ++g) {
+                const size_t s0 = st * STAGE + (size_t)warp * TILE;     // first site of this warp's tile
+                const size_t s_lane = s0 + lane;                        // the site whose count this lane owns
+                const bool lane_live = lane < TILE && s_lane < n;
+                // children's scaler counts: issued before the wait so their latency overlaps it
+                int cnt = 0;
+                if (lane_live) {
+                    if (o.cnt1) cnt = __ldg(o.cnt1 + s_lane);
+                    if (o.cnt2) cnt += __ldg(o.cnt2 + s_lane);
+                }
+                const float4 *t1 = s1 + slot * STAGE_F4 + tile_off;
+                const float4 *t2 = s2 + slot * STAGE_F4 + tile_off;
+                mbar_wait(&full[slot], phase);
+                float4 a[U], b[U], r[U];
+                unsigned ballots[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    a[u] = t1[32 * u];
+                    b[u] = t2[32 * u];
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[slot]);
+                if (++slot == DEPTH) {
+                    slot = 0;
+                    phase ^= 1u;
+                }
+                float4 *out = o.x3 + s0 * 4 + lane;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const bool live = s0 + 8 * u + site_in_row < n;
+                    bool small = category_newview<M>(c, a[u], b[u], r[u]);
+                    ballots[u] = __ballot_sync(0xffffffffu, small && live);
+                    if (nibble_all(ballots[u], site_in_row)) rescale(r[u]);
+                    if (live) st_stream(out + 32 * u, r[u]);
+                }
+                if (lane_live) {
+                    unsigned bal = ballots[0];
+#pragma unroll
+                    for (int u = 1; u < U; ++u) bal = (lane >> 3) == u ? ballots[u] : bal;
+                    const bool scaled = nibble_all(bal, lane & 7);
+                    if (o.scaler) o.scaler[s_lane] = scaled ? 1 : 0;
+                    if (o.cnt3) o.cnt3[s_lane] = cnt + (scaled ? 1 : 0);
+                    if (scaled) my_sum += wgt ? (unsigned long long)(long long)wgt[s_lane] : 1ull;
+                }
+                if (++st == stages_per_op && g + 1 < g_end) {
+                    st = 0;
+                    ++op;
+                    o = ops[op];
+                    load_cat_const(c, o.ev, o.pl, o.pr, cat, 0);
+                }
+            }
+        }
+    }
+    if (scaler_sum) block_add_u64<THREADS>(my_sum, scaler_sum);
+}
+
+// ---------------------------------------------------------------------------------------------
 // INPUT_SRC=gen analogue: no CLV is read.  Every lane holds its category's slice of the constant
 // site pattern (mm2sleft_genDNAwindowComb.cpp:44-49 / mm2sright_...:45-50); an opaque register
 // move per site keeps the compiler from hoisting the (site-invariant) arithmetic out of the loop,

@@ -33,4 +33,7 @@ KernelSel select_ldg_fma(int u, int kind, int b, int threads);
 KernelSel select_tma_strict(int u, int d, int b, int threads);
 KernelSel select_tma_fma(int u, int d, int b, int threads);
 
+// process-wide count of kernel launches issued by this library (plf_launch_count)
+void count_launches(unsigned long long n);
+
 }  // namespace plf

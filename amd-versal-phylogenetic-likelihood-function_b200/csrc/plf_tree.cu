@@ -1,0 +1,453 @@
+// csrc/plf_tree.cu -- chained newview over a rooted binary tree (plf_tree_* of include/b200plf.h).
+//
+// The reference ends at a single newview call; this is the layer that calls the path in a
+// RAxML-like code (BASELINE.json configs[4]): a post-order traversal
+// where every inner node is one newview of its two children.  Design for B200:
+//   * the post-order list is cut into LEVELS (level = 1 + max level of the children); all nodes
+//     of a level are independent and run in ONE launch of plf_newview_batch, so a 1024-taxon tree
+//     costs ~10-40 launches instead of 1023 launch-bound ones;
+//   * the level launches (+ the counter reset) are captured once into a CUDA graph and replayed;
+//   * inner CLVs and their int32 scaler-count vectors live in a pool of slots that is recycled as
+//     soon as a node's parent has been computed, so device memory is tips + O(widest level);
+//   * per-site scaler counts are carried upwards: cnt[parent] = cnt[left] + cnt[right] + rescaled.
+#include "../../include/b200plf.h"
+#include "plf_kernels.cuh"
+#include "plf_registry.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <new>
+#include <string>
+#include <vector>
+
+struct plf_tree {
+    int device = 0;
+    unsigned n_tips = 0, n_inner = 0;
+    size_t n_sites = 0;
+    int math = PLF_MATH_STRICT;
+    int tune_u = 0;
+    int num_sms = 0;
+    std::vector<int> left, right;              // children ids per inner node
+    std::vector<std::vector<int>> levels;      // inner node indices per level, in execution order
+    std::vector<int> slot;                     // pool slot of each inner node
+    unsigned n_slots = 0;
+    float *d_tips = nullptr;                   // [n_tips][n_sites*16]
+    float *d_pool = nullptr;                   // [n_slots][n_sites*16]
+    int *d_counts = nullptr;                   // [n_slots][n_sites]
+    float *d_mats = nullptr;                   // EV[16] | P_left[n_inner][64] | P_right[n_inner][64]
+    int *d_wgt = nullptr;
+    bool use_wgt = false;
+    plf::BatchOp *d_ops = nullptr;             // all ops, level after level
+    std::vector<size_t> level_op_offset;
+    unsigned long long *d_sum = nullptr, *h_sum = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    int exec_math = -1, exec_u = -1;
+    bool exec_wgt = false;
+    bool ran = false;
+    std::string error;
+};
+
+namespace {
+
+thread_local std::string g_tree_error;
+
+int tfail(plf_tree *t, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (t) t->error = buf;
+    g_tree_error = buf;
+    return code;
+}
+
+#define TREE_CUDA(t, expr)                                                                        \
+    do {                                                                                          \
+        cudaError_t e__ = (expr);                                                                 \
+        if (e__ != cudaSuccess)                                                                   \
+            return tfail(t, e__ == cudaErrorMemoryAllocation ? PLF_ERR_NOMEM : PLF_ERR_CUDA,      \
+                         "%s failed: %s", #expr, cudaGetErrorString(e__));                        \
+    } while (0)
+
+using BatchFn = void (*)(const plf::BatchOp *, int, size_t, const int *, unsigned long long *);
+
+struct BatchSel {
+    BatchFn fn;
+    int threads;
+    size_t smem;
+    int stage;
+};
+
+template <class M>
+BatchSel batch_sel(int u)
+{
+    if (u == 1)
+        return {plf::plf_newview_batch<M, 1, 16, 4, 1>, 17 * 32, plf::tma_smem_bytes<1, 16, 4>(), 128};
+    return {plf::plf_newview_batch<M, 2, 16, 3, 1>, 17 * 32, plf::tma_smem_bytes<2, 16, 3>(), 256};
+}
+
+BatchSel pick_batch(int math, int u)
+{
+    return math == PLF_MATH_FMA ? batch_sel<plf::MathFma>(u) : batch_sel<plf::MathStrict>(u);
+}
+
+float *node_clv(plf_tree *t, int node)
+{
+    const size_t stride = t->n_sites * PLF_SITE_FLOATS;
+    return node < (int)t->n_tips ? t->d_tips + (size_t)node * stride
+                                 : t->d_pool + (size_t)t->slot[node - t->n_tips] * stride;
+}
+
+int *node_counts(plf_tree *t, int node)
+{
+    return node < (int)t->n_tips ? nullptr : t->d_counts + (size_t)t->slot[node - t->n_tips] * t->n_sites;
+}
+
+int launch_level(plf_tree *t, const BatchSel &k, size_t level, cudaStream_t s)
+{
+    const int n_ops = (int)t->levels[level].size();
+    const size_t stages = ((t->n_sites + k.stage - 1) / k.stage) * (size_t)n_ops;
+    size_t grid = (size_t)t->num_sms;
+    if (grid > stages) grid = stages;
+    k.fn<<<(int)grid, k.threads, k.smem, s>>>(t->d_ops + t->level_op_offset[level], n_ops, t->n_sites,
+                                              t->use_wgt ? t->d_wgt : nullptr, t->d_sum);
+    TREE_CUDA(t, cudaGetLastError());
+    return PLF_OK;
+}
+
+// (Re)capture the traversal: counter reset + one launch per level + read-back of the counter.
+int build_graph(plf_tree *t)
+{
+    int u = t->tune_u;
+    if (u == 0) {
+        // small per-level work: finer stages balance better over 148 CTAs
+        const size_t widest = t->levels.empty() ? 1 : t->levels[0].size();
+        u = (t->n_sites / 256) * widest >= (size_t)t->num_sms * 16 ? 2 : 1;
+    }
+    const BatchSel k = pick_batch(t->math, u);
+    TREE_CUDA(t, cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.smem));
+    if (t->exec) {
+        cudaGraphExecDestroy(t->exec);
+        t->exec = nullptr;
+    }
+    cudaGraph_t graph = nullptr;
+    TREE_CUDA(t, cudaStreamBeginCapture(t->stream, cudaStreamCaptureModeThreadLocal));
+    cudaError_t e = cudaMemsetAsync(t->d_sum, 0, sizeof(unsigned long long), t->stream);
+    int rc = PLF_OK;
+    for (size_t l = 0; l < t->levels.size() && e == cudaSuccess && rc == PLF_OK; ++l) rc = launch_level(t, k, l, t->stream);
+    if (e == cudaSuccess && rc == PLF_OK)
+        e = cudaMemcpyAsync(t->h_sum, t->d_sum, sizeof(unsigned long long), cudaMemcpyDeviceToHost, t->stream);
+    cudaError_t e2 = cudaStreamEndCapture(t->stream, &graph);
+    if (rc != PLF_OK) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+    }
+    if (e != cudaSuccess || e2 != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        return tfail(t, PLF_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+    }
+    e = cudaGraphInstantiate(&t->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return tfail(t, PLF_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    t->exec_math = t->math;
+    t->exec_u = t->tune_u;
+    t->exec_wgt = t->use_wgt;
+    return PLF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *plf_tree_last_error(const plf_tree *tree)
+{
+    if (tree) g_tree_error = tree->error;
+    return g_tree_error.c_str();
+}
+
+int plf_tree_create(plf_tree **out, int device, unsigned n_tips, const int *left, const int *right, size_t n_sites)
+{
+    if (!out) return tfail(nullptr, PLF_ERR_INVALID, "NULL tree out-pointer");
+    *out = nullptr;
+    if (n_tips < 2 || !left || !right || n_sites == 0)
+        return tfail(nullptr, PLF_ERR_INVALID, "need n_tips >= 2, child arrays and n_sites > 0");
+    if (n_sites > (SIZE_MAX / 128)) return tfail(nullptr, PLF_ERR_INVALID, "n_sites too large");
+    const unsigned n_inner = n_tips - 1;
+    // validate: post-order, every node except the root is used exactly once as a child
+    std::vector<int> used(n_tips + n_inner, 0);
+    for (unsigned k = 0; k < n_inner; ++k) {
+        for (int c : {left[k], right[k]}) {
+            if (c < 0 || c >= (int)(n_tips + k))
+                return tfail(nullptr, PLF_ERR_INVALID, "inner node %u: child id %d is not an earlier node", k, c);
+            if (used[c]++) return tfail(nullptr, PLF_ERR_INVALID, "node %d is the child of two nodes", c);
+        }
+        if (left[k] == right[k]) return tfail(nullptr, PLF_ERR_INVALID, "inner node %u has identical children", k);
+    }
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return tfail(nullptr, PLF_ERR_CUDA, "no CUDA device present (no CPU fallback)");
+    }
+    if (device < 0 || device >= count) return tfail(nullptr, PLF_ERR_INVALID, "device %d not present", device);
+    TREE_CUDA(nullptr, cudaSetDevice(device));
+
+    plf_tree *t = new (std::nothrow) plf_tree;
+    if (!t) return tfail(nullptr, PLF_ERR_NOMEM, "out of host memory");
+    t->device = device;
+    t->n_tips = n_tips;
+    t->n_inner = n_inner;
+    t->n_sites = n_sites;
+    t->left.assign(left, left + n_inner);
+    t->right.assign(right, right + n_inner);
+    cudaDeviceGetAttribute(&t->num_sms, cudaDevAttrMultiProcessorCount, device);
+
+    // levels
+    std::vector<int> level(n_tips + n_inner, 0);
+    int height = 0;
+    for (unsigned k = 0; k < n_inner; ++k) {
+        level[n_tips + k] = 1 + std::max(level[left[k]], level[right[k]]);
+        height = std::max(height, level[n_tips + k]);
+    }
+    t->levels.assign(height, {});
+    for (unsigned k = 0; k < n_inner; ++k) t->levels[level[n_tips + k] - 1].push_back((int)k);
+
+    // slot pool with recycling: a child's slot is released once its parent's level has run
+    t->slot.assign(n_inner, -1);
+    std::vector<int> free_slots;
+    unsigned next_slot = 0;
+    for (auto &lv : t->levels) {
+        for (int k : lv) {
+            if (!free_slots.empty()) {
+                t->slot[k] = free_slots.back();
+                free_slots.pop_back();
+            } else {
+                t->slot[k] = (int)next_slot++;
+            }
+        }
+        for (int k : lv)
+            for (int c : {t->left[k], t->right[k]})
+                if (c >= (int)n_tips) free_slots.push_back(t->slot[c - n_tips]);
+    }
+    t->n_slots = next_slot;
+
+    const size_t clv_bytes = n_sites * PLF_SITE_FLOATS * sizeof(float);
+    cudaError_t e = cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&t->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&t->ev1);
+    if (e == cudaSuccess) e = cudaMalloc(&t->d_tips, clv_bytes * n_tips);
+    if (e == cudaSuccess) e = cudaMalloc(&t->d_pool, clv_bytes * t->n_slots);
+    if (e == cudaSuccess) e = cudaMalloc(&t->d_counts, n_sites * sizeof(int) * t->n_slots);
+    if (e == cudaSuccess) e = cudaMalloc(&t->d_mats, (16 + 128 * (size_t)n_inner) * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&t->d_ops, sizeof(plf::BatchOp) * n_inner);
+    if (e == cudaSuccess) e = cudaMalloc(&t->d_sum, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMallocHost(&t->h_sum, sizeof(unsigned long long));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        tfail(nullptr, e == cudaErrorMemoryAllocation ? PLF_ERR_NOMEM : PLF_ERR_CUDA,
+              "tree allocation failed (%u tips, %u slots, %zu sites): %s", n_tips, t->n_slots, n_sites,
+              cudaGetErrorString(e));
+        plf_tree_destroy(t);
+        return e == cudaErrorMemoryAllocation ? PLF_ERR_NOMEM : PLF_ERR_CUDA;
+    }
+    *t->h_sum = 0;
+
+    // op descriptors, level after level
+    std::vector<plf::BatchOp> ops;
+    ops.reserve(n_inner);
+    for (auto &lv : t->levels) {
+        t->level_op_offset.push_back(ops.size());
+        for (int k : lv) {
+            plf::BatchOp o;
+            o.x1 = reinterpret_cast<const float4 *>(node_clv(t, t->left[k]));
+            o.x2 = reinterpret_cast<const float4 *>(node_clv(t, t->right[k]));
+            o.x3 = reinterpret_cast<float4 *>(node_clv(t, (int)n_tips + k));
+            o.cnt1 = node_counts(t, t->left[k]);
+            o.cnt2 = node_counts(t, t->right[k]);
+            o.cnt3 = node_counts(t, (int)n_tips + k);
+            o.scaler = nullptr;
+            o.ev = t->d_mats;
+            o.pl = t->d_mats + 16 + 64 * (size_t)k;
+            o.pr = t->d_mats + 16 + 64 * (size_t)n_inner + 64 * (size_t)k;
+            ops.push_back(o);
+        }
+    }
+    e = cudaMemcpy(t->d_ops, ops.data(), sizeof(plf::BatchOp) * ops.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        tfail(nullptr, PLF_ERR_CUDA, "op table upload failed: %s", cudaGetErrorString(e));
+        plf_tree_destroy(t);
+        return PLF_ERR_CUDA;
+    }
+    *out = t;
+    return PLF_OK;
+}
+
+int plf_tree_destroy(plf_tree *t)
+{
+    if (!t) return PLF_OK;
+    cudaSetDevice(t->device);
+    if (t->stream) cudaStreamSynchronize(t->stream);
+    if (t->exec) cudaGraphExecDestroy(t->exec);
+    cudaFree(t->d_tips);
+    cudaFree(t->d_pool);
+    cudaFree(t->d_counts);
+    cudaFree(t->d_mats);
+    cudaFree(t->d_wgt);
+    cudaFree(t->d_ops);
+    cudaFree(t->d_sum);
+    if (t->h_sum) cudaFreeHost(t->h_sum);
+    if (t->ev0) cudaEventDestroy(t->ev0);
+    if (t->ev1) cudaEventDestroy(t->ev1);
+    if (t->stream) cudaStreamDestroy(t->stream);
+    delete t;
+    return PLF_OK;
+}
+
+int plf_tree_set_math(plf_tree *t, int math_mode)
+{
+    if (!t) return tfail(nullptr, PLF_ERR_INVALID, "NULL tree");
+    if (math_mode != PLF_MATH_STRICT && math_mode != PLF_MATH_FMA) return tfail(t, PLF_ERR_INVALID, "unknown math mode %d", math_mode);
+    t->math = math_mode;
+    return PLF_OK;
+}
+
+int plf_tree_set_tuning(plf_tree *t, int u)
+{
+    if (!t) return tfail(nullptr, PLF_ERR_INVALID, "NULL tree");
+    if (u < 0 || u > 2) return tfail(t, PLF_ERR_INVALID, "tuning u must be 0, 1 or 2");
+    t->tune_u = u;
+    return PLF_OK;
+}
+
+int plf_tree_tip_ptr(plf_tree *t, unsigned tip, float **clv)
+{
+    if (!t || !clv) return tfail(t, PLF_ERR_INVALID, "NULL argument");
+    if (tip >= t->n_tips) return tfail(t, PLF_ERR_INVALID, "tip %u out of range (%u tips)", tip, t->n_tips);
+    *clv = node_clv(t, (int)tip);
+    return PLF_OK;
+}
+
+int plf_tree_write_tip(plf_tree *t, unsigned tip, const float *clv, size_t bytes, size_t offset)
+{
+    if (!t) return tfail(nullptr, PLF_ERR_INVALID, "NULL tree");
+    if (tip >= t->n_tips) return tfail(t, PLF_ERR_INVALID, "tip %u out of range (%u tips)", tip, t->n_tips);
+    const size_t cap = t->n_sites * PLF_SITE_FLOATS * sizeof(float);
+    if (offset > cap || bytes > cap - offset) return tfail(t, PLF_ERR_INVALID, "write exceeds the tip CLV (%zu bytes)", cap);
+    if (bytes == 0) return PLF_OK;
+    if (!clv) return tfail(t, PLF_ERR_INVALID, "NULL host buffer");
+    TREE_CUDA(t, cudaSetDevice(t->device));
+    TREE_CUDA(t, cudaMemcpyAsync(reinterpret_cast<char *>(node_clv(t, (int)tip)) + offset, clv, bytes,
+                                 cudaMemcpyHostToDevice, t->stream));
+    return PLF_OK;
+}
+
+int plf_tree_write_matrices(plf_tree *t, const float *ev, const float *p_left, const float *p_right)
+{
+    if (!t || !ev || !p_left || !p_right) return tfail(t, PLF_ERR_INVALID, "NULL argument");
+    TREE_CUDA(t, cudaSetDevice(t->device));
+    const size_t pb = 64 * (size_t)t->n_inner * sizeof(float);
+    TREE_CUDA(t, cudaMemcpyAsync(t->d_mats, ev, 16 * sizeof(float), cudaMemcpyHostToDevice, t->stream));
+    TREE_CUDA(t, cudaMemcpyAsync(t->d_mats + 16, p_left, pb, cudaMemcpyHostToDevice, t->stream));
+    TREE_CUDA(t, cudaMemcpyAsync(t->d_mats + 16 + 64 * (size_t)t->n_inner, p_right, pb, cudaMemcpyHostToDevice, t->stream));
+    TREE_CUDA(t, cudaStreamSynchronize(t->stream));     // host arrays may be pageable temporaries
+    return PLF_OK;
+}
+
+int plf_tree_write_wgt(plf_tree *t, const int *wgt)
+{
+    if (!t) return tfail(nullptr, PLF_ERR_INVALID, "NULL tree");
+    if (!wgt) {
+        t->use_wgt = false;
+        return PLF_OK;
+    }
+    TREE_CUDA(t, cudaSetDevice(t->device));
+    if (!t->d_wgt) TREE_CUDA(t, cudaMalloc(&t->d_wgt, t->n_sites * sizeof(int)));
+    TREE_CUDA(t, cudaMemcpyAsync(t->d_wgt, wgt, t->n_sites * sizeof(int), cudaMemcpyHostToDevice, t->stream));
+    TREE_CUDA(t, cudaStreamSynchronize(t->stream));
+    t->use_wgt = true;
+    return PLF_OK;
+}
+
+int plf_tree_run_async(plf_tree *t)
+{
+    if (!t) return tfail(nullptr, PLF_ERR_INVALID, "NULL tree");
+    TREE_CUDA(t, cudaSetDevice(t->device));
+    if (!t->exec || t->exec_math != t->math || t->exec_u != t->tune_u || t->exec_wgt != t->use_wgt) {
+        int rc = build_graph(t);
+        if (rc != PLF_OK) return rc;
+    }
+    TREE_CUDA(t, cudaEventRecord(t->ev0, t->stream));
+    TREE_CUDA(t, cudaGraphLaunch(t->exec, t->stream));
+    TREE_CUDA(t, cudaEventRecord(t->ev1, t->stream));
+    plf::count_launches(t->levels.size());
+    t->ran = true;
+    return PLF_OK;
+}
+
+int plf_tree_wait(plf_tree *t)
+{
+    if (!t) return tfail(nullptr, PLF_ERR_INVALID, "NULL tree");
+    TREE_CUDA(t, cudaSetDevice(t->device));
+    TREE_CUDA(t, cudaStreamSynchronize(t->stream));
+    return PLF_OK;
+}
+
+int plf_tree_read_root(plf_tree *t, float *clv, int *scaler_counts, size_t first_site, size_t n)
+{
+    if (!t) return tfail(nullptr, PLF_ERR_INVALID, "NULL tree");
+    if (!t->ran) return tfail(t, PLF_ERR_STATE, "tree has not been run");
+    if (first_site > t->n_sites || n > t->n_sites - first_site) return tfail(t, PLF_ERR_INVALID, "site range out of bounds");
+    TREE_CUDA(t, cudaSetDevice(t->device));
+    const int root = (int)(t->n_tips + t->n_inner - 1);
+    if (clv && n)
+        TREE_CUDA(t, cudaMemcpyAsync(clv, node_clv(t, root) + first_site * PLF_SITE_FLOATS, n * PLF_SITE_FLOATS * sizeof(float),
+                                     cudaMemcpyDeviceToHost, t->stream));
+    if (scaler_counts && n)
+        TREE_CUDA(t, cudaMemcpyAsync(scaler_counts, node_counts(t, root) + first_site, n * sizeof(int),
+                                     cudaMemcpyDeviceToHost, t->stream));
+    TREE_CUDA(t, cudaStreamSynchronize(t->stream));
+    return PLF_OK;
+}
+
+int plf_tree_total_scalings(plf_tree *t, long long *total)
+{
+    if (!t || !total) return tfail(t, PLF_ERR_INVALID, "NULL argument");
+    if (!t->ran) return tfail(t, PLF_ERR_STATE, "tree has not been run");
+    int rc = plf_tree_wait(t);
+    if (rc != PLF_OK) return rc;
+    *total = (long long)*t->h_sum;
+    return PLF_OK;
+}
+
+int plf_tree_info(plf_tree *t, unsigned *levels, unsigned *clv_slots, size_t *device_bytes, size_t *traversal_bytes)
+{
+    if (!t) return tfail(nullptr, PLF_ERR_INVALID, "NULL tree");
+    if (levels) *levels = (unsigned)t->levels.size();
+    if (clv_slots) *clv_slots = t->n_slots;
+    if (device_bytes)
+        *device_bytes = t->n_sites * 64 * ((size_t)t->n_tips + t->n_slots) + t->n_sites * 4 * (size_t)t->n_slots;
+    if (traversal_bytes) {
+        // 193 B per site per node + 4 B per count vector actually read (inner children) or written
+        size_t inner_children = 0;
+        for (unsigned k = 0; k < t->n_inner; ++k)
+            inner_children += (t->left[k] >= (int)t->n_tips) + (t->right[k] >= (int)t->n_tips);
+        *traversal_bytes = t->n_sites * (192 * (size_t)t->n_inner + 4 * ((size_t)t->n_inner + inner_children));
+    }
+    return PLF_OK;
+}
+
+int plf_tree_last_ms(plf_tree *t, float *ms)
+{
+    if (!t || !ms) return tfail(t, PLF_ERR_INVALID, "NULL argument");
+    if (!t->ran) return tfail(t, PLF_ERR_STATE, "tree has not been run");
+    TREE_CUDA(t, cudaSetDevice(t->device));
+    TREE_CUDA(t, cudaEventSynchronize(t->ev1));
+    TREE_CUDA(t, cudaEventElapsedTime(ms, t->ev0, t->ev1));
+    return PLF_OK;
+}
+
+}  // extern "C"

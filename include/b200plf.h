@@ -191,6 +191,48 @@ int plf_generate_device(float *x1, float *x2, size_t first_site, size_t n, uint6
 /* The same generator evaluated on the host for a site range (for verification of slices). */
 int plf_generate_host(float *x1, float *x2, size_t first_site, size_t n, uint64_t seed);
 
+/* ---- chained newview over a tree (the caller of the path; SURVEY.md section 8f, BASELINE.json
+ *      configs[4]).  The reference stops at one newview call (its README lists the surrounding
+ *      RAxML machinery only as the origin of plf(), README.md:188-189,207-208); this is the natural
+ *      next layer: a post-order traversal in which every inner node is one newview of its two
+ *      children, per-site scaler COUNTS are carried upwards, and all nodes of one tree level run
+ *      in a single launch.                                                                   ---- */
+typedef struct plf_tree plf_tree;
+
+/* Rooted binary tree in post-order.  Node ids: 0..n_tips-1 are tips, n_tips+k is inner node k.
+ * Inner node k (0 <= k < n_tips-1) has children left[k], right[k], each a tip or an inner node
+ * with a smaller index; the last inner node is the root.  Allocates all device memory:
+ * n_tips tip CLVs, a recycled pool of inner CLVs + int32 scaler-count vectors, matrices.       */
+int plf_tree_create(plf_tree **tree, int device, unsigned n_tips, const int *left, const int *right,
+                    size_t n_sites);
+int plf_tree_destroy(plf_tree *tree);
+const char *plf_tree_last_error(const plf_tree *tree);
+int plf_tree_set_math(plf_tree *tree, int math_mode);
+/* 0 = automatic; otherwise U of the batch kernel (1: 128-site stages, 2: 256-site stages).   */
+int plf_tree_set_tuning(plf_tree *tree, int u);
+/* Device pointer of a tip CLV (n_sites*16 floats) for callers that produce tips on the device. */
+int plf_tree_tip_ptr(plf_tree *tree, unsigned tip, float **clv);
+/* Host -> device copy into a tip CLV (bytes at byte offset), asynchronous on the tree's stream. */
+int plf_tree_write_tip(plf_tree *tree, unsigned tip, const float *clv, size_t bytes, size_t offset);
+/* EV[16] shared by all nodes; P_left/P_right[(n_tips-1)][64], one pair per inner node.         */
+int plf_tree_write_matrices(plf_tree *tree, const float *ev, const float *p_left, const float *p_right);
+/* Site weights for the total (NULL = all ones). */
+int plf_tree_write_wgt(plf_tree *tree, const int *wgt);
+/* Enqueue the whole traversal (one launch per tree level, replayed from a CUDA graph). */
+int plf_tree_run_async(plf_tree *tree);
+int plf_tree_wait(plf_tree *tree);
+/* Root CLV (16 floats/site) and accumulated per-site scaler counts for sites [first, first+n). */
+int plf_tree_read_root(plf_tree *tree, float *clv, int *scaler_counts, size_t first_site, size_t n);
+/* Debug/verification: CLV and counts of any inner node are only defined for the root after a run
+ * (inner buffers are recycled); this returns sum over all newviews of sum_i wgt[i]*rescaled(i). */
+int plf_tree_total_scalings(plf_tree *tree, long long *total);
+/* Schedule facts: number of levels (= launches per traversal), CLV slots in the recycled pool,
+ * device bytes held, and algorithmic HBM bytes one traversal moves (205 B per site per node).  */
+int plf_tree_info(plf_tree *tree, unsigned *levels, unsigned *clv_slots, size_t *device_bytes,
+                  size_t *traversal_bytes);
+/* Device time of the last traversal in milliseconds (events around the graph launch). */
+int plf_tree_last_ms(plf_tree *tree, float *ms);
+
 /* Largest tile the library was compiled for, number of SMs etc. -- introspection for benches. */
 int plf_kernel_info(int variant, int math_mode, int *regs_per_thread, int *threads_per_block,
                     int *blocks_per_sm, int *num_sms);

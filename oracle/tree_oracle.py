@@ -1,0 +1,26 @@
+"""oracle/tree_oracle.py -- chained newview over a tree on the CPU.  TEST INFRASTRUCTURE ONLY.
+
+The reference has no tree code; a traversal is, by definition, the reference's plf()
+(app/src/plf.cpp:8-68, here through the pinned C restatement) applied to every inner node in
+post-order, with the per-site scaler bytes of each call summed up the tree."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def traverse(coracle, left, right, tips, ev, p_left, p_right, wgt=None):
+    """tips: [n_tips, n, 16].  Returns (root CLV [n,16], per-site counts [n], total scalings)."""
+    n_tips = tips.shape[0]
+    clv = {i: tips[i] for i in range(n_tips)}
+    cnt = {i: np.zeros(tips.shape[1], np.int32) for i in range(n_tips)}
+    total = 0
+    for k, (a, b) in enumerate(zip(left, right)):
+        x3, sc, inc = coracle.newview(clv[int(a)], clv[int(b)], ev, p_left[k], p_right[k], wgt)
+        node = n_tips + k
+        clv[node] = x3
+        cnt[node] = cnt[int(a)] + cnt[int(b)] + sc.astype(np.int32)
+        total += inc
+        for c in (int(a), int(b)):          # children are dead once their parent exists
+            del clv[c], cnt[c]
+    root = n_tips + len(left) - 1
+    return clv[root], cnt[root], total

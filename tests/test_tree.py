@@ -1,0 +1,110 @@
+"""Chained newview over a tree (BASELINE.json configs[4]): the level-batched CUDA traversal, through
+the C ABI, against the oracle applied node by node in post-order.  Strict math: bit-exact CLVs and
+identical per-site scaler counts."""
+from __future__ import annotations
+
+import numpy as np
+import pytest
+
+from conftest import bits, first_mismatch
+from oracle import tree_oracle
+
+
+def tree_inputs(n_tips, n, seed, scale_lo=-14.0):
+    """Random positive tip CLVs whose magnitude varies per (tip, site) so that rescaling events
+    happen at different depths of the tree; P/EV positive as in the reference stimulus."""
+    rng = np.random.RandomState(seed)
+    tips = (rng.random_sample((n_tips, n, 16)) * 10.0 ** rng.uniform(scale_lo, 0, (n_tips, n, 1))).astype(np.float32)
+    ev = rng.random_sample(16).astype(np.float32)
+    pl = rng.random_sample((n_tips - 1, 64)).astype(np.float32)
+    pr = rng.random_sample((n_tips - 1, 64)).astype(np.float32)
+    wgt = rng.randint(1, 6, n).astype(np.int32)
+    return tips, ev, pl, pr, wgt
+
+
+def test_tree_builders_are_postorder(pkg):
+    for n_tips in (2, 3, 7, 64, 1024):
+        for left, right in (pkg.balanced_tree(n_tips), pkg.random_tree(n_tips, 1)):
+            assert left.size == right.size == n_tips - 1
+            seen = set()
+            for k, (a, b) in enumerate(zip(left, right)):
+                assert a < n_tips + k and b < n_tips + k and a != b
+                assert a not in seen and b not in seen
+                seen.update((int(a), int(b)))
+            assert len(seen) == 2 * (n_tips - 1)      # everything but the root is somebody's child
+
+
+def test_tree_oracle_counts_are_sums_of_bytes(coracle):
+    tips, ev, pl, pr, wgt = tree_inputs(8, 50, 0)
+    left, right = np.array([0, 2, 8, 4, 6, 11, 10], np.int32), np.array([1, 3, 9, 5, 7, 12, 13], np.int32)
+    root, cnt, total = tree_oracle.traverse(coracle, left, right, tips, ev, pl, pr, wgt)
+    assert root.shape == (50, 16) and cnt.min() >= 0 and total >= int((cnt * wgt).sum()) - 0
+    assert total == int((cnt.astype(np.int64) * wgt).sum())      # every event reaches the root count
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,n_tips,n", [("balanced", 64, 3001), ("random", 33, 1000), ("balanced", 2, 129),
+                                             ("random", 257, 517), ("caterpillar", 12, 4096)])
+@pytest.mark.parametrize("u", [0, 1, 2])
+def test_tree_traversal_matches_oracle(pkg, coracle, shape, n_tips, n, u):
+    if shape == "balanced":
+        left, right = pkg.balanced_tree(n_tips)
+    elif shape == "random":
+        left, right = pkg.random_tree(n_tips, seed=n)
+    else:       # caterpillar: every level has one node -> n_tips-1 launches
+        left = np.array([0] + [n_tips + k for k in range(n_tips - 2)], np.int32)
+        right = np.arange(1, n_tips, dtype=np.int32)
+    tips, ev, pl, pr, wgt = tree_inputs(n_tips, n, seed=n_tips)
+    o_root, o_cnt, o_total = tree_oracle.traverse(coracle, left, right, tips, ev, pl, pr, wgt)
+    assert o_cnt.max() >= 2, "stimulus should rescale repeatedly along the tree"
+    with pkg.Tree(left, right, n) as t:
+        t.set_tuning(u)
+        for i in range(n_tips):
+            t.write_tip(i, tips[i])
+        t.write_matrices(ev, pl, pr)
+        t.write_wgt(wgt)
+        for _ in range(2):          # replay the captured graph: buffers are recycled correctly
+            t.run_async()
+            root, cnt = t.read_root()
+            assert np.array_equal(bits(root), bits(o_root)), first_mismatch(root, o_root)
+            assert np.array_equal(cnt, o_cnt)
+            assert t.total_scalings() == o_total
+        info = t.info()
+        assert info["levels"] >= int(np.ceil(np.log2(n_tips))) and info["clv_slots"] <= n_tips - 1
+        if shape == "balanced" and n_tips == 64:
+            assert info["levels"] == 6 and info["clv_slots"] <= 48      # recycling: 32 + 16 live at most
+        assert t.last_ms() > 0
+
+
+@pytest.mark.gpu
+def test_tree_fma_mode_within_tolerance(pkg, coracle):
+    left, right = pkg.balanced_tree(16)
+    tips, ev, pl, pr, wgt = tree_inputs(16, 2000, seed=5, scale_lo=-3.0)
+    o_root, o_cnt, _ = tree_oracle.traverse(coracle, left, right, tips, ev, pl, pr, None)
+    with pkg.Tree(left, right, 2000) as t:
+        t.set_math(pkg.MATH_FMA)
+        for i in range(16):
+            t.write_tip(i, tips[i])
+        t.write_matrices(ev, pl, pr)
+        t.run_async()
+        root, cnt = t.read_root()
+    same = cnt == o_cnt
+    assert same.mean() > 0.999          # threshold-boundary sites may differ by one rescale
+    rel = np.abs(root[same].astype(np.float64) - o_root[same]) / np.maximum(np.abs(o_root[same]), 1e-300)
+    assert rel.max() <= 4 * 1e-5        # error compounds over log2(16) = 4 chained newviews
+
+
+@pytest.mark.gpu
+def test_tree_error_behaviour(pkg):
+    with pytest.raises(pkg.PlfError):
+        pkg.Tree(np.array([0, 1], np.int32), np.array([1, 3], np.int32), 10)      # node 1 used twice
+    with pytest.raises(pkg.PlfError):
+        pkg.Tree(np.array([0], np.int32), np.array([5], np.int32), 10)            # child id not earlier
+    left, right = pkg.balanced_tree(4)
+    with pkg.Tree(left, right, 10) as t:
+        with pytest.raises(pkg.PlfError):
+            t.read_root()                                                         # not run yet
+        with pytest.raises(pkg.PlfError):
+            t.write_tip(4, np.zeros((10, 16), np.float32))                        # tip out of range
+        with pytest.raises(pkg.PlfError):
+            t.write_tip(0, np.zeros((11, 16), np.float32))                        # too large
