@@ -95,7 +95,7 @@ PROTOTYPES = {
     "plf_tree_destroy": (_i, [_vp]),
     "plf_tree_last_error": (ctypes.c_char_p, [_vp]),
     "plf_tree_set_math": (_i, [_vp, _i]),
-    "plf_tree_set_tuning": (_i, [_vp, _i]),
+    "plf_tree_set_tuning": (_i, [_vp, _i, _i]),
     "plf_tree_tip_ptr": (_i, [_vp, _u, ctypes.POINTER(_vp)]),
     "plf_tree_write_tip": (_i, [_vp, _u, _vp, _sz, _sz]),
     "plf_tree_write_matrices": (_i, [_vp, _vp, _vp, _vp]),
@@ -543,8 +543,8 @@ class Tree:
     def set_math(self, mode: int):
         self._ck(self.lib.plf_tree_set_math(self._t, mode))
 
-    def set_tuning(self, u: int):
-        self._ck(self.lib.plf_tree_set_tuning(self._t, u))
+    def set_tuning(self, u: int = 0, chunk: int = 0):
+        self._ck(self.lib.plf_tree_set_tuning(self._t, u, chunk))
 
     def tip_ptr(self, tip: int) -> int:
         p = _vp()

@@ -487,7 +487,8 @@ struct BatchOp {
 template <class M, int U, int WARPS, int DEPTH, int MINB>
 __global__ void __launch_bounds__((WARPS + 1) * 32, MINB)
 plf_newview_batch(const BatchOp *__restrict__ ops, int n_ops, size_t n,
-                  const int *__restrict__ wgt, unsigned long long *__restrict__ scaler_sum)
+                  const int *__restrict__ wgt, unsigned long long *__restrict__ scaler_sum,
+                  unsigned chunk)
 {
     constexpr int THREADS = (WARPS + 1) * 32;
     constexpr int TILE = 8 * U;
@@ -502,11 +503,14 @@ plf_newview_batch(const BatchOp *__restrict__ ops, int n_ops, size_t n,
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const size_t stages_per_op = (n + STAGE - 1) / STAGE;
-    const size_t total = stages_per_op * (size_t)n_ops;
-    const size_t per_cta = (total + gridDim.x - 1) / gridDim.x;
-    const size_t g_begin = (size_t)blockIdx.x * per_cta;
-    const size_t g_end = g_begin + per_cta < total ? g_begin + per_cta : total;
+    // The work list: stage g of the launch is stage (g % spo) of op (g / spo).  It is dealt out in
+    // chunks of `chunk` consecutive stages, chunk q to CTA q % gridDim.x: chunk = 1 interleaves the
+    // CTAs stage by stage (all SMs stream through the same few MB at any time), a large chunk gives
+    // every CTA long runs inside one op (fewer constant reloads when ops are short).
+    const uint32_t spo = (uint32_t)((n + STAGE - 1) / STAGE);          // stages per op
+    const uint32_t full_stages = (uint32_t)(n / STAGE);                // stages [0, full_stages) are complete
+    const uint32_t total = spo * (uint32_t)n_ops;
+    const uint32_t n_chunks = (total + chunk - 1) / chunk;
 
     if (threadIdx.x == 0) {
 #pragma unroll
@@ -519,19 +523,19 @@ plf_newview_batch(const BatchOp *__restrict__ ops, int n_ops, size_t n,
     __syncthreads();
 
     unsigned long long my_sum = 0;
-    if (g_begin < g_end) {
-        int op = (int)(g_begin / stages_per_op);
-        size_t st = g_begin - (size_t)op * stages_per_op;
-        if (warp == WARPS) {
-            // ===== producer =====
-            if (lane == 0) {
-                uint32_t slot = 0, phase = 0;
+    if (warp == WARPS) {
+        // ===== producer =====
+        if (lane == 0) {
+            uint32_t slot = 0, phase = 0;
+            for (uint32_t q = blockIdx.x; q < n_chunks; q += gridDim.x) {
+                const uint32_t g0 = q * chunk;
+                const uint32_t g1 = g0 + chunk < total ? g0 + chunk : total;
+                uint32_t op = g0 / spo, st = g0 - op * spo;
                 const float4 *x1 = ops[op].x1, *x2 = ops[op].x2;
-                for (size_t g = g_begin; g < g_end; ++g) {
+                for (uint32_t g = g0; g < g1; ++g) {
                     mbar_wait(&empty[slot], phase ^ 1u);
-                    const size_t s0 = st * STAGE;
-                    const size_t left = n - s0;
-                    const uint32_t bytes = (uint32_t)(left < (size_t)STAGE ? left : (size_t)STAGE) * 64u;
+                    const size_t s0 = (size_t)st * STAGE;
+                    const uint32_t bytes = (st < full_stages ? (uint32_t)STAGE : (uint32_t)(n - s0)) * 64u;
                     mbar_arrive_expect_tx(&full[slot], 2u * bytes);
                     bulk_g2s(s1 + slot * STAGE_F4, x1 + s0 * 4, bytes, &full[slot]);
                     bulk_g2s(s2 + slot * STAGE_F4, x2 + s0 * 4, bytes, &full[slot]);
@@ -539,7 +543,7 @@ plf_newview_batch(const BatchOp *__restrict__ ops, int n_ops, size_t n,
                         slot = 0;
                         phase ^= 1u;
                     }
-                    if (++st == stages_per_op && g + 1 < g_end) {
+                    if (++st == spo && g + 1 < g1) {
                         st = 0;
                         ++op;
                         x1 = ops[op].x1;
@@ -547,19 +551,30 @@ plf_newview_batch(const BatchOp *__restrict__ ops, int n_ops, size_t n,
                     }
                 }
             }
-        } else {
-            // ===== consumers =====
-            const int cat = lane & 3;
-            const int site_in_row = lane >> 2;
-            const uint32_t tile_off = warp * (TILE * 4) + lane;
-            CatConst c;
-            BatchOp o = ops[op];
-            load_cat_const(c, o.ev, o.pl, o.pr, cat, 0);
-            uint32_t slot = 0, phase = 0;
-            for (size_t g = g_begin; g < g_end; ++g) {
-                const size_t s0 = st * STAGE + (size_t)warp * TILE;     // first site of this warp's tile
-                const size_t s_lane = s0 + lane;                        // the site whose count this lane owns
-                const bool lane_live = lane < TILE && s_lane < n;
+        }
+    } else {
+        // ===== consumers =====
+        const int cat = lane & 3;
+        const int site_in_row = lane >> 2;
+        const uint32_t tile_off = warp * (TILE * 4) + lane;
+        CatConst c;
+        BatchOp o;
+        uint32_t cur_op = 0xffffffffu;
+        uint32_t slot = 0, phase = 0;
+        for (uint32_t q = blockIdx.x; q < n_chunks; q += gridDim.x) {
+            const uint32_t g0 = q * chunk;
+            const uint32_t g1 = g0 + chunk < total ? g0 + chunk : total;
+            uint32_t op = g0 / spo, st = g0 - op * spo;
+            for (uint32_t g = g0; g < g1; ++g) {
+                if (op != cur_op) {                      // new op: its pointers and 48 constants
+                    o = ops[op];
+                    load_cat_const(c, o.ev, o.pl, o.pr, cat, 0);
+                    cur_op = op;
+                }
+                const size_t s0 = (size_t)st * STAGE + (size_t)warp * TILE;   // first site of this warp's tile
+                const size_t s_lane = s0 + lane;                              // the site whose count this lane owns
+                const bool complete = st < full_stages;
+                const bool lane_live = lane < TILE && (complete || s_lane < n);
                 // children's scaler counts: issued before the wait so their latency overlaps it
                 int cnt = 0;
                 if (lane_live) {
@@ -583,13 +598,23 @@ plf_newview_batch(const BatchOp *__restrict__ ops, int n_ops, size_t n,
                     phase ^= 1u;
                 }
                 float4 *out = o.x3 + s0 * 4 + lane;
+                if (complete) {
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const bool live = s0 + 8 * u + site_in_row < n;
-                    bool small = category_newview<M>(c, a[u], b[u], r[u]);
-                    ballots[u] = __ballot_sync(0xffffffffu, small && live);
-                    if (nibble_all(ballots[u], site_in_row)) rescale(r[u]);
-                    if (live) st_stream(out + 32 * u, r[u]);
+                    for (int u = 0; u < U; ++u) {
+                        bool small = category_newview<M>(c, a[u], b[u], r[u]);
+                        ballots[u] = __ballot_sync(0xffffffffu, small);
+                        if (nibble_all(ballots[u], site_in_row)) rescale(r[u]);
+                        st_stream(out + 32 * u, r[u]);
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const bool live = s0 + 8 * u + site_in_row < n;
+                        bool small = category_newview<M>(c, a[u], b[u], r[u]);
+                        ballots[u] = __ballot_sync(0xffffffffu, small && live);
+                        if (nibble_all(ballots[u], site_in_row)) rescale(r[u]);
+                        if (live) st_stream(out + 32 * u, r[u]);
+                    }
                 }
                 if (lane_live) {
                     unsigned bal = ballots[0];
@@ -600,11 +625,9 @@ plf_newview_batch(const BatchOp *__restrict__ ops, int n_ops, size_t n,
                     if (o.cnt3) o.cnt3[s_lane] = cnt + (scaled ? 1 : 0);
                     if (scaled) my_sum += wgt ? (unsigned long long)(long long)wgt[s_lane] : 1ull;
                 }
-                if (++st == stages_per_op && g + 1 < g_end) {
+                if (++st == spo) {
                     st = 0;
                     ++op;
-                    o = ops[op];
-                    load_cat_const(c, o.ev, o.pl, o.pr, cat, 0);
                 }
             }
         }

@@ -27,6 +27,7 @@ struct plf_tree {
     size_t n_sites = 0;
     int math = PLF_MATH_STRICT;
     int tune_u = 0;
+    int tune_chunk = 0;
     int num_sms = 0;
     std::vector<int> left, right;              // children ids per inner node
     std::vector<std::vector<int>> levels;      // inner node indices per level, in execution order
@@ -44,7 +45,7 @@ struct plf_tree {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaGraphExec_t exec = nullptr;
-    int exec_math = -1, exec_u = -1;
+    int exec_math = -1, exec_u = -1, exec_chunk = -1;
     bool exec_wgt = false;
     bool ran = false;
     std::string error;
@@ -74,7 +75,7 @@ int tfail(plf_tree *t, int code, const char *fmt, ...)
                          "%s failed: %s", #expr, cudaGetErrorString(e__));                        \
     } while (0)
 
-using BatchFn = void (*)(const plf::BatchOp *, int, size_t, const int *, unsigned long long *);
+using BatchFn = void (*)(const plf::BatchOp *, int, size_t, const int *, unsigned long long *, unsigned);
 
 struct BatchSel {
     BatchFn fn;
@@ -111,11 +112,18 @@ int *node_counts(plf_tree *t, int node)
 int launch_level(plf_tree *t, const BatchSel &k, size_t level, cudaStream_t s)
 {
     const int n_ops = (int)t->levels[level].size();
-    const size_t stages = ((t->n_sites + k.stage - 1) / k.stage) * (size_t)n_ops;
+    const size_t spo = (t->n_sites + k.stage - 1) / k.stage;
+    const size_t stages = spo * (size_t)n_ops;
+    if (stages >= (1ull << 31)) return tfail(t, PLF_ERR_INVALID, "level %zu has too many stages (%zu)", level, stages);
     size_t grid = (size_t)t->num_sms;
     if (grid > stages) grid = stages;
+    // chunk of consecutive stages dealt to one CTA at a time (see plf_newview_batch).  Auto: interleave
+    // stage by stage when an op is long enough that a CTA revisits it many times, otherwise runs of
+    // about a quarter op so that the 48 constants are reloaded rarely.
+    size_t chunk = (size_t)t->tune_chunk;
+    if (chunk == 0) chunk = spo >= 16 * grid ? 1 : std::max<size_t>(1, std::min(spo / 4, (stages + grid - 1) / grid));
     k.fn<<<(int)grid, k.threads, k.smem, s>>>(t->d_ops + t->level_op_offset[level], n_ops, t->n_sites,
-                                              t->use_wgt ? t->d_wgt : nullptr, t->d_sum);
+                                              t->use_wgt ? t->d_wgt : nullptr, t->d_sum, (unsigned)chunk);
     TREE_CUDA(t, cudaGetLastError());
     return PLF_OK;
 }
@@ -156,6 +164,7 @@ int build_graph(plf_tree *t)
     if (e != cudaSuccess) return tfail(t, PLF_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
     t->exec_math = t->math;
     t->exec_u = t->tune_u;
+    t->exec_chunk = t->tune_chunk;
     t->exec_wgt = t->use_wgt;
     return PLF_OK;
 }
@@ -315,11 +324,13 @@ int plf_tree_set_math(plf_tree *t, int math_mode)
     return PLF_OK;
 }
 
-int plf_tree_set_tuning(plf_tree *t, int u)
+int plf_tree_set_tuning(plf_tree *t, int u, int chunk)
 {
     if (!t) return tfail(nullptr, PLF_ERR_INVALID, "NULL tree");
     if (u < 0 || u > 2) return tfail(t, PLF_ERR_INVALID, "tuning u must be 0, 1 or 2");
+    if (chunk < 0) return tfail(t, PLF_ERR_INVALID, "chunk must be >= 0");
     t->tune_u = u;
+    t->tune_chunk = chunk;
     return PLF_OK;
 }
 
@@ -376,7 +387,7 @@ int plf_tree_run_async(plf_tree *t)
 {
     if (!t) return tfail(nullptr, PLF_ERR_INVALID, "NULL tree");
     TREE_CUDA(t, cudaSetDevice(t->device));
-    if (!t->exec || t->exec_math != t->math || t->exec_u != t->tune_u || t->exec_wgt != t->use_wgt) {
+    if (!t->exec || t->exec_math != t->math || t->exec_u != t->tune_u || t->exec_chunk != t->tune_chunk || t->exec_wgt != t->use_wgt) {
         int rc = build_graph(t);
         if (rc != PLF_OK) return rc;
     }

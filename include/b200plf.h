@@ -208,8 +208,9 @@ int plf_tree_create(plf_tree **tree, int device, unsigned n_tips, const int *lef
 int plf_tree_destroy(plf_tree *tree);
 const char *plf_tree_last_error(const plf_tree *tree);
 int plf_tree_set_math(plf_tree *tree, int math_mode);
-/* 0 = automatic; otherwise U of the batch kernel (1: 128-site stages, 2: 256-site stages).   */
-int plf_tree_set_tuning(plf_tree *tree, int u);
+/* u: 0 = automatic, else U of the batch kernel (1: 128-site stages, 2: 256-site stages).
+ * chunk: 0 = automatic, else consecutive stages dealt to a CTA at a time (1 = fully interleaved). */
+int plf_tree_set_tuning(plf_tree *tree, int u, int chunk);
 /* Device pointer of a tip CLV (n_sites*16 floats) for callers that produce tips on the device. */
 int plf_tree_tip_ptr(plf_tree *tree, unsigned tip, float **clv);
 /* Host -> device copy into a tip CLV (bytes at byte offset), asynchronous on the tree's stream. */

@@ -29,6 +29,7 @@ def main():
     ap.add_argument("--shape", default="balanced", choices=["balanced", "random"])
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--u", type=int, default=0)
+    ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--math", default="strict")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
@@ -47,12 +48,15 @@ def main():
     first, n = sharding.shard_for_rank(args.sites, rank, world)
     left, right = (pkg.balanced_tree if args.shape == "balanced" else pkg.random_tree)(args.tips)
     rng = np.random.RandomState(1)
-    ev = rng.random_sample(16).astype(np.float32)
-    pl = rng.random_sample((args.tips - 1, 64)).astype(np.float32)
-    pr = rng.random_sample((args.tips - 1, 64)).astype(np.float32)
+    def stochastic(*shape):      # rows of every 4x4 matrix sum to 1: CLV magnitudes stay bounded
+        m = rng.random_sample(shape + (4, 4)) + 0.05
+        return (m / m.sum(axis=-1, keepdims=True)).astype(np.float32)
+    ev = stochastic().reshape(16)
+    pl = stochastic(args.tips - 1, 4).reshape(args.tips - 1, 64)
+    pr = stochastic(args.tips - 1, 4).reshape(args.tips - 1, 64)
 
     t = pkg.Tree(left, right, n, device=local)
-    t.set_tuning(args.u)
+    t.set_tuning(args.u, args.chunk)
     t.set_math(pkg.MATH_FMA if args.math == "fma" else pkg.MATH_STRICT)
     scratch = torch.empty((n, 16), device=device)
     for tip in range(args.tips):      # x1-stream of the generator for even tips, x2-stream for odd ones
@@ -83,7 +87,7 @@ def main():
                "newview_sites_per_s": nodes * args.sites / (ms_max * 1e-3),
                "hbm_gbs_per_gpu": info["traversal_bytes"] / (ms_max * 1e-3) / 1e9,
                "total_scalings": total, "root_count_max": int(cnt.max()), "root_finite": bool(np.isfinite(root).all()),
-               "u": args.u, "math": args.math}
+               "u": args.u, "chunk": args.chunk, "math": args.math}
         print(json.dumps(row), flush=True)
         if args.out:
             with open(args.out, "a") as f:
