@@ -289,9 +289,25 @@ __device__ __forceinline__ void mbar_fence_init()
 {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+// Orders this thread's generic-proxy shared-memory accesses (the LDS reads of a ring slot) before
+// later async-proxy accesses (the bulk copy that refills the slot).  Without it the release below
+// can overtake the reads: with a fast refill (data in L2, one busy CTA) the first bytes of the next
+// stage then land in the slot while a warp is still reading it.
+__device__ __forceinline__ void fence_proxy_async_smem()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+// Consumer release of a ring slot: every lane fences its own reads, then one lane arrives.
+__device__ __forceinline__ void mbar_release_slot(uint64_t *bar, int lane);
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_release_slot(uint64_t *bar, int lane)
+{
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
 {
@@ -399,9 +415,8 @@ plf_newview_tma(const float4 *__restrict__ x1, const float4 *__restrict__ x2,
                 a[u] = t1[32 * u];
                 b[u] = t2[32 * u];
             }
-            // all of this warp's reads of the slot are done once the values are in registers
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[slot]);
+            // release the slot as soon as this warp's reads of it are complete
+            mbar_release_slot(&empty[slot], lane);
             if (++slot == DEPTH) {
                 slot = 0;
                 phase ^= 1u;
@@ -591,8 +606,7 @@ plf_newview_batch(const BatchOp *__restrict__ ops, int n_ops, size_t n,
                     a[u] = t1[32 * u];
                     b[u] = t2[32 * u];
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[slot]);
+                mbar_release_slot(&empty[slot], lane);
                 if (++slot == DEPTH) {
                     slot = 0;
                     phase ^= 1u;
