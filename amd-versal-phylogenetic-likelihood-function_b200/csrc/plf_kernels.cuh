@@ -541,12 +541,17 @@ plf_newview_batch(const BatchOp *__restrict__ ops, int n_ops, size_t n,
     if (warp == WARPS) {
         // ===== producer =====
         if (lane == 0) {
-            uint32_t slot = 0, phase = 0;
+            uint32_t slot = 0, phase = 0, cur_op = 0xffffffffu;
+            const float4 *x1 = nullptr, *x2 = nullptr;
             for (uint32_t q = blockIdx.x; q < n_chunks; q += gridDim.x) {
                 const uint32_t g0 = q * chunk;
                 const uint32_t g1 = g0 + chunk < total ? g0 + chunk : total;
                 uint32_t op = g0 / spo, st = g0 - op * spo;
-                const float4 *x1 = ops[op].x1, *x2 = ops[op].x2;
+                if (op != cur_op) {          // a global load on the producer's critical path: only on op change
+                    x1 = ops[op].x1;
+                    x2 = ops[op].x2;
+                    cur_op = op;
+                }
                 for (uint32_t g = g0; g < g1; ++g) {
                     mbar_wait(&empty[slot], phase ^ 1u);
                     const size_t s0 = (size_t)st * STAGE;
@@ -563,6 +568,7 @@ plf_newview_batch(const BatchOp *__restrict__ ops, int n_ops, size_t n,
                         ++op;
                         x1 = ops[op].x1;
                         x2 = ops[op].x2;
+                        cur_op = op;
                     }
                 }
             }

@@ -117,11 +117,11 @@ int launch_level(plf_tree *t, const BatchSel &k, size_t level, cudaStream_t s)
     if (stages >= (1ull << 31)) return tfail(t, PLF_ERR_INVALID, "level %zu has too many stages (%zu)", level, stages);
     size_t grid = (size_t)t->num_sms;
     if (grid > stages) grid = stages;
-    // chunk of consecutive stages dealt to one CTA at a time (see plf_newview_batch).  Auto: interleave
-    // stage by stage when an op is long enough that a CTA revisits it many times, otherwise runs of
-    // about a quarter op so that the 48 constants are reloaded rarely.
+    // chunk of consecutive stages dealt to one CTA at a time (see plf_newview_batch).  Auto: about 16
+    // chunks per CTA keeps the level balanced while a CTA changes op (reloading the 48 constants
+    // behind two dependent global loads) as rarely as possible; never longer than one op.
     size_t chunk = (size_t)t->tune_chunk;
-    if (chunk == 0) chunk = spo >= 16 * grid ? 1 : std::max<size_t>(1, std::min(spo / 4, (stages + grid - 1) / grid));
+    if (chunk == 0) chunk = std::max<size_t>(1, std::min(spo, stages / (16 * grid)));
     k.fn<<<(int)grid, k.threads, k.smem, s>>>(t->d_ops + t->level_op_offset[level], n_ops, t->n_sites,
                                               t->use_wgt ? t->d_wgt : nullptr, t->d_sum, (unsigned)chunk);
     TREE_CUDA(t, cudaGetLastError());
@@ -133,9 +133,9 @@ int build_graph(plf_tree *t)
 {
     int u = t->tune_u;
     if (u == 0) {
-        // small per-level work: finer stages balance better over 148 CTAs
+        // 256-site stages unless even the widest level would leave most SMs with < 4 stages
         const size_t widest = t->levels.empty() ? 1 : t->levels[0].size();
-        u = (t->n_sites / 256) * widest >= (size_t)t->num_sms * 16 ? 2 : 1;
+        u = ((t->n_sites + 255) / 256) * widest >= (size_t)t->num_sms * 4 ? 2 : 1;
     }
     const BatchSel k = pick_batch(t->math, u);
     TREE_CUDA(t, cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.smem));
