@@ -479,12 +479,17 @@ constexpr size_t tma_smem_bytes()
 // (all inner nodes of one tree level are independent: BASELINE.json configs[4]).
 //
 // Same producer/consumer ring as plf_newview_tma.  The work list is the concatenation of the
-// stages of all ops; CTA b owns a contiguous run of it, so it changes op (and reloads the 48
-// matrix constants and the op's pointers) only a handful of times.  Per site the op additionally
+// stages of all ops, dealt to the CTAs in chunks of consecutive stages, so a CTA changes op (and
+// reloads the 48 matrix constants and the op's pointers) rarely.  Per site the op additionally
 // reads the children's int32 scaler counts (NULL = tip = 0) and writes
 //     cnt3[i] = cnt1[i] + cnt2[i] + (site i rescaled ? 1 : 0)
 // which is what RAxML-style codes carry up the tree instead of the single byte of one call
-// (205 B/site/node: 193 + 12).
+// (up to 204 B/site/node: 192 + 3 x 4).
+// The children's counts ride in the ring too: the producer adds one bulk copy per count vector
+// (STAGE x 4 bytes) to the stage's mbarrier transaction.  Reading them with per-warp 64-byte
+// loads instead cost 23 % of the traversal (profiles/r01_tree.md): the small requests arrive
+// late under a saturated DRAM queue and stall the warp that issued them.
+// Count vectors must be 16-byte aligned and padded to a multiple of 4 ints.
 // ---------------------------------------------------------------------------------------------
 struct BatchOp {
     const float4 *x1;
@@ -499,6 +504,12 @@ struct BatchOp {
     const float *ev;
 };
 
+template <int U, int WARPS, int DEPTH>
+constexpr size_t batch_smem_bytes()
+{
+    return tma_smem_bytes<U, WARPS, DEPTH>() + (size_t)DEPTH * (WARPS * 8 * U) * sizeof(int) * 2;
+}
+
 template <class M, int U, int WARPS, int DEPTH, int MINB>
 __global__ void __launch_bounds__((WARPS + 1) * 32, MINB)
 plf_newview_batch(const BatchOp *__restrict__ ops, int n_ops, size_t n,
@@ -511,17 +522,17 @@ plf_newview_batch(const BatchOp *__restrict__ ops, int n_ops, size_t n,
     constexpr int STAGE_F4 = STAGE * 4;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float4 *s1 = reinterpret_cast<float4 *>(smem_raw);
-    float4 *s2 = s1 + (size_t)DEPTH * STAGE_F4;
-    uint64_t *full = reinterpret_cast<uint64_t *>(s2 + (size_t)DEPTH * STAGE_F4);
+    float4 *s1 = reinterpret_cast<float4 *>(smem_raw);                 // [DEPTH][STAGE_F4]
+    float4 *s2 = s1 + (size_t)DEPTH * STAGE_F4;                        // [DEPTH][STAGE_F4]
+    int *c1 = reinterpret_cast<int *>(s2 + (size_t)DEPTH * STAGE_F4);  // [DEPTH][STAGE]
+    int *c2 = c1 + (size_t)DEPTH * STAGE;                              // [DEPTH][STAGE]
+    uint64_t *full = reinterpret_cast<uint64_t *>(c2 + (size_t)DEPTH * STAGE);
     uint64_t *empty = full + DEPTH;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     // The work list: stage g of the launch is stage (g % spo) of op (g / spo).  It is dealt out in
-    // chunks of `chunk` consecutive stages, chunk q to CTA q % gridDim.x: chunk = 1 interleaves the
-    // CTAs stage by stage (all SMs stream through the same few MB at any time), a large chunk gives
-    // every CTA long runs inside one op (fewer constant reloads when ops are short).
+    // chunks of `chunk` consecutive stages, chunk q to CTA q % gridDim.x.
     const uint32_t spo = (uint32_t)((n + STAGE - 1) / STAGE);          // stages per op
     const uint32_t full_stages = (uint32_t)(n / STAGE);                // stages [0, full_stages) are complete
     const uint32_t total = spo * (uint32_t)n_ops;
@@ -543,32 +554,36 @@ plf_newview_batch(const BatchOp *__restrict__ ops, int n_ops, size_t n,
         if (lane == 0) {
             uint32_t slot = 0, phase = 0, cur_op = 0xffffffffu;
             const float4 *x1 = nullptr, *x2 = nullptr;
+            const int *k1 = nullptr, *k2 = nullptr;
             for (uint32_t q = blockIdx.x; q < n_chunks; q += gridDim.x) {
                 const uint32_t g0 = q * chunk;
                 const uint32_t g1 = g0 + chunk < total ? g0 + chunk : total;
                 uint32_t op = g0 / spo, st = g0 - op * spo;
-                if (op != cur_op) {          // a global load on the producer's critical path: only on op change
-                    x1 = ops[op].x1;
-                    x2 = ops[op].x2;
-                    cur_op = op;
-                }
                 for (uint32_t g = g0; g < g1; ++g) {
+                    if (op != cur_op) {          // global loads on the producer's critical path: only on op change
+                        x1 = ops[op].x1;
+                        x2 = ops[op].x2;
+                        k1 = ops[op].cnt1;
+                        k2 = ops[op].cnt2;
+                        cur_op = op;
+                    }
                     mbar_wait(&empty[slot], phase ^ 1u);
                     const size_t s0 = (size_t)st * STAGE;
-                    const uint32_t bytes = (st < full_stages ? (uint32_t)STAGE : (uint32_t)(n - s0)) * 64u;
-                    mbar_arrive_expect_tx(&full[slot], 2u * bytes);
+                    const uint32_t sites = st < full_stages ? (uint32_t)STAGE : (uint32_t)(n - s0);
+                    const uint32_t bytes = sites * 64u;
+                    const uint32_t cbytes = ((sites * 4u) + 15u) & ~15u;     // count vectors are padded to 16 B
+                    mbar_arrive_expect_tx(&full[slot], 2u * bytes + (k1 ? cbytes : 0u) + (k2 ? cbytes : 0u));
                     bulk_g2s(s1 + slot * STAGE_F4, x1 + s0 * 4, bytes, &full[slot]);
                     bulk_g2s(s2 + slot * STAGE_F4, x2 + s0 * 4, bytes, &full[slot]);
+                    if (k1) bulk_g2s(c1 + slot * STAGE, k1 + s0, cbytes, &full[slot]);
+                    if (k2) bulk_g2s(c2 + slot * STAGE, k2 + s0, cbytes, &full[slot]);
                     if (++slot == DEPTH) {
                         slot = 0;
                         phase ^= 1u;
                     }
-                    if (++st == spo && g + 1 < g1) {
+                    if (++st == spo) {
                         st = 0;
                         ++op;
-                        x1 = ops[op].x1;
-                        x2 = ops[op].x2;
-                        cur_op = op;
                     }
                 }
             }
@@ -596,12 +611,6 @@ plf_newview_batch(const BatchOp *__restrict__ ops, int n_ops, size_t n,
                 const size_t s_lane = s0 + lane;                              // the site whose count this lane owns
                 const bool complete = st < full_stages;
                 const bool lane_live = lane < TILE && (complete || s_lane < n);
-                // children's scaler counts: issued before the wait so their latency overlaps it
-                int cnt = 0;
-                if (lane_live) {
-                    if (o.cnt1) cnt = __ldg(o.cnt1 + s_lane);
-                    if (o.cnt2) cnt += __ldg(o.cnt2 + s_lane);
-                }
                 const float4 *t1 = s1 + slot * STAGE_F4 + tile_off;
                 const float4 *t2 = s2 + slot * STAGE_F4 + tile_off;
                 mbar_wait(&full[slot], phase);
@@ -611,6 +620,11 @@ plf_newview_batch(const BatchOp *__restrict__ ops, int n_ops, size_t n,
                 for (int u = 0; u < U; ++u) {
                     a[u] = t1[32 * u];
                     b[u] = t2[32 * u];
+                }
+                int cnt = 0;
+                if (lane_live) {
+                    if (o.cnt1) cnt = c1[slot * STAGE + warp * TILE + lane];
+                    if (o.cnt2) cnt += c2[slot * STAGE + warp * TILE + lane];
                 }
                 mbar_release_slot(&empty[slot], lane);
                 if (++slot == DEPTH) {

@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <new>
 #include <string>
 #include <vector>
@@ -123,7 +124,7 @@ int launch_level(plf_tree *t, const BatchSel &k, size_t level, cudaStream_t s)
     size_t chunk = (size_t)t->tune_chunk;
     if (chunk == 0) chunk = std::max<size_t>(1, std::min(spo, stages / (16 * grid)));
     k.fn<<<(int)grid, k.threads, k.smem, s>>>(t->d_ops + t->level_op_offset[level], n_ops, t->n_sites,
-                                              t->use_wgt ? t->d_wgt : nullptr, t->d_sum, (unsigned)chunk);
+                                              t->use_wgt ? t->d_wgt : nullptr, t->d_sum, (unsigned)chunk | (getenv("PLF_DBG_SKIPCNT") ? 0x80000000u : 0u));
     TREE_CUDA(t, cudaGetLastError());
     return PLF_OK;
 }

@@ -26,7 +26,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--tips", type=int, default=1024)
     ap.add_argument("--sites", type=int, default=1 << 20, help="total sites (split over ranks)")
-    ap.add_argument("--shape", default="balanced", choices=["balanced", "random"])
+    ap.add_argument("--shape", default="balanced", choices=["balanced", "random", "caterpillar"])
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--u", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=0)
@@ -46,7 +46,11 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     first, n = sharding.shard_for_rank(args.sites, rank, world)
-    left, right = (pkg.balanced_tree if args.shape == "balanced" else pkg.random_tree)(args.tips)
+    if args.shape == "caterpillar":      # one op per level; every op but the first has one inner child
+        left = np.array([0] + [args.tips + k for k in range(args.tips - 2)], np.int32)
+        right = np.arange(1, args.tips, dtype=np.int32)
+    else:
+        left, right = (pkg.balanced_tree if args.shape == "balanced" else pkg.random_tree)(args.tips)
     rng = np.random.RandomState(1)
     def stochastic(*shape):      # rows of every 4x4 matrix sum to 1: CLV magnitudes stay bounded
         m = rng.random_sample(shape + (4, 4)) + 0.05
