@@ -17,7 +17,6 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
-#include <cstdlib>
 #include <new>
 #include <string>
 #include <vector>
@@ -89,8 +88,8 @@ template <class M>
 BatchSel batch_sel(int u)
 {
     if (u == 1)
-        return {plf::plf_newview_batch<M, 1, 16, 4, 1>, 17 * 32, plf::tma_smem_bytes<1, 16, 4>(), 128};
-    return {plf::plf_newview_batch<M, 2, 16, 3, 1>, 17 * 32, plf::tma_smem_bytes<2, 16, 3>(), 256};
+        return {plf::plf_newview_batch<M, 1, 16, 4, 1>, 17 * 32, plf::batch_smem_bytes<1, 16, 4>(), 128};
+    return {plf::plf_newview_batch<M, 2, 16, 3, 1>, 17 * 32, plf::batch_smem_bytes<2, 16, 3>(), 256};
 }
 
 BatchSel pick_batch(int math, int u)
@@ -105,9 +104,13 @@ float *node_clv(plf_tree *t, int node)
                                  : t->d_pool + (size_t)t->slot[node - t->n_tips] * stride;
 }
 
+// count vectors are padded to a multiple of 4 ints so that every stage of them is a legal
+// (16-byte aligned, 16-byte granular) bulk copy
+size_t count_stride(const plf_tree *t) { return (t->n_sites + 3) & ~(size_t)3; }
+
 int *node_counts(plf_tree *t, int node)
 {
-    return node < (int)t->n_tips ? nullptr : t->d_counts + (size_t)t->slot[node - t->n_tips] * t->n_sites;
+    return node < (int)t->n_tips ? nullptr : t->d_counts + (size_t)t->slot[node - t->n_tips] * count_stride(t);
 }
 
 int launch_level(plf_tree *t, const BatchSel &k, size_t level, cudaStream_t s)
@@ -124,7 +127,7 @@ int launch_level(plf_tree *t, const BatchSel &k, size_t level, cudaStream_t s)
     size_t chunk = (size_t)t->tune_chunk;
     if (chunk == 0) chunk = std::max<size_t>(1, std::min(spo, stages / (16 * grid)));
     k.fn<<<(int)grid, k.threads, k.smem, s>>>(t->d_ops + t->level_op_offset[level], n_ops, t->n_sites,
-                                              t->use_wgt ? t->d_wgt : nullptr, t->d_sum, (unsigned)chunk | (getenv("PLF_DBG_SKIPCNT") ? 0x80000000u : 0u));
+                                              t->use_wgt ? t->d_wgt : nullptr, t->d_sum, (unsigned)chunk);
     TREE_CUDA(t, cudaGetLastError());
     return PLF_OK;
 }
@@ -251,7 +254,8 @@ int plf_tree_create(plf_tree **out, int device, unsigned n_tips, const int *left
     if (e == cudaSuccess) e = cudaEventCreate(&t->ev1);
     if (e == cudaSuccess) e = cudaMalloc(&t->d_tips, clv_bytes * n_tips);
     if (e == cudaSuccess) e = cudaMalloc(&t->d_pool, clv_bytes * t->n_slots);
-    if (e == cudaSuccess) e = cudaMalloc(&t->d_counts, n_sites * sizeof(int) * t->n_slots);
+    if (e == cudaSuccess) e = cudaMalloc(&t->d_counts, count_stride(t) * sizeof(int) * t->n_slots);
+    if (e == cudaSuccess) e = cudaMemset(t->d_counts, 0, count_stride(t) * sizeof(int) * t->n_slots);
     if (e == cudaSuccess) e = cudaMalloc(&t->d_mats, (16 + 128 * (size_t)n_inner) * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&t->d_ops, sizeof(plf::BatchOp) * n_inner);
     if (e == cudaSuccess) e = cudaMalloc(&t->d_sum, sizeof(unsigned long long));
