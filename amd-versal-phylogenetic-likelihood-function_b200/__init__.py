@@ -107,6 +107,8 @@ PROTOTYPES = {
     "plf_tree_info": (_i, [_vp, ctypes.POINTER(_u), ctypes.POINTER(_u), ctypes.POINTER(_sz),
                            ctypes.POINTER(_sz)]),
     "plf_tree_last_ms": (_i, [_vp, ctypes.POINTER(ctypes.c_float)]),
+    "plf_tree_evaluate_root": (_i, [_vp, _vp, ctypes.POINTER(ctypes.c_double)]),
+    "plf_evaluate_device": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "plf_kernel_info": (_i, [_i, _i] + [ctypes.POINTER(_i)] * 4),
     "plf_launch_count": (ctypes.c_ulonglong, []),
 }
@@ -599,3 +601,15 @@ class Tree:
         v = ctypes.c_float(0)
         self._ck(self.lib.plf_tree_last_ms(self._t, ctypes.byref(v)))
         return v.value
+
+    def evaluate_root(self, diag) -> float:
+        """Log-likelihood of this rank's sites across the root branch (after run_async)."""
+        diag = np.ascontiguousarray(diag, np.float32).reshape(16)
+        v = ctypes.c_double(0)
+        self._ck(self.lib.plf_tree_evaluate_root(self._t, _ptr(diag), ctypes.byref(v)))
+        return v.value
+
+
+def evaluate_device(x1, x2, cnt1, cnt2, wgt, diag, n: int, lnl, stream: int = 0):
+    """Root log-likelihood on caller-owned DEVICE memory; pointers are ints; ADDS to the double *lnl."""
+    _check(load().plf_evaluate_device(x1, x2, cnt1, cnt2, wgt, diag, n, lnl, stream or None))

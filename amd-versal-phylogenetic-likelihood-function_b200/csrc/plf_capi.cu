@@ -808,6 +808,18 @@ int plf_generate_host(float *x1, float *x2, size_t first_site, size_t n, uint64_
     return PLF_OK;
 }
 
+int plf_evaluate_device(const float *x1, const float *x2, const int *cnt1, const int *cnt2, const int *wgt,
+                        const float *diag, size_t n, double *lnl, void *stream)
+{
+    if (n == 0) return PLF_OK;
+    if (!x1 || !x2 || !diag || !lnl) return fail(nullptr, PLF_ERR_INVALID, "evaluate: NULL device pointer");
+    if (((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)diag) & 15u)
+        return fail(nullptr, PLF_ERR_INVALID, "evaluate: CLV / diag pointers must be 16-byte aligned");
+    int rc = plf::launch_evaluate(x1, x2, cnt1, cnt2, wgt, diag, n, lnl, static_cast<cudaStream_t>(stream));
+    if (rc != PLF_OK) return fail(nullptr, rc, "evaluate kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return PLF_OK;
+}
+
 int plf_kernel_info(int variant, int math_mode, int *regs_per_thread, int *threads_per_block,
                     int *blocks_per_sm, int *num_sms)
 {

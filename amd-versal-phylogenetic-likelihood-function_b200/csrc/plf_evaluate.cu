@@ -1,0 +1,87 @@
+// csrc/plf_evaluate.cu -- root log-likelihood across a branch: the step right after the newview
+// path in RAxML-like codes.  NOT part of the reference repository: the
+// algorithm is evaluateGTRGAMMA of standard-RAxML (evaluateGenericSpecial.c), which the reference's
+// plf() was derived from (README.md:188-189,207-208), restated for the reference's CLV layout:
+//
+//   lnL = sum_i wgt[i] * ( log(0.25 * | sum_{j,k} x1[i,j,k] * x2[i,j,k] * diag[j,k] |)
+//                          + (cnt1[i] + cnt2[i]) * log(2^-32) )
+//
+// x1, x2 are the CLVs at the two ends of the branch (eigen-space, as newview leaves them), diag[j,k]
+// = exp(lambda_k * rate_j * t) for the branch, cnt1/cnt2 the accumulated per-site scaler counts.
+// One thread per (site, category) as in the newview kernels: a 128-bit load per child, four fp64
+// products, two shuffles for the per-site sum; fp64 log and accumulation; block reduction and one
+// atomicAdd(double) per block.  HBM-bound: 128 B/site (+ 4 B per count vector and for wgt).
+#include "../../include/b200plf.h"
+#include "plf_kernels.cuh"
+#include "plf_registry.h"
+
+namespace plf {
+
+constexpr int kEvalThreads = 256;
+
+__global__ void __launch_bounds__(kEvalThreads)
+plf_evaluate_kernel(const float4 *__restrict__ x1, const float4 *__restrict__ x2,
+                    const int *__restrict__ cnt1, const int *__restrict__ cnt2,
+                    const int *__restrict__ wgt, const float *__restrict__ diag, size_t n,
+                    double *__restrict__ lnl)
+{
+    const int lane = threadIdx.x & 31;
+    const int cat = lane & 3;
+    const float4 dg = __ldg(reinterpret_cast<const float4 *>(diag) + cat);
+    const double d0 = dg.x, d1 = dg.y, d2 = dg.z, d3 = dg.w;
+    const double log_min = -32.0 * 0.69314718055994530942;        // log(2^-32)
+    const size_t n_vec = n * 4;
+    const size_t stride = (size_t)gridDim.x * kEvalThreads;
+    double acc = 0.0;
+    // n_vec is a multiple of 4 and the stride a multiple of 32, so the 4 lanes of a site stay together
+    for (size_t v = (size_t)blockIdx.x * kEvalThreads + threadIdx.x; v < ((n_vec + 31) & ~(size_t)31); v += stride) {
+        const bool live = v < n_vec;
+        double t = 0.0;
+        if (live) {
+            const float4 a = ld_stream(x1 + v), b = ld_stream(x2 + v);
+            t = (double)a.x * (double)b.x * d0 + (double)a.y * (double)b.y * d1 +
+                (double)a.z * (double)b.z * d2 + (double)a.w * (double)b.w * d3;
+        }
+        t += __shfl_xor_sync(0xffffffffu, t, 1);
+        t += __shfl_xor_sync(0xffffffffu, t, 2);
+        if (live && cat == 0) {
+            const size_t s = v >> 2;
+            double term = log(0.25 * fabs(t));
+            int c = 0;
+            if (cnt1) c += __ldg(cnt1 + s);
+            if (cnt2) c += __ldg(cnt2 + s);
+            term += (double)c * log_min;
+            acc += (wgt ? (double)__ldg(wgt + s) : 1.0) * term;
+        }
+    }
+    __shared__ double warp_acc[kEvalThreads / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) warp_acc[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double t = threadIdx.x < kEvalThreads / 32 ? warp_acc[threadIdx.x] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0) atomicAdd(lnl, t);
+    }
+}
+
+int launch_evaluate(const float *x1, const float *x2, const int *cnt1, const int *cnt2, const int *wgt,
+                    const float *diag, size_t n, double *lnl, cudaStream_t stream)
+{
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+        return PLF_ERR_CUDA;
+    size_t grid = (n * 4 + kEvalThreads - 1) / kEvalThreads;
+    if (grid > (size_t)sms * 8) grid = (size_t)sms * 8;
+    if (grid == 0) return PLF_OK;
+    plf_evaluate_kernel<<<(int)grid, kEvalThreads, 0, stream>>>(reinterpret_cast<const float4 *>(x1),
+                                                                reinterpret_cast<const float4 *>(x2), cnt1, cnt2,
+                                                                wgt, diag, n, lnl);
+    count_launches(1);
+    return cudaGetLastError() == cudaSuccess ? PLF_OK : PLF_ERR_CUDA;
+}
+
+}  // namespace plf

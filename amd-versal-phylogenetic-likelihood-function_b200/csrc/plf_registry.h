@@ -33,6 +33,10 @@ KernelSel select_ldg_fma(int u, int kind, int b, int threads);
 KernelSel select_tma_strict(int u, int d, int b, int threads);
 KernelSel select_tma_fma(int u, int d, int b, int threads);
 
+// root log-likelihood kernel (plf_evaluate.cu); returns a plf_status
+int launch_evaluate(const float *x1, const float *x2, const int *cnt1, const int *cnt2, const int *wgt,
+                    const float *diag, size_t n, double *lnl, cudaStream_t stream);
+
 // process-wide count of kernel launches issued by this library (plf_launch_count)
 void count_launches(unsigned long long n);
 

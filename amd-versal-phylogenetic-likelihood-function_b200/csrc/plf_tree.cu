@@ -42,6 +42,7 @@ struct plf_tree {
     plf::BatchOp *d_ops = nullptr;             // all ops, level after level
     std::vector<size_t> level_op_offset;
     unsigned long long *d_sum = nullptr, *h_sum = nullptr;
+    double *d_lnl = nullptr;                   // [0] lnL accumulator, [1..4] diag (as 16 floats)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaGraphExec_t exec = nullptr;
@@ -313,6 +314,7 @@ int plf_tree_destroy(plf_tree *t)
     cudaFree(t->d_wgt);
     cudaFree(t->d_ops);
     cudaFree(t->d_sum);
+    cudaFree(t->d_lnl);
     if (t->h_sum) cudaFreeHost(t->h_sum);
     if (t->ev0) cudaEventDestroy(t->ev0);
     if (t->ev1) cudaEventDestroy(t->ev1);
@@ -453,6 +455,24 @@ int plf_tree_info(plf_tree *t, unsigned *levels, unsigned *clv_slots, size_t *de
             inner_children += (t->left[k] >= (int)t->n_tips) + (t->right[k] >= (int)t->n_tips);
         *traversal_bytes = t->n_sites * (192 * (size_t)t->n_inner + 4 * ((size_t)t->n_inner + inner_children));
     }
+    return PLF_OK;
+}
+
+int plf_tree_evaluate_root(plf_tree *t, const float *diag, double *lnl)
+{
+    if (!t || !diag || !lnl) return tfail(t, PLF_ERR_INVALID, "NULL argument");
+    if (!t->ran) return tfail(t, PLF_ERR_STATE, "tree has not been run");
+    TREE_CUDA(t, cudaSetDevice(t->device));
+    if (!t->d_lnl) TREE_CUDA(t, cudaMalloc(&t->d_lnl, 2 * sizeof(double) + 16 * sizeof(float)));
+    float *d_diag = reinterpret_cast<float *>(t->d_lnl + 2);          // 16-byte aligned behind the accumulator
+    TREE_CUDA(t, cudaMemsetAsync(t->d_lnl, 0, sizeof(double), t->stream));
+    TREE_CUDA(t, cudaMemcpyAsync(d_diag, diag, 16 * sizeof(float), cudaMemcpyHostToDevice, t->stream));
+    const int a = t->left[t->n_inner - 1], b = t->right[t->n_inner - 1];
+    int rc = plf::launch_evaluate(node_clv(t, a), node_clv(t, b), node_counts(t, a), node_counts(t, b),
+                                  t->use_wgt ? t->d_wgt : nullptr, d_diag, t->n_sites, t->d_lnl, t->stream);
+    if (rc != PLF_OK) return tfail(t, rc, "evaluate kernel launch failed");
+    TREE_CUDA(t, cudaMemcpyAsync(lnl, t->d_lnl, sizeof(double), cudaMemcpyDeviceToHost, t->stream));
+    TREE_CUDA(t, cudaStreamSynchronize(t->stream));
     return PLF_OK;
 }
 

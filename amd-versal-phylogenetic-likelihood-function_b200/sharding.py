@@ -36,6 +36,18 @@ def reduce_scaler_increment(local_increment: int, device=None, group=None) -> in
     return int(t.item())
 
 
+def reduce_log_likelihood(local_lnl: float, device=None, group=None) -> float:
+    """Sum of the per-rank log-likelihoods (one float64 all-reduce): sites are independent, so the
+    log-likelihood of an alignment is the sum over the site ranges of the ranks."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return float(local_lnl)
+    t = torch.tensor([float(local_lnl)], dtype=torch.float64, device=device or "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return float(t.item())
+
+
 def max_over_ranks(value: float, device=None, group=None) -> float:
     """Max of a per-rank scalar (device timings are reported as the max over ranks)."""
     import torch

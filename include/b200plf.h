@@ -234,6 +234,20 @@ int plf_tree_info(plf_tree *tree, unsigned *levels, unsigned *clv_slots, size_t 
 /* Device time of the last traversal in milliseconds (events around the graph launch). */
 int plf_tree_last_ms(plf_tree *tree, float *ms);
 
+/* ---- root log-likelihood across a branch ---------------------------
+ * The step after the path in RAxML-like codes (standard-RAxML evaluateGTRGAMMA; not in the
+ * reference repository, which stops at newview):
+ *   lnL = sum_i wgt[i] * ( log(0.25*|sum_{j,k} x1[i,j,k]*x2[i,j,k]*diag[j,k]|) + (cnt1[i]+cnt2[i])*log(2^-32) )
+ * All pointers are DEVICE pointers: x1,x2 CLVs (16-byte aligned), diag float[16] = [category][state],
+ * cnt1/cnt2 int32 per-site scaler counts or NULL, wgt int32 or NULL.  The result is ADDED to *lnl
+ * (device double; the caller zeroes it).  fp64 products, log and accumulation.                  */
+int plf_evaluate_device(const float *x1, const float *x2, const int *cnt1, const int *cnt2,
+                        const int *wgt, const float *diag, size_t n, double *lnl, void *stream);
+/* The same across the ROOT branch of a traversed tree: between the two children of the last inner
+ * node, with their accumulated scaler counts and the tree's weights.  diag is a HOST float[16].
+ * Must follow a completed plf_tree_run_async (the children's buffers are still intact then).  */
+int plf_tree_evaluate_root(plf_tree *tree, const float *diag, double *lnl);
+
 /* Largest tile the library was compiled for, number of SMs etc. -- introspection for benches. */
 int plf_kernel_info(int variant, int math_mode, int *regs_per_thread, int *threads_per_block,
                     int *blocks_per_sm, int *num_sms);

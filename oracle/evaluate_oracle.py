@@ -1,0 +1,33 @@
+"""oracle/evaluate_oracle.py -- root log-likelihood across a branch on the CPU (float64 numpy).
+TEST INFRASTRUCTURE ONLY.
+
+PARITY UNPINNED: this step is not in /root/reference (which stops at newview, app/src/plf.cpp).
+It restates evaluateGTRGAMMA of standard-RAxML (evaluateGenericSpecial.c, the code base the
+reference's plf() derives from, README.md:188-189,207-208) for the reference's CLV layout:
+
+    term_i = log(0.25 * |sum_{j,k} x1[i,j,k] * x2[i,j,k] * diag[j,k]|) + (cnt1_i + cnt2_i) * log(2^-32)
+    lnL    = sum_i wgt_i * term_i
+
+There is no golden vector for it in the reference; the GPU kernel is checked against this
+restatement only (tolerance 1e-9 relative: fp64 on both sides, different summation order)."""
+from __future__ import annotations
+
+import numpy as np
+
+LOG_MIN = -32.0 * np.log(2.0)
+
+
+def evaluate(x1, x2, diag, cnt1=None, cnt2=None, wgt=None) -> float:
+    x1 = np.asarray(x1, np.float64).reshape(-1, 16)
+    x2 = np.asarray(x2, np.float64).reshape(-1, 16)
+    d = np.asarray(diag, np.float32).astype(np.float64).reshape(1, 16)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        term = np.log(0.25 * np.abs((x1 * x2 * d).sum(axis=1)))
+    c = np.zeros(x1.shape[0])
+    if cnt1 is not None:
+        c = c + np.asarray(cnt1, np.float64)
+    if cnt2 is not None:
+        c = c + np.asarray(cnt2, np.float64)
+    term = term + c * LOG_MIN
+    w = np.ones(x1.shape[0]) if wgt is None else np.asarray(wgt, np.float64)
+    return float((w * term).sum())

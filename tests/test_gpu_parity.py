@@ -181,6 +181,31 @@ def test_per_category_ev(pkg, gpu, coracle):
         assert np.array_equal(bits(x3), bits(o3)) and np.array_equal(sc, osc) and inc == oinc
 
 
+@pytest.mark.parametrize("variant,threads", [(0, 0), (2, 256), (4, 256), (1322, 512), (1421, 128), (2422, 256)])
+def test_no_out_of_bounds_writes(pkg, gpu, coracle, variant, threads):
+    """Guard bands around x3 and the scaler bytes stay untouched for ragged site counts, and input
+    buffers that end exactly at the last site are enough (compute-sanitizer is closed on this pool)."""
+    torch = gpu
+    guard = 64
+    for n in (1, 5, 127, 257, 4097, 70001):
+        ev, left, right, x1, x2, _ = signed_inputs(n, seed=n + 1)
+        o3, osc, oinc = coracle.newview(x1, x2, ev, left, right)
+        d1, d2 = dev(torch, x1), dev(torch, x2)                     # exact-size inputs
+        mats = [dev(torch, a) for a in (ev, left, right)]
+        d3 = torch.full((n + 2 * guard, 16), -7.0, device="cuda")
+        dsc = torch.full((n + 2 * guard,), 9, dtype=torch.uint8, device="cuda")
+        dsum = torch.zeros(1, dtype=torch.int64, device="cuda")
+        pkg.newview_device(d1.data_ptr(), d2.data_ptr(), d3[guard:].data_ptr(), dsc[guard:].data_ptr(),
+                           mats[0].data_ptr(), mats[1].data_ptr(), mats[2].data_ptr(), None, n,
+                           dsum.data_ptr(), pkg.make_opts(0, variant, threads), 0)
+        torch.cuda.synchronize()
+        h3, hsc = d3.cpu().numpy(), dsc.cpu().numpy()
+        assert (h3[:guard] == -7.0).all() and (h3[guard + n:] == -7.0).all(), (variant, n)
+        assert (hsc[:guard] == 9).all() and (hsc[guard + n:] == 9).all(), (variant, n)
+        assert np.array_equal(bits(h3[guard:guard + n]), bits(o3)) and np.array_equal(hsc[guard:guard + n], osc)
+        assert int(dsum.item()) == oinc
+
+
 def test_null_scaler_and_null_sum(pkg, gpu, coracle):
     torch = gpu
     n = 777

@@ -82,6 +82,9 @@ def main():
     ms = float(np.median(times))
     ms_max = sharding.max_over_ranks(ms, device)
     total = sharding.reduce_scaler_increment(t.total_scalings(), device)
+    # the optional final reduction of the path: per-rank log-likelihood across the root branch, summed over NCCL
+    diag = np.exp(-np.linspace(0.0, 1.5, 16)).astype(np.float32)
+    lnl = sharding.reduce_log_likelihood(t.evaluate_root(diag), device)
     root, cnt = t.read_root(0, min(n, 4096))
     if rank == 0:
         nodes = args.tips - 1
@@ -90,7 +93,7 @@ def main():
                "ms_per_traversal": ms_max, "ms_min": float(min(times)),
                "newview_sites_per_s": nodes * args.sites / (ms_max * 1e-3),
                "hbm_gbs_per_gpu": info["traversal_bytes"] / (ms_max * 1e-3) / 1e9,
-               "total_scalings": total, "root_count_max": int(cnt.max()), "root_finite": bool(np.isfinite(root).all()),
+               "total_scalings": total, "log_likelihood": lnl, "root_count_max": int(cnt.max()), "root_finite": bool(np.isfinite(root).all()),
                "u": args.u, "chunk": args.chunk, "math": args.math}
         print(json.dumps(row), flush=True)
         if args.out:
