@@ -23,6 +23,7 @@
 namespace {
 
 thread_local std::string g_last_error = "";
+constexpr unsigned kSumSlots = 1024;
 std::atomic<unsigned long long> g_launches{0};
 
 struct Instance {
@@ -34,9 +35,11 @@ struct Instance {
     unsigned char *d_scaler = nullptr;
     int *d_wgt = nullptr;
     bool use_wgt = false;
-    unsigned long long *d_sum = nullptr;    // [0] scaler sum of the last run
+    unsigned long long *d_sum = nullptr;    // ring of kSumSlots counters, one per run (no per-run memset)
+    unsigned sum_slot = 0;                  // slot of the last run
+    unsigned long long runs = 0;
     double *d_check = nullptr;              // gen-discard checksum of the last run
-    unsigned long long *h_sum = nullptr;    // pinned mirrors, filled after each run
+    unsigned long long *h_sum = nullptr;    // pinned landing buffers for the read-backs
     double *h_check = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t marks[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -167,10 +170,25 @@ int launch_newview(plf_ctx *ctx, const float *x1, const float *x2, float *x3, un
     int grid = 0;
     int rc = resolve_launch(ctx, opts, n, &k, &grid);
     if (rc != PLF_OK) return rc;
-    k.fn<<<grid, k.threads, k.smem, stream>>>(reinterpret_cast<const float4 *>(x1),
-                                              reinterpret_cast<const float4 *>(x2),
-                                              reinterpret_cast<float4 *>(x3), scaler, ev, pl, pr, wgt, n,
-                                              sum, opts ? opts->ev_per_category : 0);
+    // Programmatic dependent launch: the kernel's prologue may overlap the tail of the previous kernel
+    // in the stream (it blocks in griddepcontrol.wait before touching global memory).  PLF_PDL=0 disables.
+    static const bool use_pdl = [] {
+        const char *e = getenv("PLF_PDL");
+        return !(e && e[0] == '0');
+    }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)k.threads);
+    cfg.dynamicSmemBytes = k.smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = use_pdl ? 1 : 0;
+    PLF_CUDA(ctx, cudaLaunchKernelEx(&cfg, k.fn, reinterpret_cast<const float4 *>(x1),
+                                     reinterpret_cast<const float4 *>(x2), reinterpret_cast<float4 *>(x3), scaler,
+                                     ev, pl, pr, wgt, n, sum, opts ? opts->ev_per_category : 0));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     PLF_CUDA(ctx, cudaGetLastError());
     return PLF_OK;
@@ -398,7 +416,8 @@ int plf_ctx_create(plf_ctx **out, int device, unsigned n_instances, int layout, 
     for (auto &I : ctx->inst) {
         cudaError_t e = cudaStreamCreateWithFlags(&I.stream, cudaStreamNonBlocking);
         for (int m = 0; m < 4 && e == cudaSuccess; ++m) e = cudaEventCreate(&I.marks[m]);
-        if (e == cudaSuccess) e = cudaMalloc(&I.d_sum, sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaMalloc(&I.d_sum, kSumSlots * sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaMemset(I.d_sum, 0, kSumSlots * sizeof(unsigned long long));
         if (e == cudaSuccess) e = cudaMalloc(&I.d_check, sizeof(double));
         if (e == cudaSuccess) e = cudaMallocHost(&I.h_sum, sizeof(unsigned long long));
         if (e == cudaSuccess) e = cudaMallocHost(&I.h_check, sizeof(double));
@@ -409,6 +428,12 @@ int plf_ctx_create(plf_ctx **out, int device, unsigned n_instances, int layout, 
         }
         *I.h_sum = 0;
         *I.h_check = 0.0;
+    }
+    {
+        KernelSel k = pick_kernel(PLF_MATH_STRICT, kDefaultVariant, kDefaultThreads);
+        cudaFuncAttributes attr;
+        if (k.fn && cudaFuncGetAttributes(&attr, k.fn) == cudaSuccess) prepare_kernel(nullptr, k);
+        cudaGetLastError();
     }
     if (input_src == PLF_INPUT_GEN) {
         rc = gen_pattern_device(nullptr, &ctx->d_gen);
@@ -578,7 +603,11 @@ int plf_run_async(plf_ctx *ctx, unsigned inst, size_t sites)
         return fail(ctx, PLF_ERR_INVALID, "run of %zu sites exceeds the instance capacity of %zu", sites,
                     I->max_sites);
     PLF_CUDA(ctx, cudaSetDevice(ctx->device));
-    PLF_CUDA(ctx, cudaMemsetAsync(I->d_sum, 0, sizeof(unsigned long long), I->stream));
+    // every run accumulates into its own zeroed counter; the ring is re-zeroed once per kSumSlots runs
+    const unsigned slot = (unsigned)(I->runs % kSumSlots);
+    if (slot == 0 && I->runs != 0)
+        PLF_CUDA(ctx, cudaMemsetAsync(I->d_sum, 0, kSumSlots * sizeof(unsigned long long), I->stream));
+    unsigned long long *d_sum = I->d_sum + slot;
     plf_launch_opts opts;
     opts.math_mode = ctx->math;
     opts.variant = ctx->variant;
@@ -592,18 +621,15 @@ int plf_run_async(plf_ctx *ctx, unsigned inst, size_t sites)
         const float *pr = ctx->layout == PLF_LAYOUT_COMB ? I->d_right + PLF_EV_FLOATS : I->d_right;
         const float *x2 = I->d_right + right_header(ctx);
         rc = launch_newview(ctx, x1, x2, I->d_out, I->d_scaler, ev, pl, pr,
-                            I->use_wgt ? I->d_wgt : nullptr, sites, I->d_sum, &opts, I->stream);
+                            I->use_wgt ? I->d_wgt : nullptr, sites, d_sum, &opts, I->stream);
     } else {
         PLF_CUDA(ctx, cudaMemsetAsync(I->d_check, 0, sizeof(double), I->stream));
-        rc = launch_gen(ctx, I->d_out, I->d_scaler, ctx->d_gen, sites, I->d_sum, I->d_check,
+        rc = launch_gen(ctx, I->d_out, I->d_scaler, ctx->d_gen, sites, d_sum, I->d_check,
                         ctx->gen_sink, &opts, I->stream);
-        if (rc == PLF_OK)
-            PLF_CUDA(ctx, cudaMemcpyAsync(I->h_check, I->d_check, sizeof(double), cudaMemcpyDeviceToHost,
-                                          I->stream));
     }
     if (rc != PLF_OK) return rc;
-    PLF_CUDA(ctx, cudaMemcpyAsync(I->h_sum, I->d_sum, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
-                                  I->stream));
+    I->sum_slot = slot;
+    ++I->runs;
     return PLF_OK;
 }
 
@@ -655,6 +681,13 @@ int plf_scaler_increment(plf_ctx *ctx, unsigned inst, long long *increment)
     int rc = check_inst(ctx, inst, false, &I);
     if (rc != PLF_OK) return rc;
     if (!increment) return fail(ctx, PLF_ERR_INVALID, "NULL increment");
+    if (I->runs == 0) {
+        *increment = 0;
+        return PLF_OK;
+    }
+    PLF_CUDA(ctx, cudaSetDevice(ctx->device));
+    PLF_CUDA(ctx, cudaMemcpyAsync(I->h_sum, I->d_sum + I->sum_slot, sizeof(unsigned long long),
+                                  cudaMemcpyDeviceToHost, I->stream));
     rc = plf_wait(ctx, inst);
     if (rc != PLF_OK) return rc;
     *increment = (long long)*I->h_sum;
@@ -667,6 +700,8 @@ int plf_gen_checksum(plf_ctx *ctx, unsigned inst, double *checksum)
     int rc = check_inst(ctx, inst, false, &I);
     if (rc != PLF_OK) return rc;
     if (!checksum) return fail(ctx, PLF_ERR_INVALID, "NULL checksum");
+    PLF_CUDA(ctx, cudaSetDevice(ctx->device));
+    PLF_CUDA(ctx, cudaMemcpyAsync(I->h_check, I->d_check, sizeof(double), cudaMemcpyDeviceToHost, I->stream));
     rc = plf_wait(ctx, inst);
     if (rc != PLF_OK) return rc;
     *checksum = *I->h_check;

@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <new>
 #include <string>
 #include <vector>
@@ -127,8 +128,25 @@ int launch_level(plf_tree *t, const BatchSel &k, size_t level, cudaStream_t s)
     // behind two dependent global loads) as rarely as possible; never longer than one op.
     size_t chunk = (size_t)t->tune_chunk;
     if (chunk == 0) chunk = std::max<size_t>(1, std::min(spo, stages / (16 * grid)));
-    k.fn<<<(int)grid, k.threads, k.smem, s>>>(t->d_ops + t->level_op_offset[level], n_ops, t->n_sites,
-                                              t->use_wgt ? t->d_wgt : nullptr, t->d_sum, (unsigned)chunk);
+    // programmatic dependent launch between consecutive levels: the next level's CTAs take over SMs as
+    // this level drains and wait in griddepcontrol.wait for its completion (PLF_PDL=0 disables)
+    static const bool use_pdl = [] {
+        const char *e = getenv("PLF_PDL");
+        return !(e && e[0] == '0');
+    }();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)k.threads);
+    cfg.dynamicSmemBytes = k.smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (use_pdl && level > 0) ? 1 : 0;      // level 0 follows a memset node: plain dependency
+    const plf::BatchOp *ops = t->d_ops + t->level_op_offset[level];
+    const int *wgt = t->use_wgt ? t->d_wgt : nullptr;
+    TREE_CUDA(t, cudaLaunchKernelEx(&cfg, k.fn, ops, n_ops, t->n_sites, wgt, t->d_sum, (unsigned)chunk));
     TREE_CUDA(t, cudaGetLastError());
     return PLF_OK;
 }

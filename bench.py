@@ -93,10 +93,12 @@ def host_inputs_tiled(n_sites: int):
     return ev, left, right, x1, x2, np.ones(n_sites, np.int32)
 
 
-def cpu_reference_rate(n_sites: int, repeats: int, threads: int):
+def cpu_reference_rate(n_sites: int, repeats: int, threads: int, lib: str | None = None):
     """Best-of-`repeats` sites/s of the reference plf() over n_sites with `threads` threads."""
     import oracle
-    if oracle.RefOracle.available():
+    if lib is not None:
+        ref, kind = oracle.RefOracle(lib), "reference"
+    elif oracle.RefOracle.available():
         ref, kind = oracle.RefOracle(), "reference"
     else:
         ref, kind = None, "port"
@@ -285,6 +287,10 @@ def run_b200_arm(args):
                          "each running the unmodified plf() on a contiguous site range "
                          "(-O2 -ffp-contract=off)",
                "single_thread_sites_per_s": (1 << 20) / min(t1)}
+        import oracle
+        if os.path.exists(oracle.LIB_REF_O0):      # the reference's own host flags: -g, no optimisation
+            _, t0 = cpu_reference_rate(1 << 20, 2, 1, oracle.LIB_REF_O0)
+            cpu["single_thread_sites_per_s_reference_flags_g_O0"] = (1 << 20) / min(t0)
 
     if world > 1:
         dist.barrier()

@@ -305,6 +305,24 @@ def test_repeated_calls_reuse_buffers(pkg, gpu, coracle):
             assert np.array_equal(bits(out), bits(o3))
 
 
+def test_scaler_counter_ring_wraps(pkg, gpu, coracle):
+    """The per-run scaler counters live in a ring that is re-zeroed every 1024 runs."""
+    n = 64
+    ev, left, right, x1, x2, wgt = signed_inputs(n, seed=21)
+    x1[::2] = 0.0                                   # half of the sites rescale
+    _, _, oinc = coracle.newview(x1, x2, ev, left, right, wgt)
+    with pkg.Context(0, 1) as ctx:
+        ctx.instance_alloc(0, n)
+        assert ctx.scaler_increment(0) == 0          # nothing has run yet
+        ctx.write_left(0, pkg.pack_left(ev, left, x1))
+        ctx.write_right(0, pkg.pack_right(ev, right, x2))
+        ctx.write_wgt(0, wgt)
+        for call in range(2100):
+            ctx.run_async(0, n)
+            if call in (0, 1, 1022, 1023, 1024, 1025, 2047, 2048, 2099):
+                assert ctx.scaler_increment(0) == oinc, call
+
+
 def test_pinned_host_buffers_and_marks(pkg, gpu, coracle):
     n = 100_000
     ev, left, right, x1, x2, _ = oracle.host_mem_inputs(n, seed=4)
