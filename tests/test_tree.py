@@ -108,3 +108,34 @@ def test_tree_error_behaviour(pkg):
             t.write_tip(4, np.zeros((10, 16), np.float32))                        # tip out of range
         with pytest.raises(pkg.PlfError):
             t.write_tip(0, np.zeros((11, 16), np.float32))                        # too large
+
+
+@pytest.mark.gpu
+def test_tree_stress_single_busy_cta_with_poisoned_memory(pkg, coracle):
+    """Regression for the ring's write-after-read hazard (profiles/r01_tree.md): one CTA does a whole
+    level (chunk >= level size), refills come from L2 and are fast, device memory is poisoned with
+    NaNs between iterations.  Before the proxy fence in the slot release ~1 in 3 iterations failed."""
+    import torch
+    cases = []
+    for shape, n_tips, n in (("random", 257, 517), ("balanced", 64, 3001)):
+        left, right = pkg.random_tree(n_tips, seed=n) if shape == "random" else pkg.balanced_tree(n_tips)
+        tips, ev, pl, pr, wgt = tree_inputs(n_tips, n, seed=n_tips)
+        cases.append((left, right, n_tips, n, tips, ev, pl, pr, wgt,
+                      tree_oracle.traverse(coracle, left, right, tips, ev, pl, pr, wgt)))
+    for it in range(12):
+        poison = torch.full((32 << 20,), float("nan"), device="cuda")
+        del poison
+        torch.cuda.empty_cache()
+        for left, right, n_tips, n, tips, ev, pl, pr, wgt, (o_root, o_cnt, o_total) in cases:
+            for u in (1, 2):
+                with pkg.Tree(left, right, n) as t:
+                    t.set_tuning(u, 1000)
+                    for i in range(n_tips):
+                        t.write_tip(i, tips[i])
+                    t.write_matrices(ev, pl, pr)
+                    t.write_wgt(wgt)
+                    for _ in range(2):
+                        t.run_async()
+                        root, cnt = t.read_root()
+                        assert np.array_equal(bits(root), bits(o_root)), (it, u, first_mismatch(root, o_root))
+                        assert np.array_equal(cnt, o_cnt) and t.total_scalings() == o_total
