@@ -92,6 +92,9 @@ PROTOTYPES = {
     "plf_generate_device": (_i, [_vp, _vp, _sz, _sz, ctypes.c_uint64, _vp]),
     "plf_generate_host": (_i, [_vp, _vp, _sz, _sz, ctypes.c_uint64]),
     "plf_tree_create": (_i, [ctypes.POINTER(_vp), _i, _u, _vp, _vp, _sz]),
+    "plf_tree_create_ex": (_i, [ctypes.POINTER(_vp), _i, _u, _vp, _vp, _sz, _i]),
+    "plf_tree_write_tip_codes": (_i, [_vp, _u, _vp, _sz, _sz]),
+    "plf_tree_write_tip_vector": (_i, [_vp, _vp]),
     "plf_tree_destroy": (_i, [_vp]),
     "plf_tree_last_error": (ctypes.c_char_p, [_vp]),
     "plf_tree_set_math": (_i, [_vp, _i]),
@@ -508,16 +511,17 @@ class Tree:
     """Post-order traversal of a rooted binary tree on one GPU: every inner node is one fused
     newview of its two children; all nodes of one level run in one launch."""
 
-    def __init__(self, left, right, n_sites: int, device: int = 0):
+    def __init__(self, left, right, n_sites: int, device: int = 0, tip_codes: bool = False):
         self.lib = load()
+        self.tip_codes = tip_codes
         self.left = np.ascontiguousarray(left, np.int32)
         self.right = np.ascontiguousarray(right, np.int32)
         self.n_inner = self.left.size
         self.n_tips = self.n_inner + 1
         self.n_sites = n_sites
         self._t = _vp()
-        rc = self.lib.plf_tree_create(ctypes.byref(self._t), device, self.n_tips, _ptr(self.left),
-                                      _ptr(self.right), n_sites)
+        rc = self.lib.plf_tree_create_ex(ctypes.byref(self._t), device, self.n_tips, _ptr(self.left),
+                                         _ptr(self.right), n_sites, 1 if tip_codes else 0)
         if rc != 0:
             raise PlfError(rc, self.lib.plf_tree_last_error(None).decode())
 
@@ -557,6 +561,15 @@ class Tree:
         clv = np.ascontiguousarray(clv, np.float32)
         self._ck(self.lib.plf_tree_write_tip(self._t, tip, _ptr(clv), clv.nbytes, offset))
         self.wait()     # clv may be a temporary
+
+    def write_tip_codes(self, tip: int, codes, first_site: int = 0):
+        codes = np.ascontiguousarray(codes, np.uint8)
+        self._ck(self.lib.plf_tree_write_tip_codes(self._t, tip, _ptr(codes), codes.size, first_site))
+        self.wait()
+
+    def write_tip_vector(self, tip_vector):
+        tv = np.ascontiguousarray(tip_vector, np.float32).reshape(64)
+        self._ck(self.lib.plf_tree_write_tip_vector(self._t, _ptr(tv)))
 
     def write_matrices(self, ev, p_left, p_right):
         ev = np.ascontiguousarray(ev, np.float32).reshape(16)

@@ -516,12 +516,18 @@ struct BatchOp {
     const float *pl;      // P_left[64], P_right[64], EV[16] of this op
     const float *pr;
     const float *ev;
+    // Compressed tips: when tip1 / tip2 is non-NULL that child is a tip stored
+    // as one state code per site (0..15) and its CLV is x[i][j][l] = tipvec[code_i][l] for every
+    // category j (RAxML's tipVector lookup); x1 / x2 is then ignored.  1 B/site instead of 64.
+    const unsigned char *tip1;
+    const unsigned char *tip2;
+    const float *tipvec;  // [16][4], shared by all ops of a launch; NULL when no op has a compressed tip
 };
 
 template <int U, int WARPS, int DEPTH>
 constexpr size_t batch_smem_bytes()
 {
-    return tma_smem_bytes<U, WARPS, DEPTH>() + (size_t)DEPTH * (WARPS * 8 * U) * sizeof(int) * 2;
+    return tma_smem_bytes<U, WARPS, DEPTH>() + (size_t)DEPTH * (WARPS * 8 * U) * (sizeof(int) * 2 + 2) + 256;
 }
 
 template <class M, int U, int WARPS, int DEPTH, int MINB>
@@ -540,7 +546,10 @@ plf_newview_batch(const BatchOp *__restrict__ ops, int n_ops, size_t n,
     float4 *s2 = s1 + (size_t)DEPTH * STAGE_F4;                        // [DEPTH][STAGE_F4]
     int *c1 = reinterpret_cast<int *>(s2 + (size_t)DEPTH * STAGE_F4);  // [DEPTH][STAGE]
     int *c2 = c1 + (size_t)DEPTH * STAGE;                              // [DEPTH][STAGE]
-    uint64_t *full = reinterpret_cast<uint64_t *>(c2 + (size_t)DEPTH * STAGE);
+    unsigned char *k1s = reinterpret_cast<unsigned char *>(c2 + (size_t)DEPTH * STAGE);   // [DEPTH][STAGE] tip codes
+    unsigned char *k2s = k1s + (size_t)DEPTH * STAGE;
+    float4 *tv = reinterpret_cast<float4 *>(k2s + (size_t)DEPTH * STAGE);                 // [16] tip vector table
+    uint64_t *full = reinterpret_cast<uint64_t *>(tv + 16);
     uint64_t *empty = full + DEPTH;
 
     const int warp = threadIdx.x >> 5;
@@ -560,8 +569,9 @@ plf_newview_batch(const BatchOp *__restrict__ ops, int n_ops, size_t n,
         }
         mbar_fence_init();
     }
-    __syncthreads();
     pdl_wait();                    // everything above overlapped the previous kernel's tail
+    if (threadIdx.x < 16 && ops[0].tipvec) tv[threadIdx.x] = __ldg(reinterpret_cast<const float4 *>(ops[0].tipvec) + threadIdx.x);
+    __syncthreads();
     pdl_launch_dependents();
 
     unsigned long long my_sum = 0;
@@ -571,6 +581,7 @@ plf_newview_batch(const BatchOp *__restrict__ ops, int n_ops, size_t n,
             uint32_t slot = 0, phase = 0, cur_op = 0xffffffffu;
             const float4 *x1 = nullptr, *x2 = nullptr;
             const int *k1 = nullptr, *k2 = nullptr;
+            const unsigned char *tp1 = nullptr, *tp2 = nullptr;
             for (uint32_t q = blockIdx.x; q < n_chunks; q += gridDim.x) {
                 const uint32_t g0 = q * chunk;
                 const uint32_t g1 = g0 + chunk < total ? g0 + chunk : total;
@@ -581,6 +592,8 @@ plf_newview_batch(const BatchOp *__restrict__ ops, int n_ops, size_t n,
                         x2 = ops[op].x2;
                         k1 = ops[op].cnt1;
                         k2 = ops[op].cnt2;
+                        tp1 = ops[op].tip1;
+                        tp2 = ops[op].tip2;
                         cur_op = op;
                     }
                     mbar_wait(&empty[slot], phase ^ 1u);
@@ -588,9 +601,13 @@ plf_newview_batch(const BatchOp *__restrict__ ops, int n_ops, size_t n,
                     const uint32_t sites = st < full_stages ? (uint32_t)STAGE : (uint32_t)(n - s0);
                     const uint32_t bytes = sites * 64u;
                     const uint32_t cbytes = ((sites * 4u) + 15u) & ~15u;     // count vectors are padded to 16 B
-                    mbar_arrive_expect_tx(&full[slot], 2u * bytes + (k1 ? cbytes : 0u) + (k2 ? cbytes : 0u));
-                    bulk_g2s(s1 + slot * STAGE_F4, x1 + s0 * 4, bytes, &full[slot]);
-                    bulk_g2s(s2 + slot * STAGE_F4, x2 + s0 * 4, bytes, &full[slot]);
+                    const uint32_t tbytes = (sites + 15u) & ~15u;            // so are tip code vectors
+                    mbar_arrive_expect_tx(&full[slot], (tp1 ? tbytes : bytes) + (tp2 ? tbytes : bytes) +
+                                                           (k1 ? cbytes : 0u) + (k2 ? cbytes : 0u));
+                    if (tp1) bulk_g2s(k1s + slot * STAGE, tp1 + s0, tbytes, &full[slot]);
+                    else bulk_g2s(s1 + slot * STAGE_F4, x1 + s0 * 4, bytes, &full[slot]);
+                    if (tp2) bulk_g2s(k2s + slot * STAGE, tp2 + s0, tbytes, &full[slot]);
+                    else bulk_g2s(s2 + slot * STAGE_F4, x2 + s0 * 4, bytes, &full[slot]);
                     if (k1) bulk_g2s(c1 + slot * STAGE, k1 + s0, cbytes, &full[slot]);
                     if (k2) bulk_g2s(c2 + slot * STAGE, k2 + s0, cbytes, &full[slot]);
                     if (++slot == DEPTH) {
@@ -632,10 +649,11 @@ plf_newview_batch(const BatchOp *__restrict__ ops, int n_ops, size_t n,
                 mbar_wait(&full[slot], phase);
                 float4 a[U], b[U], r[U];
                 unsigned ballots[U];
+                const uint32_t code_off = slot * STAGE + warp * TILE + site_in_row;
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    a[u] = t1[32 * u];
-                    b[u] = t2[32 * u];
+                    a[u] = o.tip1 ? tv[k1s[code_off + 8 * u] & 15] : t1[32 * u];
+                    b[u] = o.tip2 ? tv[k2s[code_off + 8 * u] & 15] : t2[32 * u];
                 }
                 int cnt = 0;
                 if (lane_live) {

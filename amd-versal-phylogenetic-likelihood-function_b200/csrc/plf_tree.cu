@@ -34,10 +34,12 @@ struct plf_tree {
     std::vector<std::vector<int>> levels;      // inner node indices per level, in execution order
     std::vector<int> slot;                     // pool slot of each inner node
     unsigned n_slots = 0;
-    float *d_tips = nullptr;                   // [n_tips][n_sites*16]
+    int tip_format = 0;                        // 0: dense CLVs, 1: one state code per site + tip vector table
+    float *d_tips = nullptr;                   // dense: [n_tips][n_sites*16]
+    unsigned char *d_codes = nullptr;          // codes: [n_tips][code_stride]
     float *d_pool = nullptr;                   // [n_slots][n_sites*16]
     int *d_counts = nullptr;                   // [n_slots][n_sites]
-    float *d_mats = nullptr;                   // EV[16] | P_left[n_inner][64] | P_right[n_inner][64]
+    float *d_mats = nullptr;                   // EV[16] | P_left[n_inner][64] | P_right[n_inner][64] | tipvec[16][4]
     int *d_wgt = nullptr;
     bool use_wgt = false;
     plf::BatchOp *d_ops = nullptr;             // all ops, level after level
@@ -99,12 +101,23 @@ BatchSel pick_batch(int math, int u)
     return math == PLF_MATH_FMA ? batch_sel<plf::MathFma>(u) : batch_sel<plf::MathStrict>(u);
 }
 
+// tip code vectors are padded to a multiple of 16 bytes (bulk-copy granularity)
+size_t code_stride(const plf_tree *t) { return (t->n_sites + 15) & ~(size_t)15; }
+
+// dense CLV of a node; NULL for a compressed tip
 float *node_clv(plf_tree *t, int node)
 {
     const size_t stride = t->n_sites * PLF_SITE_FLOATS;
-    return node < (int)t->n_tips ? t->d_tips + (size_t)node * stride
-                                 : t->d_pool + (size_t)t->slot[node - t->n_tips] * stride;
+    if (node < (int)t->n_tips) return t->tip_format ? nullptr : t->d_tips + (size_t)node * stride;
+    return t->d_pool + (size_t)t->slot[node - t->n_tips] * stride;
 }
+
+const unsigned char *node_codes(plf_tree *t, int node)
+{
+    return (t->tip_format && node < (int)t->n_tips) ? t->d_codes + (size_t)node * code_stride(t) : nullptr;
+}
+
+float *tipvec_ptr(plf_tree *t) { return t->d_mats + 16 + 128 * (size_t)t->n_inner; }
 
 // count vectors are padded to a multiple of 4 ints so that every stage of them is a legal
 // (16-byte aligned, 16-byte granular) bulk copy
@@ -204,11 +217,19 @@ const char *plf_tree_last_error(const plf_tree *tree)
 
 int plf_tree_create(plf_tree **out, int device, unsigned n_tips, const int *left, const int *right, size_t n_sites)
 {
+    return plf_tree_create_ex(out, device, n_tips, left, right, n_sites, PLF_TIPS_DENSE);
+}
+
+int plf_tree_create_ex(plf_tree **out, int device, unsigned n_tips, const int *left, const int *right, size_t n_sites,
+                       int tip_format)
+{
     if (!out) return tfail(nullptr, PLF_ERR_INVALID, "NULL tree out-pointer");
     *out = nullptr;
     if (n_tips < 2 || !left || !right || n_sites == 0)
         return tfail(nullptr, PLF_ERR_INVALID, "need n_tips >= 2, child arrays and n_sites > 0");
     if (n_sites > (SIZE_MAX / 128)) return tfail(nullptr, PLF_ERR_INVALID, "n_sites too large");
+    if (tip_format != PLF_TIPS_DENSE && tip_format != PLF_TIPS_CODES)
+        return tfail(nullptr, PLF_ERR_INVALID, "unknown tip format %d", tip_format);
     const unsigned n_inner = n_tips - 1;
     // validate: post-order, every node except the root is used exactly once as a child
     std::vector<int> used(n_tips + n_inner, 0);
@@ -234,6 +255,7 @@ int plf_tree_create(plf_tree **out, int device, unsigned n_tips, const int *left
     t->n_tips = n_tips;
     t->n_inner = n_inner;
     t->n_sites = n_sites;
+    t->tip_format = tip_format;
     t->left.assign(left, left + n_inner);
     t->right.assign(right, right + n_inner);
     cudaDeviceGetAttribute(&t->num_sms, cudaDevAttrMultiProcessorCount, device);
@@ -271,11 +293,13 @@ int plf_tree_create(plf_tree **out, int device, unsigned n_tips, const int *left
     cudaError_t e = cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&t->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&t->ev1);
-    if (e == cudaSuccess) e = cudaMalloc(&t->d_tips, clv_bytes * n_tips);
+    if (e == cudaSuccess && tip_format == PLF_TIPS_DENSE) e = cudaMalloc(&t->d_tips, clv_bytes * n_tips);
+    if (e == cudaSuccess && tip_format == PLF_TIPS_CODES) e = cudaMalloc(&t->d_codes, code_stride(t) * n_tips);
+    if (e == cudaSuccess && tip_format == PLF_TIPS_CODES) e = cudaMemset(t->d_codes, 0, code_stride(t) * n_tips);
     if (e == cudaSuccess) e = cudaMalloc(&t->d_pool, clv_bytes * t->n_slots);
     if (e == cudaSuccess) e = cudaMalloc(&t->d_counts, count_stride(t) * sizeof(int) * t->n_slots);
     if (e == cudaSuccess) e = cudaMemset(t->d_counts, 0, count_stride(t) * sizeof(int) * t->n_slots);
-    if (e == cudaSuccess) e = cudaMalloc(&t->d_mats, (16 + 128 * (size_t)n_inner) * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&t->d_mats, (16 + 128 * (size_t)n_inner + 64) * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&t->d_ops, sizeof(plf::BatchOp) * n_inner);
     if (e == cudaSuccess) e = cudaMalloc(&t->d_sum, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMallocHost(&t->h_sum, sizeof(unsigned long long));
@@ -303,6 +327,9 @@ int plf_tree_create(plf_tree **out, int device, unsigned n_tips, const int *left
             o.cnt2 = node_counts(t, t->right[k]);
             o.cnt3 = node_counts(t, (int)n_tips + k);
             o.scaler = nullptr;
+            o.tip1 = node_codes(t, t->left[k]);
+            o.tip2 = node_codes(t, t->right[k]);
+            o.tipvec = tip_format == PLF_TIPS_CODES ? tipvec_ptr(t) : nullptr;
             o.ev = t->d_mats;
             o.pl = t->d_mats + 16 + 64 * (size_t)k;
             o.pr = t->d_mats + 16 + 64 * (size_t)n_inner + 64 * (size_t)k;
@@ -326,6 +353,7 @@ int plf_tree_destroy(plf_tree *t)
     if (t->stream) cudaStreamSynchronize(t->stream);
     if (t->exec) cudaGraphExecDestroy(t->exec);
     cudaFree(t->d_tips);
+    cudaFree(t->d_codes);
     cudaFree(t->d_pool);
     cudaFree(t->d_counts);
     cudaFree(t->d_mats);
@@ -363,6 +391,7 @@ int plf_tree_tip_ptr(plf_tree *t, unsigned tip, float **clv)
 {
     if (!t || !clv) return tfail(t, PLF_ERR_INVALID, "NULL argument");
     if (tip >= t->n_tips) return tfail(t, PLF_ERR_INVALID, "tip %u out of range (%u tips)", tip, t->n_tips);
+    if (t->tip_format != PLF_TIPS_DENSE) return tfail(t, PLF_ERR_STATE, "tree stores tips as state codes: use plf_tree_write_tip_codes");
     *clv = node_clv(t, (int)tip);
     return PLF_OK;
 }
@@ -371,6 +400,7 @@ int plf_tree_write_tip(plf_tree *t, unsigned tip, const float *clv, size_t bytes
 {
     if (!t) return tfail(nullptr, PLF_ERR_INVALID, "NULL tree");
     if (tip >= t->n_tips) return tfail(t, PLF_ERR_INVALID, "tip %u out of range (%u tips)", tip, t->n_tips);
+    if (t->tip_format != PLF_TIPS_DENSE) return tfail(t, PLF_ERR_STATE, "tree stores tips as state codes: use plf_tree_write_tip_codes");
     const size_t cap = t->n_sites * PLF_SITE_FLOATS * sizeof(float);
     if (offset > cap || bytes > cap - offset) return tfail(t, PLF_ERR_INVALID, "write exceeds the tip CLV (%zu bytes)", cap);
     if (bytes == 0) return PLF_OK;
@@ -378,6 +408,30 @@ int plf_tree_write_tip(plf_tree *t, unsigned tip, const float *clv, size_t bytes
     TREE_CUDA(t, cudaSetDevice(t->device));
     TREE_CUDA(t, cudaMemcpyAsync(reinterpret_cast<char *>(node_clv(t, (int)tip)) + offset, clv, bytes,
                                  cudaMemcpyHostToDevice, t->stream));
+    return PLF_OK;
+}
+
+int plf_tree_write_tip_codes(plf_tree *t, unsigned tip, const unsigned char *codes, size_t n, size_t first_site)
+{
+    if (!t) return tfail(nullptr, PLF_ERR_INVALID, "NULL tree");
+    if (t->tip_format != PLF_TIPS_CODES) return tfail(t, PLF_ERR_STATE, "tree stores dense tip CLVs: use plf_tree_write_tip");
+    if (tip >= t->n_tips) return tfail(t, PLF_ERR_INVALID, "tip %u out of range (%u tips)", tip, t->n_tips);
+    if (first_site > t->n_sites || n > t->n_sites - first_site) return tfail(t, PLF_ERR_INVALID, "site range out of bounds");
+    if (n == 0) return PLF_OK;
+    if (!codes) return tfail(t, PLF_ERR_INVALID, "NULL host buffer");
+    TREE_CUDA(t, cudaSetDevice(t->device));
+    TREE_CUDA(t, cudaMemcpyAsync(t->d_codes + (size_t)tip * code_stride(t) + first_site, codes, n, cudaMemcpyHostToDevice,
+                                 t->stream));
+    return PLF_OK;
+}
+
+int plf_tree_write_tip_vector(plf_tree *t, const float *tip_vector)
+{
+    if (!t || !tip_vector) return tfail(t, PLF_ERR_INVALID, "NULL argument");
+    if (t->tip_format != PLF_TIPS_CODES) return tfail(t, PLF_ERR_STATE, "tree stores dense tip CLVs");
+    TREE_CUDA(t, cudaSetDevice(t->device));
+    TREE_CUDA(t, cudaMemcpyAsync(tipvec_ptr(t), tip_vector, 64 * sizeof(float), cudaMemcpyHostToDevice, t->stream));
+    TREE_CUDA(t, cudaStreamSynchronize(t->stream));
     return PLF_OK;
 }
 
@@ -465,13 +519,18 @@ int plf_tree_info(plf_tree *t, unsigned *levels, unsigned *clv_slots, size_t *de
     if (levels) *levels = (unsigned)t->levels.size();
     if (clv_slots) *clv_slots = t->n_slots;
     if (device_bytes)
-        *device_bytes = t->n_sites * 64 * ((size_t)t->n_tips + t->n_slots) + t->n_sites * 4 * (size_t)t->n_slots;
+        *device_bytes = (t->tip_format ? code_stride(t) * (size_t)t->n_tips : t->n_sites * 64 * (size_t)t->n_tips) +
+                        t->n_sites * 64 * (size_t)t->n_slots + count_stride(t) * 4 * (size_t)t->n_slots;
     if (traversal_bytes) {
-        // 193 B per site per node + 4 B per count vector actually read (inner children) or written
+        // per node: 64 B/site written, 64 B/site read per dense child (1 B/site per compressed tip),
+        // + 4 B per count vector read (inner children) or written
         size_t inner_children = 0;
         for (unsigned k = 0; k < t->n_inner; ++k)
             inner_children += (t->left[k] >= (int)t->n_tips) + (t->right[k] >= (int)t->n_tips);
-        *traversal_bytes = t->n_sites * (192 * (size_t)t->n_inner + 4 * ((size_t)t->n_inner + inner_children));
+        const size_t tip_children = 2 * (size_t)t->n_inner - inner_children;
+        const size_t tip_read = t->tip_format ? 1 : 64;
+        *traversal_bytes = t->n_sites * (64 * (size_t)t->n_inner + 64 * inner_children + tip_read * tip_children +
+                                         4 * ((size_t)t->n_inner + inner_children));
     }
     return PLF_OK;
 }
@@ -486,6 +545,8 @@ int plf_tree_evaluate_root(plf_tree *t, const float *diag, double *lnl)
     TREE_CUDA(t, cudaMemsetAsync(t->d_lnl, 0, sizeof(double), t->stream));
     TREE_CUDA(t, cudaMemcpyAsync(d_diag, diag, 16 * sizeof(float), cudaMemcpyHostToDevice, t->stream));
     const int a = t->left[t->n_inner - 1], b = t->right[t->n_inner - 1];
+    if (!node_clv(t, a) || !node_clv(t, b))
+        return tfail(t, PLF_ERR_STATE, "a child of the root is a compressed tip: evaluate needs two dense CLVs");
     int rc = plf::launch_evaluate(node_clv(t, a), node_clv(t, b), node_counts(t, a), node_counts(t, b),
                                   t->use_wgt ? t->d_wgt : nullptr, d_diag, t->n_sites, t->d_lnl, t->stream);
     if (rc != PLF_OK) return tfail(t, rc, "evaluate kernel launch failed");

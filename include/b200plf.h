@@ -205,6 +205,17 @@ typedef struct plf_tree plf_tree;
  * n_tips tip CLVs, a recycled pool of inner CLVs + int32 scaler-count vectors, matrices.       */
 int plf_tree_create(plf_tree **tree, int device, unsigned n_tips, const int *left, const int *right,
                     size_t n_sites);
+/* Tip storage.  DENSE: a tip is a full CLV (64 B/site), written with
+ * plf_tree_write_tip.  CODES: a tip is one state code per site (0..15, the 4-bit ambiguity code of a
+ * DNA alignment) and its CLV is x[i][j][l] = tip_vector[code_i][l] for every category j (RAxML's
+ * tipVector lookup) -- 1 B/site of HBM traffic and memory instead of 64.                        */
+typedef enum plf_tip_format { PLF_TIPS_DENSE = 0, PLF_TIPS_CODES = 1 } plf_tip_format;
+int plf_tree_create_ex(plf_tree **tree, int device, unsigned n_tips, const int *left, const int *right,
+                       size_t n_sites, int tip_format);
+/* CODES trees: n state codes of a tip starting at first_site; the 16 x 4 table tip_vector[code][state]. */
+int plf_tree_write_tip_codes(plf_tree *tree, unsigned tip, const unsigned char *codes, size_t n,
+                             size_t first_site);
+int plf_tree_write_tip_vector(plf_tree *tree, const float *tip_vector);
 int plf_tree_destroy(plf_tree *tree);
 const char *plf_tree_last_error(const plf_tree *tree);
 int plf_tree_set_math(plf_tree *tree, int math_mode);

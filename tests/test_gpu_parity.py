@@ -286,6 +286,42 @@ def test_instances_are_independent_streams(pkg, gpu, coracle):
         assert len({ctx.stream(k) for k in range(9)}) == 9
 
 
+def test_instances_driven_from_host_threads(pkg, gpu, coracle):
+    """The ABI is thread-compatible: distinct instances of one ctx driven from distinct host threads
+    (the reference drives each instance from its own xrt::queue workers, host_mem.cpp:249-260)."""
+    import threading
+    n, calls, inst = 20000, 20, 6
+    data = [signed_inputs(n, seed=300 + k) for k in range(inst)]
+    want = [coracle.newview(x1, x2, ev, left, right, wgt) for ev, left, right, x1, x2, wgt in data]
+    errors = []
+    with pkg.Context(0, inst) as ctx:
+        def worker(k):
+            try:
+                ev, left, right, x1, x2, wgt = data[k]
+                lb, rb = pkg.pack_left(ev, left, x1), pkg.pack_right(ev, right, x2)
+                out = np.empty((n, 16), np.float32)
+                sc = np.empty(n, np.uint8)
+                ctx.instance_alloc(k, n)
+                for _ in range(calls):
+                    ctx.write_left(k, lb)
+                    ctx.write_right(k, rb)
+                    ctx.write_wgt(k, wgt)
+                    ctx.run_async(k, n)
+                    ctx.read_out(k, out)
+                    ctx.read_scaler(k, sc)
+                    ctx.wait(k)
+                    assert ctx.scaler_increment(k) == want[k][2]
+                    assert np.array_equal(bits(out), bits(want[k][0])) and np.array_equal(sc, want[k][1])
+            except Exception as e:          # surfaced in the main thread
+                errors.append((k, repr(e)))
+        threads = [threading.Thread(target=worker, args=(k,)) for k in range(inst)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    assert not errors, errors
+
+
 def test_repeated_calls_reuse_buffers(pkg, gpu, coracle):
     """plf_calls > 1: the run handle and buffers are reused (host_mem.cpp:283-325)."""
     n = 3000

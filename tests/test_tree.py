@@ -139,3 +139,59 @@ def test_tree_stress_single_busy_cta_with_poisoned_memory(pkg, coracle):
                         root, cnt = t.read_root()
                         assert np.array_equal(bits(root), bits(o_root)), (it, u, first_mismatch(root, o_root))
                         assert np.array_equal(cnt, o_cnt) and t.total_scalings() == o_total
+
+
+def expand_tip_codes(codes, tip_vector):
+    """Dense CLV of a compressed tip: x[i][j][l] = tip_vector[code_i][l] for every category j."""
+    tv = np.asarray(tip_vector, np.float32).reshape(16, 4)
+    return np.tile(tv[codes], (1, 4)).astype(np.float32)          # [n, 16]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,n_tips,n", [("balanced", 64, 3001), ("random", 33, 1000), ("balanced", 2, 129),
+                                             ("random", 257, 517), ("caterpillar", 12, 4099)])
+@pytest.mark.parametrize("u,chunk", [(0, 0), (1, 1), (2, 3), (1, 1000)])
+def test_tree_with_compressed_tips_matches_dense_oracle(pkg, coracle, shape, n_tips, n, u, chunk):
+    """tips stored as one state code per site + a 16x4 tip-vector table give exactly the
+    traversal of the expanded dense tips (tip-tip, tip-inner and inner-inner nodes all occur)."""
+    if shape == "balanced":
+        left, right = pkg.balanced_tree(n_tips)
+    elif shape == "random":
+        left, right = pkg.random_tree(n_tips, seed=n)
+    else:
+        left = np.array([0] + [n_tips + k for k in range(n_tips - 2)], np.int32)
+        right = np.arange(1, n_tips, dtype=np.int32)
+    rng = np.random.RandomState(n_tips + n)
+    codes = rng.randint(0, 16, (n_tips, n)).astype(np.uint8)
+    tip_vector = (rng.random_sample((16, 4)) * 10.0 ** rng.uniform(-9, 0, (16, 1))).astype(np.float32)
+    _, ev, pl, pr, wgt = tree_inputs(n_tips, 4, seed=n_tips)
+    wgt = rng.randint(1, 6, n).astype(np.int32)
+    dense = np.stack([expand_tip_codes(codes[i], tip_vector) for i in range(n_tips)])
+    o_root, o_cnt, o_total = tree_oracle.traverse(coracle, left, right, dense, ev, pl, pr, wgt)
+    with pkg.Tree(left, right, n, tip_codes=True) as t:
+        t.set_tuning(u, chunk)
+        for i in range(n_tips):
+            t.write_tip_codes(i, codes[i])
+        t.write_tip_vector(tip_vector)
+        t.write_matrices(ev, pl, pr)
+        t.write_wgt(wgt)
+        with pytest.raises(pkg.PlfError):
+            t.write_tip(0, dense[0])                      # wrong tip format for this tree
+        for _ in range(2):
+            t.run_async()
+            root, cnt = t.read_root()
+            assert np.array_equal(bits(root), bits(o_root)), first_mismatch(root, o_root)
+            assert np.array_equal(cnt, o_cnt) and t.total_scalings() == o_total
+        dense_bytes = n * 64 * n_tips
+        assert t.info()["device_bytes"] < dense_bytes + n * 68 * (n_tips - 1)     # tips cost 1 B/site, not 64
+    assert o_cnt.max() >= 1
+
+
+@pytest.mark.gpu
+def test_dense_tree_rejects_tip_codes(pkg):
+    left, right = pkg.balanced_tree(4)
+    with pkg.Tree(left, right, 10) as t:
+        with pytest.raises(pkg.PlfError):
+            t.write_tip_codes(0, np.zeros(10, np.uint8))
+        with pytest.raises(pkg.PlfError):
+            t.write_tip_vector(np.zeros(64, np.float32))

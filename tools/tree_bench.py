@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--u", type=int, default=0)
     ap.add_argument("--chunk", type=int, default=0)
     ap.add_argument("--math", default="strict")
+    ap.add_argument("--tip-codes", action="store_true", help="tips as 1 B/site state codes + tip vector table")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
 
@@ -59,14 +60,20 @@ def main():
     pl = stochastic(args.tips - 1, 4).reshape(args.tips - 1, 64)
     pr = stochastic(args.tips - 1, 4).reshape(args.tips - 1, 64)
 
-    t = pkg.Tree(left, right, n, device=local)
+    t = pkg.Tree(left, right, n, device=local, tip_codes=args.tip_codes)
     t.set_tuning(args.u, args.chunk)
     t.set_math(pkg.MATH_FMA if args.math == "fma" else pkg.MATH_STRICT)
-    scratch = torch.empty((n, 16), device=device)
-    for tip in range(args.tips):      # x1-stream of the generator for even tips, x2-stream for odd ones
-        a, b = (t.tip_ptr(tip), scratch.data_ptr()) if tip % 2 == 0 else (scratch.data_ptr(), t.tip_ptr(tip))
-        pkg.generate_device(a, b, first + tip * 7919, n, 1000 + tip)
-    torch.cuda.synchronize()
+    if args.tip_codes:
+        tv = (rng.random_sample((16, 4)) * np.where(np.arange(16)[:, None] % 4 == 0, 1e-10, 1.0)).astype(np.float32)
+        t.write_tip_vector(tv)
+        for tip in range(args.tips):
+            t.write_tip_codes(tip, np.random.RandomState(first + tip).randint(0, 16, n).astype(np.uint8))
+    else:
+        scratch = torch.empty((n, 16), device=device)
+        for tip in range(args.tips):      # x1-stream of the generator for even tips, x2-stream for odd ones
+            a, b = (t.tip_ptr(tip), scratch.data_ptr()) if tip % 2 == 0 else (scratch.data_ptr(), t.tip_ptr(tip))
+            pkg.generate_device(a, b, first + tip * 7919, n, 1000 + tip)
+        torch.cuda.synchronize()
     t.write_matrices(ev, pl, pr)
     info = t.info()
     for _ in range(3):
@@ -94,7 +101,8 @@ def main():
                "newview_sites_per_s": nodes * args.sites / (ms_max * 1e-3),
                "hbm_gbs_per_gpu": info["traversal_bytes"] / (ms_max * 1e-3) / 1e9,
                "total_scalings": total, "log_likelihood": lnl, "root_count_max": int(cnt.max()), "root_finite": bool(np.isfinite(root).all()),
-               "u": args.u, "chunk": args.chunk, "math": args.math}
+               "u": args.u, "chunk": args.chunk, "math": args.math, "tip_codes": args.tip_codes,
+               "traversal_GB": info["traversal_bytes"] / 1e9}
         print(json.dumps(row), flush=True)
         if args.out:
             with open(args.out, "a") as f:
