@@ -301,25 +301,40 @@ __device__ __forceinline__ void mbar_fence_init()
 {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-// Orders this thread's generic-proxy shared-memory accesses (the LDS reads of a ring slot) before
-// later async-proxy accesses (the bulk copy that refills the slot).  Without it the release below
-// can overtake the reads: with a fast refill (data in L2, one busy CTA) the first bytes of the next
-// stage then land in the slot while a warp is still reading it.
+// Releasing a ring slot.  The consumer's LDS reads of the slot must be COMPLETE before the producer is
+// allowed to refill it with the bulk-copy engine: an mbarrier.arrive issued right after the LDS
+// instructions can overtake them, and with a fast refill (data in L2, one busy CTA) the first bytes of
+// the next stage then land in the slot while a warp is still reading it (found by the tree stress
+// test, profiles/r01_tree.md).  Two ways to close the window:
+//   * fence.proxy.async.shared::cta before the arrive (the CUTLASS consumer_release pattern for
+//     ld.shared consumers).  ptxas emits MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC.S, which also waits for the
+//     warp's outstanding GLOBAL stores -- invisible while DRAM-bound, but it caps a traffic-light
+//     kernel (compressed tips) at ~2600 cycles per stage;
+//   * make the arrive DATA-DEPENDENT on the loaded registers: a load whose value has been consumed
+//     has been performed, and a performed read cannot be affected by a later write of any proxy.
+// mbar_release_slot() does the second: `dep` is an XOR over one register of every LDS of the slot;
+// the comparison can never be proven by the compiler, both branches arrive exactly once, and the
+// (practically never taken) equal branch falls back to the fence.
 __device__ __forceinline__ void fence_proxy_async_smem()
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-// Consumer release of a ring slot: every lane fences its own reads, then one lane arrives.
-__device__ __forceinline__ void mbar_release_slot(uint64_t *bar, int lane);
+__device__ __forceinline__ void mbar_release_slot(uint64_t *bar, int lane, unsigned dep);
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_release_slot(uint64_t *bar, int lane)
+__device__ __forceinline__ void mbar_release_slot(uint64_t *bar, int lane, unsigned dep)
 {
-    fence_proxy_async_smem();
     __syncwarp();
-    if (lane == 0) mbar_arrive(bar);
+    if (lane == 0) {
+        if (dep != 0x9E3779B9u) {
+            mbar_arrive(bar);
+        } else {
+            fence_proxy_async_smem();
+            mbar_arrive(bar);
+        }
+    }
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
 {
@@ -430,7 +445,10 @@ plf_newview_tma(const float4 *__restrict__ x1, const float4 *__restrict__ x2,
                 b[u] = t2[32 * u];
             }
             // release the slot as soon as this warp's reads of it are complete
-            mbar_release_slot(&empty[slot], lane);
+            unsigned dep = 0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) dep ^= __float_as_uint(a[u].x) ^ __float_as_uint(b[u].w);
+            mbar_release_slot(&empty[slot], lane, dep);
             if (++slot == DEPTH) {
                 slot = 0;
                 phase ^= 1u;
@@ -660,7 +678,10 @@ plf_newview_batch(const BatchOp *__restrict__ ops, int n_ops, size_t n,
                     if (o.cnt1) cnt = c1[slot * STAGE + warp * TILE + lane];
                     if (o.cnt2) cnt += c2[slot * STAGE + warp * TILE + lane];
                 }
-                mbar_release_slot(&empty[slot], lane);
+                unsigned dep = (unsigned)cnt;
+#pragma unroll
+                for (int u = 0; u < U; ++u) dep ^= __float_as_uint(a[u].x) ^ __float_as_uint(b[u].w);
+                mbar_release_slot(&empty[slot], lane, dep);
                 if (++slot == DEPTH) {
                     slot = 0;
                     phase ^= 1u;
