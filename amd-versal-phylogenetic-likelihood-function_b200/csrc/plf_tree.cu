@@ -91,6 +91,8 @@ struct BatchSel {
 template <class M>
 BatchSel batch_sel(int u)
 {
+    // u = 1: 128-site stages x 4;  u = 2: 256-site stages x 3 (default).  A deeper ring (x 6) was
+    // measured and is slower, for dense and for compressed-tip trees alike (profiles/r01_tree.md).
     if (u == 1)
         return {plf::plf_newview_batch<M, 1, 16, 4, 1>, 17 * 32, plf::batch_smem_bytes<1, 16, 4>(), 128};
     return {plf::plf_newview_batch<M, 2, 16, 3, 1>, 17 * 32, plf::batch_smem_bytes<2, 16, 3>(), 256};
