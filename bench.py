@@ -309,11 +309,13 @@ def run_b200_arm(args):
             "hbm_gbs_per_gpu": value * BYTES_PER_SITE / 1e9 / world,
             "frac_of_8TBs_per_gpu": value * BYTES_PER_SITE / 1e9 / world / NOMINAL_HBM_GBS,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": (traffic or {}).get("dram_bytes_per_launch"),
+                         "frac": achieved / peak, "traffic": ((traffic or {}).get("dram_bytes_per_site") or 0) * n or None,
                          "peak_source": peak_src, "launch_ms_mean": mean_launch_ms,
                          "launch_ms_min": min(per_launch_ms), "launch_ms_max": max(per_launch_ms),
                          "algorithmic_bytes_per_launch": BYTES_PER_SITE * n,
-                         "traffic_note": (traffic or {}).get("note")},
+                         "traffic_note": (f"ncu dram bytes per site ({(traffic or {}).get('dram_bytes_per_site', 0):.2f}, captured at "
+                                          f"{(traffic or {}).get('sites_per_launch')} sites/launch) x {n} sites of this launch; "
+                                          + str((traffic or {}).get("note"))) if traffic else None},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_all, "clocks": clocks,
             "scaler_increment": total_inc,
         }
