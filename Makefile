@@ -53,7 +53,7 @@ CSRC := $(PKG)/csrc
 OBJDIR := $(PKG)/build
 KHDRS := $(CSRC)/plf_kernels.cuh $(CSRC)/plf_registry.h include/b200plf.h
 OBJS := $(OBJDIR)/plf_capi.o $(OBJDIR)/plf_tree.o $(OBJDIR)/plf_evaluate.o $(OBJDIR)/sel_ldg_strict.o $(OBJDIR)/sel_ldg_fma.o \
-        $(OBJDIR)/sel_tma_strict.o $(OBJDIR)/sel_tma_fma.o
+        $(OBJDIR)/sel_tma_strict.o $(OBJDIR)/sel_tma_fma.o $(OBJDIR)/sel_dyn_strict.o $(OBJDIR)/sel_dyn_fma.o
 
 $(OBJDIR)/plf_capi.o: $(CSRC)/plf_capi.cu $(KHDRS)
 	@mkdir -p $(OBJDIR)
@@ -79,6 +79,13 @@ $(OBJDIR)/sel_tma_strict.o: $(CSRC)/plf_sel_tma.cu $(KHDRS)
 $(OBJDIR)/sel_tma_fma.o: $(CSRC)/plf_sel_tma.cu $(KHDRS)
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) -DPLF_SEL_MATH=MathFma -DPLF_SEL_NAME=select_tma_fma -c -o $@ $<
+
+$(OBJDIR)/sel_dyn_strict.o: $(CSRC)/plf_sel_tma.cu $(KHDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -DPLF_SEL_DYNAMIC -DPLF_SEL_MATH=MathStrict -DPLF_SEL_NAME=select_tma_dyn_strict -c -o $@ $<
+$(OBJDIR)/sel_dyn_fma.o: $(CSRC)/plf_sel_tma.cu $(KHDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -DPLF_SEL_DYNAMIC -DPLF_SEL_MATH=MathFma -DPLF_SEL_NAME=select_tma_dyn_fma -c -o $@ $<
 
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS)

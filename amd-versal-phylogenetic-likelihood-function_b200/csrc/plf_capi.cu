@@ -103,6 +103,7 @@ KernelSel pick_kernel(int math, int variant, int threads)
     const int u = variant % 10, kind = (variant / 10) % 10, d = (variant / 100) % 10, b = variant / 1000;
     const bool fma = math == PLF_MATH_FMA;
     if (kind == 2) return fma ? plf::select_tma_fma(u, d, b, threads) : plf::select_tma_strict(u, d, b, threads);
+    if (kind == 3) return fma ? plf::select_tma_dyn_fma(u, d, b, threads) : plf::select_tma_dyn_strict(u, d, b, threads);
     if ((kind == 0 || kind == 1) && d == 0)
         return fma ? plf::select_ldg_fma(u, kind, b, threads) : plf::select_ldg_strict(u, kind, b, threads);
     return KernelSel{};
@@ -156,6 +157,32 @@ int resolve_launch(plf_ctx *ctx, const plf_launch_opts *opts, size_t n, KernelSe
     return PLF_OK;
 }
 
+// Work-counter pairs for the dynamically scheduled kernels: one ring per device, zeroed once; every
+// launch takes the next pair and the kernel's last CTA leaves it zeroed again (self-cleaning), so
+// concurrent launches on different streams never share a pair unless kWorkPairs launches are in flight.
+constexpr unsigned kWorkPairs = 4096;
+std::mutex g_work_mu;
+unsigned long long *g_work_dev[64] = {nullptr};
+std::atomic<unsigned> g_work_next{0};
+
+int work_pair(plf_ctx *ctx, unsigned long long **out)
+{
+    int dev = 0;
+    PLF_CUDA(ctx, cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(ctx, PLF_ERR_INVALID, "device ordinal %d out of range", dev);
+    {
+        std::lock_guard<std::mutex> g(g_work_mu);
+        if (!g_work_dev[dev]) {
+            unsigned long long *d = nullptr;
+            PLF_CUDA(ctx, cudaMalloc(&d, 2 * kWorkPairs * sizeof(unsigned long long)));
+            PLF_CUDA(ctx, cudaMemset(d, 0, 2 * kWorkPairs * sizeof(unsigned long long)));
+            g_work_dev[dev] = d;
+        }
+    }
+    *out = g_work_dev[dev] + 2 * (g_work_next.fetch_add(1, std::memory_order_relaxed) % kWorkPairs);
+    return PLF_OK;
+}
+
 int launch_newview(plf_ctx *ctx, const float *x1, const float *x2, float *x3, unsigned char *scaler,
                    const float *ev, const float *pl, const float *pr, const int *wgt, size_t n,
                    unsigned long long *sum, const plf_launch_opts *opts, cudaStream_t stream)
@@ -170,6 +197,11 @@ int launch_newview(plf_ctx *ctx, const float *x1, const float *x2, float *x3, un
     int grid = 0;
     int rc = resolve_launch(ctx, opts, n, &k, &grid);
     if (rc != PLF_OK) return rc;
+    unsigned long long *work = nullptr;
+    if (k.dynamic) {
+        rc = work_pair(ctx, &work);
+        if (rc != PLF_OK) return rc;
+    }
     // Programmatic dependent launch: the kernel's prologue may overlap the tail of the previous kernel
     // in the stream (it blocks in griddepcontrol.wait before touching global memory).  PLF_PDL=0 disables.
     static const bool use_pdl = [] {
@@ -188,7 +220,7 @@ int launch_newview(plf_ctx *ctx, const float *x1, const float *x2, float *x3, un
     cfg.numAttrs = use_pdl ? 1 : 0;
     PLF_CUDA(ctx, cudaLaunchKernelEx(&cfg, k.fn, reinterpret_cast<const float4 *>(x1),
                                      reinterpret_cast<const float4 *>(x2), reinterpret_cast<float4 *>(x3), scaler,
-                                     ev, pl, pr, wgt, n, sum, opts ? opts->ev_per_category : 0));
+                                     ev, pl, pr, wgt, n, sum, opts ? opts->ev_per_category : 0, work));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     PLF_CUDA(ctx, cudaGetLastError());
     return PLF_OK;

@@ -202,7 +202,8 @@ plf_newview_ldg(const float4 *__restrict__ x1, const float4 *__restrict__ x2,
                 float4 *__restrict__ x3, unsigned char *__restrict__ scaler,
                 const float *__restrict__ ev, const float *__restrict__ pl,
                 const float *__restrict__ pr, const int *__restrict__ wgt, size_t n,
-                unsigned long long *__restrict__ scaler_sum, int ev_per_category)
+                unsigned long long *__restrict__ scaler_sum, int ev_per_category,
+                unsigned long long * /*work: unused, static schedule*/)
 {
     constexpr int TILE = 8 * U;                       // sites per warp tile
     const int lane = threadIdx.x & 31;
@@ -368,7 +369,8 @@ plf_newview_tma(const float4 *__restrict__ x1, const float4 *__restrict__ x2,
                 float4 *__restrict__ x3, unsigned char *__restrict__ scaler,
                 const float *__restrict__ ev, const float *__restrict__ pl,
                 const float *__restrict__ pr, const int *__restrict__ wgt, size_t n,
-                unsigned long long *__restrict__ scaler_sum, int ev_per_category)
+                unsigned long long *__restrict__ scaler_sum, int ev_per_category,
+                unsigned long long * /*work: unused, static schedule*/)
 {
     constexpr int THREADS = (WARPS + 1) * 32;
     constexpr int TILE = 8 * U;                 // sites per consumer warp per stage
@@ -502,7 +504,149 @@ plf_newview_tma(const float4 *__restrict__ x1, const float4 *__restrict__ x2,
 template <int U, int WARPS, int DEPTH>
 constexpr size_t tma_smem_bytes()
 {
-    return (size_t)DEPTH * (WARPS * 8 * U) * 64 * 2 + (size_t)DEPTH * 2 * sizeof(uint64_t);
+    return (size_t)DEPTH * (WARPS * 8 * U) * 64 * 2 + (size_t)DEPTH * 2 * sizeof(uint64_t) + 64;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Variant 2b ("tma-dyn"): the same ring kernel with DYNAMIC stage scheduling.  With the static
+// schedule (stage st to CTA st % grid) every SM is given the same share, so the launch lasts as long
+// as its slowest SM: SMs do not get equal DRAM service (two dies, distance to the L2 slices), and
+// the launch-to-launch spread of the static kernel shows it (8 Mi sites: mean 0.256 ms, min
+// 0.240 ms).  Here the producer of each CTA takes the next stage index from a global counter
+// (`work[0]`), publishes it to its consumers through shared memory together with the stage's
+// data, and a sentinel index ends the loop.  The fetch for stage k+1 is issued before the copies of
+// stage k, so the atomic's latency is off the critical path.  The last CTA to finish (`work[1]`
+// counts them) zeroes both words: the pair is clean for its next user without a memset.
+// ---------------------------------------------------------------------------------------------
+template <class M, int U, int WARPS, int DEPTH, int MINB>
+__global__ void __launch_bounds__((WARPS + 1) * 32, MINB)
+plf_newview_tma_dyn(const float4 *__restrict__ x1, const float4 *__restrict__ x2,
+                    float4 *__restrict__ x3, unsigned char *__restrict__ scaler,
+                    const float *__restrict__ ev, const float *__restrict__ pl,
+                    const float *__restrict__ pr, const int *__restrict__ wgt, size_t n,
+                    unsigned long long *__restrict__ scaler_sum, int ev_per_category,
+                    unsigned long long *work)
+{
+    constexpr int THREADS = (WARPS + 1) * 32;
+    constexpr int TILE = 8 * U;
+    constexpr int STAGE = WARPS * TILE;
+    constexpr int STAGE_F4 = STAGE * 4;
+    constexpr uint32_t kDone = 0xffffffffu;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4 *s1 = reinterpret_cast<float4 *>(smem_raw);
+    float4 *s2 = s1 + (size_t)DEPTH * STAGE_F4;
+    uint64_t *full = reinterpret_cast<uint64_t *>(s2 + (size_t)DEPTH * STAGE_F4);
+    uint64_t *empty = full + DEPTH;
+    volatile uint32_t *stage_of = reinterpret_cast<volatile uint32_t *>(empty + DEPTH);   // [DEPTH]
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const unsigned long long n_stages = (n + STAGE - 1) / STAGE;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int d = 0; d < DEPTH; ++d) {
+            mbar_init(&full[d], 1);
+            mbar_init(&empty[d], WARPS);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    pdl_wait();
+    pdl_launch_dependents();
+
+    unsigned long long my_sum = 0;
+
+    if (warp == WARPS) {
+        // ===== producer =====
+        if (lane == 0) {
+            uint32_t slot = 0, phase = 0;
+            unsigned long long next = atomicAdd(work, 1ull);
+            for (;;) {
+                const unsigned long long st = next;
+                mbar_wait(&empty[slot], phase ^ 1u);
+                if (st >= n_stages) {                     // out of work: tell the consumers and stop
+                    stage_of[slot] = kDone;
+                    mbar_arrive(&full[slot]);
+                    break;
+                }
+                next = atomicAdd(work, 1ull);             // needed one iteration from now
+                stage_of[slot] = (uint32_t)st;
+                const size_t s0 = (size_t)st * STAGE;
+                const size_t left = n - s0;
+                const uint32_t bytes = (uint32_t)(left < (size_t)STAGE ? left : (size_t)STAGE) * 64u;
+                mbar_arrive_expect_tx(&full[slot], 2u * bytes);
+                bulk_g2s(s1 + slot * STAGE_F4, x1 + s0 * 4, bytes, &full[slot]);
+                bulk_g2s(s2 + slot * STAGE_F4, x2 + s0 * 4, bytes, &full[slot]);
+                if (++slot == DEPTH) {
+                    slot = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+    } else {
+        // ===== consumers =====
+        const int cat = lane & 3;
+        const int site_in_row = lane >> 2;
+        CatConst c;
+        load_cat_const(c, ev, pl, pr, cat, ev_per_category);
+        const size_t last_full = n / STAGE;
+        const uint32_t tile_off = warp * (TILE * 4) + lane;
+
+        uint32_t slot = 0, phase = 0;
+        for (;;) {
+            const float4 *t1 = s1 + slot * STAGE_F4 + tile_off;
+            const float4 *t2 = s2 + slot * STAGE_F4 + tile_off;
+            mbar_wait(&full[slot], phase);
+            const uint32_t st = stage_of[slot];
+            if (st == kDone) break;
+            float4 a[U], b[U], o[U];
+            unsigned ballots[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                a[u] = t1[32 * u];
+                b[u] = t2[32 * u];
+            }
+            unsigned dep = st;
+#pragma unroll
+            for (int u = 0; u < U; ++u) dep ^= __float_as_uint(a[u].x) ^ __float_as_uint(b[u].w);
+            mbar_release_slot(&empty[slot], lane, dep);
+            if (++slot == DEPTH) {
+                slot = 0;
+                phase ^= 1u;
+            }
+            const size_t s0 = (size_t)st * STAGE + (size_t)warp * TILE;
+            float4 *out = x3 + s0 * 4 + lane;
+            const bool complete = st < last_full;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const bool live = complete || s0 + 8 * u + site_in_row < n;
+                bool small = category_newview<M>(c, a[u], b[u], o[u]);
+                ballots[u] = __ballot_sync(0xffffffffu, small && live);
+                if (nibble_all(ballots[u], site_in_row)) rescale(o[u]);
+                if (live) st_stream(out + 32 * u, o[u]);
+            }
+            if (lane < TILE && (complete || s0 + lane < n)) {
+                unsigned bal = ballots[0];
+#pragma unroll
+                for (int u = 1; u < U; ++u) bal = (lane >> 3) == u ? ballots[u] : bal;
+                const bool scaled = nibble_all(bal, lane & 7);
+                if (scaler) scaler[s0 + lane] = scaled ? 1 : 0;
+                if (scaled) my_sum += wgt ? (unsigned long long)(long long)wgt[s0 + lane] : 1ull;
+            }
+        }
+    }
+    if (scaler_sum) block_add_u64<THREADS>(my_sum, scaler_sum);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned long long finished = atomicAdd(work + 1, 1ull);
+        if (finished == gridDim.x - 1) {          // last CTA out: leave the pair clean for its next user
+            work[0] = 0ull;
+            work[1] = 0ull;
+            __threadfence();
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

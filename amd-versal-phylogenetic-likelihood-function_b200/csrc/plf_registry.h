@@ -4,7 +4,8 @@
 //   U : 128-bit loads per child per thread per tile (1, 2 or 4)
 //   K : 0 = "ldg" register-staged kernel with streaming load/store policy
 //       1 = "ldg" with plain (cached) loads/stores
-//       2 = "tma" bulk-copy / mbarrier ring kernel
+//       2 = "tma" bulk-copy / mbarrier ring kernel, static stage schedule
+//       3 = "tma-dyn": the same ring with dynamic stage scheduling (global work counter)
 //   D : tma only: ring depth in stages (2, 3, 4, 6; 0 -> 4)
 //   B : minimum resident blocks per SM given to __launch_bounds__ (0 -> 1); caps registers/thread
 // threads_per_block is the number of COMPUTE threads: 128, 256 or 512 (tma adds one producer warp).
@@ -18,13 +19,15 @@
 namespace plf {
 
 using NewviewFn = void (*)(const float4 *, const float4 *, float4 *, unsigned char *, const float *,
-                           const float *, const float *, const int *, size_t, unsigned long long *, int);
+                           const float *, const float *, const int *, size_t, unsigned long long *, int,
+                           unsigned long long *);
 
 struct KernelSel {
     NewviewFn fn = nullptr;
     int threads = 0;                 // launch block size
     size_t smem = 0;                 // dynamic shared memory
     int sites_per_block_iter = 0;    // sites one block consumes per loop iteration
+    bool dynamic = false;            // needs a zeroed work-counter pair
 };
 
 // math: 0 strict, 1 fma.  Return fn == nullptr for combinations that are not compiled in.
@@ -32,6 +35,8 @@ KernelSel select_ldg_strict(int u, int kind, int b, int threads);
 KernelSel select_ldg_fma(int u, int kind, int b, int threads);
 KernelSel select_tma_strict(int u, int d, int b, int threads);
 KernelSel select_tma_fma(int u, int d, int b, int threads);
+KernelSel select_tma_dyn_strict(int u, int d, int b, int threads);
+KernelSel select_tma_dyn_fma(int u, int d, int b, int threads);
 
 // root log-likelihood kernel (plf_evaluate.cu); returns a plf_status
 int launch_evaluate(const float *x1, const float *x2, const int *cnt1, const int *cnt2, const int *wgt,

@@ -14,7 +14,12 @@ KernelSel sel_one()
     KernelSel k;
     k.smem = tma_smem_bytes<U, WARPS, DEPTH>();
     if (k.smem * MINB > 227u * 1024u) return KernelSel{};
+#ifdef PLF_SEL_DYNAMIC
+    k.fn = plf_newview_tma_dyn<M, U, WARPS, DEPTH, MINB>;
+    k.dynamic = true;
+#else
     k.fn = plf_newview_tma<M, U, WARPS, DEPTH, MINB>;
+#endif
     k.threads = (WARPS + 1) * 32;
     k.sites_per_block_iter = WARPS * 8 * U;
     return k;

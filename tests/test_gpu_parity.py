@@ -22,7 +22,8 @@ pytestmark = pytest.mark.gpu
 REL_TOL_FMA = 1e-5
 # kernel variants exercised everywhere: (variant id, compute threads per block)
 VARIANTS = [(0, 0), (2, 256), (1, 128), (4, 256), (12, 256), (3002, 256), (2422, 256), (1421, 128),
-            (1324, 256), (1622, 512), (1322, 512), (3222, 128), (1221, 512)]
+            (1324, 256), (1622, 512), (1322, 512), (3222, 128), (1221, 512),
+            (1332, 512), (3332, 128), (1334, 256), (1431, 128)]          # K=3: dynamic stage scheduling
 RAGGED = [1, 7, 8, 9, 31, 33, 127, 128, 129, 1000, 4097, 65536 + 5]
 
 
@@ -181,7 +182,8 @@ def test_per_category_ev(pkg, gpu, coracle):
         assert np.array_equal(bits(x3), bits(o3)) and np.array_equal(sc, osc) and inc == oinc
 
 
-@pytest.mark.parametrize("variant,threads", [(0, 0), (2, 256), (4, 256), (1322, 512), (1421, 128), (2422, 256)])
+@pytest.mark.parametrize("variant,threads", [(0, 0), (2, 256), (4, 256), (1322, 512), (1421, 128), (2422, 256),
+                                             (1332, 512), (3332, 128)])
 def test_no_out_of_bounds_writes(pkg, gpu, coracle, variant, threads):
     """Guard bands around x3 and the scaler bytes stay untouched for ragged site counts, and input
     buffers that end exactly at the last site are enough (compute-sanitizer is closed on this pool)."""

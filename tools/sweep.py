@@ -77,6 +77,13 @@ def main():
                          (1324, 512), (2322, 128), (3322, 128), (3222, 128), (1324, 256), (2322, 256), (2222, 256),
                          (1422, 256), (1424, 128), (3002, 256), (2, 256)):
                 combos.append((v, t, 0, math))
+    elif args.grid == "dyn":        # static vs dynamic stage scheduling, same shapes
+        combos = []
+        for math in (0, 1):
+            for d, u, t, b in ((3, 2, 512, 1), (4, 2, 512, 1), (2, 2, 512, 1), (3, 4, 256, 1), (3, 2, 128, 2), (3, 2, 128, 3),
+                               (3, 2, 256, 2), (4, 1, 512, 1), (6, 1, 512, 1)):
+                for kind in (2, 3):
+                    combos.append((1000 * b + 100 * d + 10 * kind + u, t, 0, math))
     elif args.grid == "tma":
         combos = []
         for math in (0, 1):
