@@ -89,9 +89,10 @@ int fail(plf_ctx *ctx, int code, const char *fmt, ...)
     } while (0)
 
 // ---- kernel variant registry: see plf_registry.h for the variant encoding ----------------------
-// Default: tma ring, 16 consumer warps, U=2 (256-site / 32 KB stages), 3 stages, 1 CTA per SM --
-// the fastest strict configuration in the sweep on B200 (profiles/r01_sweep.md).
-constexpr int kDefaultVariant = 1322;
+// Default: tma ring with dynamic stage scheduling, 16 consumer warps, U=2 (256-site / 32 KB stages),
+// 4 stages, 1 CTA per SM -- the fastest strict configuration at 8 Mi and 64 Mi sites per launch on
+// B200 (profiles/r01_sweep.md, "static vs dynamic").
+constexpr int kDefaultVariant = 1432;
 constexpr int kDefaultThreads = 512;
 
 using plf::KernelSel;
