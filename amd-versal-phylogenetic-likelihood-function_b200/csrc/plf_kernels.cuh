@@ -689,19 +689,20 @@ struct BatchOp {
 template <int U, int WARPS, int DEPTH>
 constexpr size_t batch_smem_bytes()
 {
-    return tma_smem_bytes<U, WARPS, DEPTH>() + (size_t)DEPTH * (WARPS * 8 * U) * (sizeof(int) * 2 + 2) + 256;
+    return tma_smem_bytes<U, WARPS, DEPTH>() + (size_t)DEPTH * (WARPS * 8 * U) * (sizeof(int) * 2 + 2) + 256;   // tma_smem_bytes already holds the barriers + stage indices
 }
 
 template <class M, int U, int WARPS, int DEPTH, int MINB>
 __global__ void __launch_bounds__((WARPS + 1) * 32, MINB)
 plf_newview_batch(const BatchOp *__restrict__ ops, int n_ops, size_t n,
                   const int *__restrict__ wgt, unsigned long long *__restrict__ scaler_sum,
-                  unsigned chunk)
+                  unsigned chunk, unsigned long long *work)
 {
     constexpr int THREADS = (WARPS + 1) * 32;
     constexpr int TILE = 8 * U;
     constexpr int STAGE = WARPS * TILE;
     constexpr int STAGE_F4 = STAGE * 4;
+    constexpr uint32_t kDone = 0xffffffffu;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4 *s1 = reinterpret_cast<float4 *>(smem_raw);                 // [DEPTH][STAGE_F4]
@@ -713,11 +714,15 @@ plf_newview_batch(const BatchOp *__restrict__ ops, int n_ops, size_t n,
     float4 *tv = reinterpret_cast<float4 *>(k2s + (size_t)DEPTH * STAGE);                 // [16] tip vector table
     uint64_t *full = reinterpret_cast<uint64_t *>(tv + 16);
     uint64_t *empty = full + DEPTH;
+    volatile uint32_t *stage_of = reinterpret_cast<volatile uint32_t *>(empty + DEPTH);   // [DEPTH] global stage index
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     // The work list: stage g of the launch is stage (g % spo) of op (g / spo).  It is dealt out in
-    // chunks of `chunk` consecutive stages, chunk q to CTA q % gridDim.x.
+    // chunks of `chunk` consecutive stages.  With a work counter the producers take chunks dynamically
+    // (as plf_newview_tma_dyn takes stages; the fetch of the next chunk is issued a chunk ahead);
+    // without one chunk q goes to CTA q % gridDim.x.  Either way the producer publishes the global
+    // stage index of every slot to its consumers and ends with a sentinel.
     const uint32_t spo = (uint32_t)((n + STAGE - 1) / STAGE);          // stages per op
     const uint32_t full_stages = (uint32_t)(n / STAGE);                // stages [0, full_stages) are complete
     const uint32_t total = spo * (uint32_t)n_ops;
@@ -744,8 +749,10 @@ plf_newview_batch(const BatchOp *__restrict__ ops, int n_ops, size_t n,
             const float4 *x1 = nullptr, *x2 = nullptr;
             const int *k1 = nullptr, *k2 = nullptr;
             const unsigned char *tp1 = nullptr, *tp2 = nullptr;
-            for (uint32_t q = blockIdx.x; q < n_chunks; q += gridDim.x) {
-                const uint32_t g0 = q * chunk;
+            unsigned long long q = work ? atomicAdd(work, 1ull) : (unsigned long long)blockIdx.x;
+            while (q < n_chunks) {
+                const unsigned long long q_next = work ? atomicAdd(work, 1ull) : q + gridDim.x;   // used a chunk from now
+                const uint32_t g0 = (uint32_t)q * chunk;
                 const uint32_t g1 = g0 + chunk < total ? g0 + chunk : total;
                 uint32_t op = g0 / spo, st = g0 - op * spo;
                 for (uint32_t g = g0; g < g1; ++g) {
@@ -759,6 +766,7 @@ plf_newview_batch(const BatchOp *__restrict__ ops, int n_ops, size_t n,
                         cur_op = op;
                     }
                     mbar_wait(&empty[slot], phase ^ 1u);
+                    stage_of[slot] = g;
                     const size_t s0 = (size_t)st * STAGE;
                     const uint32_t sites = st < full_stages ? (uint32_t)STAGE : (uint32_t)(n - s0);
                     const uint32_t bytes = sites * 64u;
@@ -781,7 +789,11 @@ plf_newview_batch(const BatchOp *__restrict__ ops, int n_ops, size_t n,
                         ++op;
                     }
                 }
+                q = q_next;
             }
+            mbar_wait(&empty[slot], phase ^ 1u);          // out of work: tell the consumers and stop
+            stage_of[slot] = kDone;
+            mbar_arrive(&full[slot]);
         }
     } else {
         // ===== consumers =====
@@ -790,82 +802,89 @@ plf_newview_batch(const BatchOp *__restrict__ ops, int n_ops, size_t n,
         const uint32_t tile_off = warp * (TILE * 4) + lane;
         CatConst c;
         BatchOp o;
-        uint32_t cur_op = 0xffffffffu;
+        uint32_t cur_op = 0xffffffffu, op_base = 0;
         uint32_t slot = 0, phase = 0;
-        for (uint32_t q = blockIdx.x; q < n_chunks; q += gridDim.x) {
-            const uint32_t g0 = q * chunk;
-            const uint32_t g1 = g0 + chunk < total ? g0 + chunk : total;
-            uint32_t op = g0 / spo, st = g0 - op * spo;
-            for (uint32_t g = g0; g < g1; ++g) {
-                if (op != cur_op) {                      // new op: its pointers and 48 constants
-                    o = ops[op];
-                    load_cat_const(c, o.ev, o.pl, o.pr, cat, 0);
-                    cur_op = op;
-                }
-                const size_t s0 = (size_t)st * STAGE + (size_t)warp * TILE;   // first site of this warp's tile
-                const size_t s_lane = s0 + lane;                              // the site whose count this lane owns
-                const bool complete = st < full_stages;
-                const bool lane_live = lane < TILE && (complete || s_lane < n);
-                const float4 *t1 = s1 + slot * STAGE_F4 + tile_off;
-                const float4 *t2 = s2 + slot * STAGE_F4 + tile_off;
-                mbar_wait(&full[slot], phase);
-                float4 a[U], b[U], r[U];
-                unsigned ballots[U];
-                const uint32_t code_off = slot * STAGE + warp * TILE + site_in_row;
+        for (;;) {
+            const float4 *t1 = s1 + slot * STAGE_F4 + tile_off;
+            const float4 *t2 = s2 + slot * STAGE_F4 + tile_off;
+            mbar_wait(&full[slot], phase);
+            const uint32_t g = stage_of[slot];
+            if (g == kDone) break;
+            uint32_t st = g - op_base;
+            if (cur_op == 0xffffffffu || st >= spo) {    // first stage, or a stage of another op: its pointers and 48 constants
+                cur_op = g / spo;
+                op_base = cur_op * spo;
+                st = g - op_base;
+                o = ops[cur_op];
+                load_cat_const(c, o.ev, o.pl, o.pr, cat, 0);
+            }
+            const size_t s0 = (size_t)st * STAGE + (size_t)warp * TILE;   // first site of this warp's tile
+            const size_t s_lane = s0 + lane;                              // the site whose count this lane owns
+            const bool complete = st < full_stages;
+            const bool lane_live = lane < TILE && (complete || s_lane < n);
+            float4 a[U], b[U], r[U];
+            unsigned ballots[U];
+            const uint32_t code_off = slot * STAGE + warp * TILE + site_in_row;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                a[u] = o.tip1 ? tv[k1s[code_off + 8 * u] & 15] : t1[32 * u];
+                b[u] = o.tip2 ? tv[k2s[code_off + 8 * u] & 15] : t2[32 * u];
+            }
+            int cnt = 0;
+            if (lane_live) {
+                if (o.cnt1) cnt = c1[slot * STAGE + warp * TILE + lane];
+                if (o.cnt2) cnt += c2[slot * STAGE + warp * TILE + lane];
+            }
+            unsigned dep = (unsigned)cnt ^ g;
+#pragma unroll
+            for (int u = 0; u < U; ++u) dep ^= __float_as_uint(a[u].x) ^ __float_as_uint(b[u].w);
+            mbar_release_slot(&empty[slot], lane, dep);
+            if (++slot == DEPTH) {
+                slot = 0;
+                phase ^= 1u;
+            }
+            float4 *out = o.x3 + s0 * 4 + lane;
+            if (complete) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    a[u] = o.tip1 ? tv[k1s[code_off + 8 * u] & 15] : t1[32 * u];
-                    b[u] = o.tip2 ? tv[k2s[code_off + 8 * u] & 15] : t2[32 * u];
+                    bool small = category_newview<M>(c, a[u], b[u], r[u]);
+                    ballots[u] = __ballot_sync(0xffffffffu, small);
+                    if (nibble_all(ballots[u], site_in_row)) rescale(r[u]);
+                    st_stream(out + 32 * u, r[u]);
                 }
-                int cnt = 0;
-                if (lane_live) {
-                    if (o.cnt1) cnt = c1[slot * STAGE + warp * TILE + lane];
-                    if (o.cnt2) cnt += c2[slot * STAGE + warp * TILE + lane];
-                }
-                unsigned dep = (unsigned)cnt;
+            } else {
 #pragma unroll
-                for (int u = 0; u < U; ++u) dep ^= __float_as_uint(a[u].x) ^ __float_as_uint(b[u].w);
-                mbar_release_slot(&empty[slot], lane, dep);
-                if (++slot == DEPTH) {
-                    slot = 0;
-                    phase ^= 1u;
+                for (int u = 0; u < U; ++u) {
+                    const bool live = s0 + 8 * u + site_in_row < n;
+                    bool small = category_newview<M>(c, a[u], b[u], r[u]);
+                    ballots[u] = __ballot_sync(0xffffffffu, small && live);
+                    if (nibble_all(ballots[u], site_in_row)) rescale(r[u]);
+                    if (live) st_stream(out + 32 * u, r[u]);
                 }
-                float4 *out = o.x3 + s0 * 4 + lane;
-                if (complete) {
+            }
+            if (lane_live) {
+                unsigned bal = ballots[0];
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        bool small = category_newview<M>(c, a[u], b[u], r[u]);
-                        ballots[u] = __ballot_sync(0xffffffffu, small);
-                        if (nibble_all(ballots[u], site_in_row)) rescale(r[u]);
-                        st_stream(out + 32 * u, r[u]);
-                    }
-                } else {
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const bool live = s0 + 8 * u + site_in_row < n;
-                        bool small = category_newview<M>(c, a[u], b[u], r[u]);
-                        ballots[u] = __ballot_sync(0xffffffffu, small && live);
-                        if (nibble_all(ballots[u], site_in_row)) rescale(r[u]);
-                        if (live) st_stream(out + 32 * u, r[u]);
-                    }
-                }
-                if (lane_live) {
-                    unsigned bal = ballots[0];
-#pragma unroll
-                    for (int u = 1; u < U; ++u) bal = (lane >> 3) == u ? ballots[u] : bal;
-                    const bool scaled = nibble_all(bal, lane & 7);
-                    if (o.scaler) o.scaler[s_lane] = scaled ? 1 : 0;
-                    if (o.cnt3) o.cnt3[s_lane] = cnt + (scaled ? 1 : 0);
-                    if (scaled) my_sum += wgt ? (unsigned long long)(long long)wgt[s_lane] : 1ull;
-                }
-                if (++st == spo) {
-                    st = 0;
-                    ++op;
-                }
+                for (int u = 1; u < U; ++u) bal = (lane >> 3) == u ? ballots[u] : bal;
+                const bool scaled = nibble_all(bal, lane & 7);
+                if (o.scaler) o.scaler[s_lane] = scaled ? 1 : 0;
+                if (o.cnt3) o.cnt3[s_lane] = cnt + (scaled ? 1 : 0);
+                if (scaled) my_sum += wgt ? (unsigned long long)(long long)wgt[s_lane] : 1ull;
             }
         }
     }
     if (scaler_sum) block_add_u64<THREADS>(my_sum, scaler_sum);
+    if (work) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned long long finished = atomicAdd(work + 1, 1ull);
+            if (finished == gridDim.x - 1) {      // last CTA out: leave the pair clean for the next level
+                work[0] = 0ull;
+                work[1] = 0ull;
+                __threadfence();
+            }
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

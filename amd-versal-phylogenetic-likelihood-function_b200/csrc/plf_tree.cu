@@ -45,6 +45,8 @@ struct plf_tree {
     plf::BatchOp *d_ops = nullptr;             // all ops, level after level
     std::vector<size_t> level_op_offset;
     unsigned long long *d_sum = nullptr, *h_sum = nullptr;
+    unsigned long long *d_work = nullptr;      // work-counter pair of the dynamically scheduled level launches
+    bool dynamic = true;
     double *d_lnl = nullptr;                   // [0] lnL accumulator, [1..4] diag (as 16 floats)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -79,7 +81,8 @@ int tfail(plf_tree *t, int code, const char *fmt, ...)
                          "%s failed: %s", #expr, cudaGetErrorString(e__));                        \
     } while (0)
 
-using BatchFn = void (*)(const plf::BatchOp *, int, size_t, const int *, unsigned long long *, unsigned);
+using BatchFn = void (*)(const plf::BatchOp *, int, size_t, const int *, unsigned long long *, unsigned,
+                         unsigned long long *);
 
 struct BatchSel {
     BatchFn fn;
@@ -161,7 +164,8 @@ int launch_level(plf_tree *t, const BatchSel &k, size_t level, cudaStream_t s)
     cfg.numAttrs = (use_pdl && level > 0) ? 1 : 0;      // level 0 follows a memset node: plain dependency
     const plf::BatchOp *ops = t->d_ops + t->level_op_offset[level];
     const int *wgt = t->use_wgt ? t->d_wgt : nullptr;
-    TREE_CUDA(t, cudaLaunchKernelEx(&cfg, k.fn, ops, n_ops, t->n_sites, wgt, t->d_sum, (unsigned)chunk));
+    unsigned long long *work = t->dynamic ? t->d_work : nullptr;
+    TREE_CUDA(t, cudaLaunchKernelEx(&cfg, k.fn, ops, n_ops, t->n_sites, wgt, t->d_sum, (unsigned)chunk, work));
     TREE_CUDA(t, cudaGetLastError());
     return PLF_OK;
 }
@@ -258,6 +262,7 @@ int plf_tree_create_ex(plf_tree **out, int device, unsigned n_tips, const int *l
     t->n_inner = n_inner;
     t->n_sites = n_sites;
     t->tip_format = tip_format;
+    if (const char *e = getenv("PLF_TREE_STATIC")) t->dynamic = !(e[0] == '1');
     t->left.assign(left, left + n_inner);
     t->right.assign(right, right + n_inner);
     cudaDeviceGetAttribute(&t->num_sms, cudaDevAttrMultiProcessorCount, device);
@@ -304,6 +309,8 @@ int plf_tree_create_ex(plf_tree **out, int device, unsigned n_tips, const int *l
     if (e == cudaSuccess) e = cudaMalloc(&t->d_mats, (16 + 128 * (size_t)n_inner + 64) * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&t->d_ops, sizeof(plf::BatchOp) * n_inner);
     if (e == cudaSuccess) e = cudaMalloc(&t->d_sum, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&t->d_work, 2 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(t->d_work, 0, 2 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMallocHost(&t->h_sum, sizeof(unsigned long long));
     if (e != cudaSuccess) {
         cudaGetLastError();
@@ -363,6 +370,7 @@ int plf_tree_destroy(plf_tree *t)
     cudaFree(t->d_ops);
     cudaFree(t->d_sum);
     cudaFree(t->d_lnl);
+    cudaFree(t->d_work);
     if (t->h_sum) cudaFreeHost(t->h_sum);
     if (t->ev0) cudaEventDestroy(t->ev0);
     if (t->ev1) cudaEventDestroy(t->ev1);
