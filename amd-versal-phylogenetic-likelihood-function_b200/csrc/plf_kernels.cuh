@@ -40,31 +40,77 @@ constexpr float kTwoToThe32 = 0x1p+32f;      // plf.cpp:5
 // (dot4_final), which canonicalises any -0 to +0: outputs stay bit-identical to plf() at 92
 // instead of 100 fp32 operations per (site, category).
 // ---------------------------------------------------------------------------------------------
+// Packed fp32x2 arithmetic (sm_100+: SASS FMUL2 / FFMA2).  Each half is an independent IEEE-754
+// round-to-nearest fp32 operation, so results are bit-identical to two scalar instructions, at half
+// the issue slots.  The register pairs are the natural ones: (x0,x1),(x2,x3) of a 128-bit load and
+// adjacent matrix constants, so no moves are needed.
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b)
+{
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
 struct MathStrict {
-    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    // the four products of a dot product: two FMUL2, each product rounded on its own
+    static __device__ __forceinline__ void prod4(float a0, float a1, float a2, float a3, float b0, float b1,
+                                                 float b2, float b3, float &q0, float &q1, float &q2, float &q3)
+    {
+        f2_unpack(f2_mul(f2_pack(a0, a1), f2_pack(b0, b1)), q0, q1);
+        f2_unpack(f2_mul(f2_pack(a2, a3), f2_pack(b2, b3)), q2, q3);
+    }
+    // p[k] = a[k] * b[k] for two k at once
+    static __device__ __forceinline__ void mul_pair(float a0, float a1, float b0, float b1, float &p0, float &p1)
+    {
+        f2_unpack(f2_mul(f2_pack(a0, a1), f2_pack(b0, b1)), p0, p1);
+    }
     // ((a0*b0 + a1*b1) + a2*b2) + a3*b3
     static __device__ __forceinline__ float dot4_inner(float a0, float a1, float a2, float a3,
                                                        float b0, float b1, float b2, float b3)
     {
-        float acc = __fadd_rn(__fmul_rn(a0, b0), __fmul_rn(a1, b1));
-        acc = __fadd_rn(acc, __fmul_rn(a2, b2));
-        acc = __fadd_rn(acc, __fmul_rn(a3, b3));
+        float q0, q1, q2, q3;
+        prod4(a0, a1, a2, a3, b0, b1, b2, b3, q0, q1, q2, q3);
+        float acc = __fadd_rn(q0, q1);
+        acc = __fadd_rn(acc, q2);
+        acc = __fadd_rn(acc, q3);
         return acc;
     }
     // ((((+0 + a0*b0) + a1*b1) + a2*b2) + a3*b3)
     static __device__ __forceinline__ float dot4_final(float a0, float a1, float a2, float a3,
                                                        float b0, float b1, float b2, float b3)
     {
-        float acc = __fadd_rn(0.0f, __fmul_rn(a0, b0));
-        acc = __fadd_rn(acc, __fmul_rn(a1, b1));
-        acc = __fadd_rn(acc, __fmul_rn(a2, b2));
-        acc = __fadd_rn(acc, __fmul_rn(a3, b3));
+        float q0, q1, q2, q3;
+        prod4(a0, a1, a2, a3, b0, b1, b2, b3, q0, q1, q2, q3);
+        float acc = __fadd_rn(0.0f, q0);
+        acc = __fadd_rn(acc, q1);
+        acc = __fadd_rn(acc, q2);
+        acc = __fadd_rn(acc, q3);
         return acc;
     }
 };
 
 struct MathFma {
-    static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
+    static __device__ __forceinline__ void mul_pair(float a0, float a1, float b0, float b1, float &p0, float &p1)
+    {
+        p0 = a0 * b0;
+        p1 = a1 * b1;
+    }
     static __device__ __forceinline__ float dot4_inner(float a0, float a1, float a2, float a3,
                                                        float b0, float b1, float b2, float b3)
     {
@@ -110,7 +156,8 @@ __device__ __forceinline__ void st_plain(float4 *p, const float4 &v) { *p = v; }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-// The 48 per-category constants: P_left[j], P_right[j] as [k][l], EV (or EV4[j]) as [k][l].
+// The 48 per-category constants: P_left[j], P_right[j] as [k][l]; EV (or EV4[j]) TRANSPOSED as [l][k], so that
+// the four factors of every dot product sit in adjacent registers (pairs for the packed multiplies).
 struct CatConst {
     float L[16];
     float R[16];
@@ -130,7 +177,7 @@ __device__ __forceinline__ void load_cat_const(CatConst &c, const float *__restr
         float4 a = __ldg(l4 + k), b = __ldg(r4 + k), e = __ldg(e4 + k);
         c.L[4 * k + 0] = a.x; c.L[4 * k + 1] = a.y; c.L[4 * k + 2] = a.z; c.L[4 * k + 3] = a.w;
         c.R[4 * k + 0] = b.x; c.R[4 * k + 1] = b.y; c.R[4 * k + 2] = b.z; c.R[4 * k + 3] = b.w;
-        c.E[4 * k + 0] = e.x; c.E[4 * k + 1] = e.y; c.E[4 * k + 2] = e.z; c.E[4 * k + 3] = e.w;
+        c.E[k] = e.x; c.E[4 + k] = e.y; c.E[8 + k] = e.z; c.E[12 + k] = e.w;      // transposed: E[4*l + k] = EV[k][l]
     }
 }
 
@@ -140,17 +187,18 @@ template <class M>
 __device__ __forceinline__ bool category_newview(const CatConst &c, const float4 &u, const float4 &v,
                                                  float4 &o)
 {
-    float p[4];
+    float a[4], b[4], p[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        float a = M::dot4_inner(u.x, u.y, u.z, u.w, c.L[4 * k], c.L[4 * k + 1], c.L[4 * k + 2], c.L[4 * k + 3]);
-        float b = M::dot4_inner(v.x, v.y, v.z, v.w, c.R[4 * k], c.R[4 * k + 1], c.R[4 * k + 2], c.R[4 * k + 3]);
-        p[k] = M::mul(a, b);
+        a[k] = M::dot4_inner(u.x, u.y, u.z, u.w, c.L[4 * k], c.L[4 * k + 1], c.L[4 * k + 2], c.L[4 * k + 3]);
+        b[k] = M::dot4_inner(v.x, v.y, v.z, v.w, c.R[4 * k], c.R[4 * k + 1], c.R[4 * k + 2], c.R[4 * k + 3]);
     }
-    o.x = M::dot4_final(p[0], p[1], p[2], p[3], c.E[0], c.E[4], c.E[8], c.E[12]);
-    o.y = M::dot4_final(p[0], p[1], p[2], p[3], c.E[1], c.E[5], c.E[9], c.E[13]);
-    o.z = M::dot4_final(p[0], p[1], p[2], p[3], c.E[2], c.E[6], c.E[10], c.E[14]);
-    o.w = M::dot4_final(p[0], p[1], p[2], p[3], c.E[3], c.E[7], c.E[11], c.E[15]);
+    M::mul_pair(a[0], a[1], b[0], b[1], p[0], p[1]);
+    M::mul_pair(a[2], a[3], b[2], b[3], p[2], p[3]);
+    o.x = M::dot4_final(p[0], p[1], p[2], p[3], c.E[0], c.E[1], c.E[2], c.E[3]);
+    o.y = M::dot4_final(p[0], p[1], p[2], p[3], c.E[4], c.E[5], c.E[6], c.E[7]);
+    o.z = M::dot4_final(p[0], p[1], p[2], p[3], c.E[8], c.E[9], c.E[10], c.E[11]);
+    o.w = M::dot4_final(p[0], p[1], p[2], p[3], c.E[12], c.E[13], c.E[14], c.E[15]);
     // NaN compares false, exactly like ABS(x) < minlikelihood on the CPU.
     return (fabsf(o.x) < kMinLikelihood) & (fabsf(o.y) < kMinLikelihood) &
            (fabsf(o.z) < kMinLikelihood) & (fabsf(o.w) < kMinLikelihood);
