@@ -105,6 +105,35 @@ struct MathStrict {
     }
 };
 
+// The same arithmetic with scalar FMUL/FADD only (92 instructions per site-category).  Used by the
+// batch/tree kernel, whose 96-register budget (17 warps are allocated as 20) has no room for the
+// pair constraints of the packed version: with FMUL2 it spills 164 bytes and a traversal is 12 %
+// slower (profiles/r01_tree.md).
+struct MathStrictScalar {
+    static __device__ __forceinline__ void mul_pair(float a0, float a1, float b0, float b1, float &p0, float &p1)
+    {
+        p0 = __fmul_rn(a0, b0);
+        p1 = __fmul_rn(a1, b1);
+    }
+    static __device__ __forceinline__ float dot4_inner(float a0, float a1, float a2, float a3,
+                                                       float b0, float b1, float b2, float b3)
+    {
+        float acc = __fadd_rn(__fmul_rn(a0, b0), __fmul_rn(a1, b1));
+        acc = __fadd_rn(acc, __fmul_rn(a2, b2));
+        acc = __fadd_rn(acc, __fmul_rn(a3, b3));
+        return acc;
+    }
+    static __device__ __forceinline__ float dot4_final(float a0, float a1, float a2, float a3,
+                                                       float b0, float b1, float b2, float b3)
+    {
+        float acc = __fadd_rn(0.0f, __fmul_rn(a0, b0));
+        acc = __fadd_rn(acc, __fmul_rn(a1, b1));
+        acc = __fadd_rn(acc, __fmul_rn(a2, b2));
+        acc = __fadd_rn(acc, __fmul_rn(a3, b3));
+        return acc;
+    }
+};
+
 struct MathFma {
     static __device__ __forceinline__ void mul_pair(float a0, float a1, float b0, float b1, float &p0, float &p1)
     {

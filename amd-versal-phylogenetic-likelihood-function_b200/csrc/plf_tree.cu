@@ -103,7 +103,7 @@ BatchSel batch_sel(int u)
 
 BatchSel pick_batch(int math, int u)
 {
-    return math == PLF_MATH_FMA ? batch_sel<plf::MathFma>(u) : batch_sel<plf::MathStrict>(u);
+    return math == PLF_MATH_FMA ? batch_sel<plf::MathFma>(u) : batch_sel<plf::MathStrictScalar>(u);
 }
 
 // tip code vectors are padded to a multiple of 16 bytes (bulk-copy granularity)
