@@ -57,6 +57,10 @@ KernelSel sel_u(int d, int b, int threads)
         default: return KernelSel{};
         }
     case 512: return b == 1 ? sel_depth<U, 16, 1>(d) : KernelSel{};
+    // 15 / 11 consumer warps + the producer warp = 16 / 12 warps: register allocation is per 4 warps, so
+    // 17 warps are charged as 20 (96 registers per thread) while 16 get 128 and 12 get 168
+    case 480: return b == 1 ? sel_depth<U, 15, 1>(d) : KernelSel{};
+    case 352: return b == 1 ? sel_depth<U, 11, 1>(d) : KernelSel{};
     default: return KernelSel{};
     }
 }

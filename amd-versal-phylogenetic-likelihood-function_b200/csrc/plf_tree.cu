@@ -91,19 +91,24 @@ struct BatchSel {
     int stage;
 };
 
-template <class M>
+template <class M, class M15>
 BatchSel batch_sel(int u)
 {
-    // u = 1: 128-site stages x 4;  u = 2: 256-site stages x 3 (default).  A deeper ring (x 6) was
-    // measured and is slower, for dense and for compressed-tip trees alike (profiles/r01_tree.md).
+    // u = 1: 16 consumer warps, 128-site stages x 4;  u = 2: 16 consumer warps, 256-site stages x 3;
+    // u = 3 (default for all but tiny levels): 15 consumer warps, 240-site stages x 3.  Registers are
+    // allocated per 4 warps: 16 + 1 warps are charged as 20 (96 registers per thread, the batch kernel
+    // spills), 15 + 1 get 128 -- room for the packed strict arithmetic; 2-3 % faster traversals.
     if (u == 1)
         return {plf::plf_newview_batch<M, 1, 16, 4, 1>, 17 * 32, plf::batch_smem_bytes<1, 16, 4>(), 128};
-    return {plf::plf_newview_batch<M, 2, 16, 3, 1>, 17 * 32, plf::batch_smem_bytes<2, 16, 3>(), 256};
+    if (u == 2)
+        return {plf::plf_newview_batch<M, 2, 16, 3, 1>, 17 * 32, plf::batch_smem_bytes<2, 16, 3>(), 256};
+    return {plf::plf_newview_batch<M15, 2, 15, 3, 1>, 16 * 32, plf::batch_smem_bytes<2, 15, 3>(), 240};
 }
 
 BatchSel pick_batch(int math, int u)
 {
-    return math == PLF_MATH_FMA ? batch_sel<plf::MathFma>(u) : batch_sel<plf::MathStrictScalar>(u);
+    return math == PLF_MATH_FMA ? batch_sel<plf::MathFma, plf::MathFma>(u)
+                                : batch_sel<plf::MathStrictScalar, plf::MathStrict>(u);
 }
 
 // tip code vectors are padded to a multiple of 16 bytes (bulk-copy granularity)
@@ -175,9 +180,9 @@ int build_graph(plf_tree *t)
 {
     int u = t->tune_u;
     if (u == 0) {
-        // 256-site stages unless even the widest level would leave most SMs with < 4 stages
+        // 240-site stages unless even the widest level would leave most SMs with < 4 stages
         const size_t widest = t->levels.empty() ? 1 : t->levels[0].size();
-        u = ((t->n_sites + 255) / 256) * widest >= (size_t)t->num_sms * 4 ? 2 : 1;
+        u = ((t->n_sites + 239) / 240) * widest >= (size_t)t->num_sms * 4 ? 3 : 1;
     }
     const BatchSel k = pick_batch(t->math, u);
     TREE_CUDA(t, cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.smem));
@@ -390,7 +395,7 @@ int plf_tree_set_math(plf_tree *t, int math_mode)
 int plf_tree_set_tuning(plf_tree *t, int u, int chunk)
 {
     if (!t) return tfail(nullptr, PLF_ERR_INVALID, "NULL tree");
-    if (u < 0 || u > 2) return tfail(t, PLF_ERR_INVALID, "tuning u must be 0, 1 or 2");
+    if (u < 0 || u > 3) return tfail(t, PLF_ERR_INVALID, "tuning u must be 0..3");
     if (chunk < 0) return tfail(t, PLF_ERR_INVALID, "chunk must be >= 0");
     t->tune_u = u;
     t->tune_chunk = chunk;
