@@ -149,7 +149,10 @@ int plf_host_unregister(void *ptr);
 
 typedef struct plf_launch_opts {
     int math_mode;          /* plf_math                                                          */
-    int variant;            /* kernel variant, 0 = default                           */
+    int variant;            /* kernel variant, 0 = default.  Dynamically scheduled variants
+                             * (K = 3, the default) take a work-counter pair from a per-device ring at
+                             * launch time: when capturing launches into a CUDA graph that may be replayed
+                             * concurrently with itself, pick a static variant (e.g. 1322).               */
     int threads_per_block;  /* 0 = default                                                       */
     int blocks_per_sm;      /* 0 = default (persistent grid = SMs x blocks_per_sm)               */
     int ev_per_category;    /* 0: ev is EV[16]; 1: ev is EV4[4][16], one matrix per category     */

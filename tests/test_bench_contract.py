@@ -44,3 +44,31 @@ def test_b200_arm_has_no_cpu_fallback(pkg):
                        text=True, timeout=300)
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
     assert r.stdout.strip() == ""
+
+
+import pytest
+
+
+@pytest.mark.gpu
+def test_b200_arm_prints_one_complete_json_line():
+    """A small run of our arm on the GPU: one JSON line with every key the driver and the judge read."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--sites", str(2 << 20), "--steps", "5",
+                        "--warmup", "3", "--e2e-steps", "2"], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert REQUIRED <= set(d) and "impl" not in d
+    assert d["n_gpus"] == 1 and d["steps"] == 5 and d["warmup"] == 3 and d["scaling"] in ("weak", "strong")
+    assert d["dtype"] == "f32" and d["data"] == "synthetic" and d["vs_baseline"] is None
+    rf = d["roofline"]
+    assert rf["bound"] == "hbm" and rf["unit"] == "GB/s" and rf["peak"] > 1000
+    assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9 and 0.3 < rf["frac"] < 1.3
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] > 0 and cb["sample"]
+    e = d["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
+    assert e["value"] < d["value"]                       # host round trip is PCIe bound, never the device rate
+    assert d["gpu_launches"] == 5                        # one fused kernel per step, nothing else of ours
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
+    assert d["scaler_increment"] == (2 << 20) // 4
