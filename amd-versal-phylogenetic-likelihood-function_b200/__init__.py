@@ -82,6 +82,7 @@ PROTOTYPES = {
     "plf_elapsed_ms": (_i, [_vp, _u, _i, _i, ctypes.POINTER(ctypes.c_float)]),
     "plf_instance_device_ptrs": (_i, [_vp, _u] + [ctypes.POINTER(_vp)] * 4),
     "plf_instance_stream": (_i, [_vp, _u, ctypes.POINTER(_vp)]),
+    "plf_newview_stream": (_i, [_vp] * 9 + [_sz, _sz, ctypes.POINTER(ctypes.c_longlong)]),
     "plf_host_alloc": (_i, [ctypes.POINTER(_vp), _sz]),
     "plf_host_free": (_i, [_vp]),
     "plf_host_register": (_i, [_vp, _sz]),
@@ -365,6 +366,18 @@ class Context:
         s = _vp()
         self._ck(self.lib.plf_instance_stream(self._ctx, inst, ctypes.byref(s)))
         return s.value or 0
+
+    def newview_stream(self, ev, p_left, p_right, x1, x2, x3, scaler=None, wgt=None, n_sites: int | None = None,
+                       chunk_sites: int = 0) -> int:
+        """Streamed round trip over host arrays (numpy arrays or raw pointers); returns the scaler increment."""
+        ev = np.ascontiguousarray(ev, np.float32)
+        pl = np.ascontiguousarray(p_left, np.float32)
+        pr = np.ascontiguousarray(p_right, np.float32)
+        n = n_sites if n_sites is not None else x1.size // 16
+        inc = ctypes.c_longlong(0)
+        self._ck(self.lib.plf_newview_stream(self._ctx, _ptr(ev), _ptr(pl), _ptr(pr), _ptr(x1), _ptr(x2), _ptr(x3),
+                                             _ptr(scaler), _ptr(wgt), n, chunk_sites, ctypes.byref(inc)))
+        return inc.value
 
     # -- the reference host's per-call sequence (host_mem.cpp:287-325) for numpy inputs --------
     def newview(self, ev, p_left, p_right, x1, x2, wgt=None, instances: int | None = None,

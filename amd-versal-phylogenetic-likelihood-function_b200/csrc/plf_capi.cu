@@ -58,6 +58,17 @@ struct plf_ctx {
     int variant = 0, threads = 0, blocks_per_sm = 0;
     int num_sms = 0;
     float *d_gen = nullptr;                 // gen pattern: x1[16] x2[16] ev4[64] pl[64] pr[64]
+    // streamed host path (plf_newview_stream): kStreamSlots chunk buffers + streams, allocated lazily
+    static constexpr int kStreamSlots = 3;
+    size_t stream_chunk = 0;                // sites per chunk the slots are sized for
+    float *sd_x1[kStreamSlots] = {nullptr, nullptr, nullptr};
+    float *sd_x2[kStreamSlots] = {nullptr, nullptr, nullptr};
+    float *sd_x3[kStreamSlots] = {nullptr, nullptr, nullptr};
+    unsigned char *sd_sc[kStreamSlots] = {nullptr, nullptr, nullptr};
+    int *sd_wgt[kStreamSlots] = {nullptr, nullptr, nullptr};
+    cudaStream_t s_stream[kStreamSlots] = {nullptr, nullptr, nullptr};
+    float *sd_mats = nullptr;               // EV[16] | P_left[64] | P_right[64]
+    unsigned long long *sd_sum = nullptr, *sh_sum = nullptr;
     std::vector<Instance> inst;
     std::mutex err_mu;
     std::string error;
@@ -494,6 +505,18 @@ int plf_ctx_destroy(plf_ctx *ctx)
             if (m) cudaEventDestroy(m);
         if (I.stream) cudaStreamDestroy(I.stream);
     }
+    for (int k = 0; k < plf_ctx::kStreamSlots; ++k) {
+        if (ctx->s_stream[k]) cudaStreamSynchronize(ctx->s_stream[k]);
+        cudaFree(ctx->sd_x1[k]);
+        cudaFree(ctx->sd_x2[k]);
+        cudaFree(ctx->sd_x3[k]);
+        cudaFree(ctx->sd_sc[k]);
+        cudaFree(ctx->sd_wgt[k]);
+        if (ctx->s_stream[k]) cudaStreamDestroy(ctx->s_stream[k]);
+    }
+    cudaFree(ctx->sd_mats);
+    cudaFree(ctx->sd_sum);
+    if (ctx->sh_sum) cudaFreeHost(ctx->sh_sum);
     delete ctx;
     return PLF_OK;
 }
@@ -873,6 +896,89 @@ int plf_generate_host(float *x1, float *x2, size_t first_site, size_t n, uint64_
     if (!x1 || !x2) return fail(nullptr, PLF_ERR_INVALID, "NULL argument");
     for (size_t e = 0; e < n * 16; ++e)
         plf::gen_pair(seed, (uint64_t)first_site * 16u + e, x1[e], x2[e]);
+    return PLF_OK;
+}
+
+// Streamed host path: the whole round trip of one newview over host-resident,
+// UNPACKED arrays, cut into chunks that flow through kStreamSlots device buffers on as many streams, so
+// that the H2D copy of chunk k+1, the kernel of chunk k and the D2H copy of chunk k-1 overlap.  It is the
+// analogue of the reference's NO_INTERMEDIATE_RESULTS=1 round-trip mode (host_mem.cpp:327-382) without
+// the host-side packing pass, and it lifts the device-memory limit (the reference's sweep list goes to
+// 1e9 sites = 192 GB of CLVs, Makefile:16).
+int plf_newview_stream(plf_ctx *ctx, const float *ev, const float *p_left, const float *p_right, const float *x1,
+                       const float *x2, float *x3, char *scaler, const int *wgt, size_t n_sites, size_t chunk_sites,
+                       long long *increment)
+{
+    if (!ctx) return fail(nullptr, PLF_ERR_INVALID, "NULL context");
+    if (!ev || !p_left || !p_right) return fail(ctx, PLF_ERR_INVALID, "stream: NULL matrix");
+    if (n_sites && (!x1 || !x2 || !x3)) return fail(ctx, PLF_ERR_INVALID, "stream: NULL host CLV");
+    PLF_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (chunk_sites == 0) chunk_sites = (size_t)2 << 20;            // 128 MiB per CLV chunk
+    if (chunk_sites > n_sites && n_sites > 0) chunk_sites = n_sites;
+    chunk_sites = (chunk_sites + 255) & ~(size_t)255;
+    constexpr int K = plf_ctx::kStreamSlots;
+    if (!ctx->sd_mats) {
+        PLF_CUDA(ctx, cudaMalloc(&ctx->sd_mats, 144 * sizeof(float)));
+        PLF_CUDA(ctx, cudaMalloc(&ctx->sd_sum, sizeof(unsigned long long)));
+        PLF_CUDA(ctx, cudaMallocHost(&ctx->sh_sum, sizeof(unsigned long long)));
+        for (int k = 0; k < K; ++k) PLF_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_stream[k], cudaStreamNonBlocking));
+    }
+    if (ctx->stream_chunk < chunk_sites) {                          // (re)size the chunk buffers
+        for (int k = 0; k < K; ++k) {
+            PLF_CUDA(ctx, cudaStreamSynchronize(ctx->s_stream[k]));
+            cudaFree(ctx->sd_x1[k]);
+            cudaFree(ctx->sd_x2[k]);
+            cudaFree(ctx->sd_x3[k]);
+            cudaFree(ctx->sd_sc[k]);
+            cudaFree(ctx->sd_wgt[k]);
+            ctx->sd_x1[k] = ctx->sd_x2[k] = ctx->sd_x3[k] = nullptr;
+            ctx->sd_sc[k] = nullptr;
+            ctx->sd_wgt[k] = nullptr;
+        }
+        ctx->stream_chunk = 0;
+        const size_t clv = chunk_sites * PLF_SITE_FLOATS * sizeof(float);
+        for (int k = 0; k < K; ++k) {
+            PLF_CUDA(ctx, cudaMalloc(&ctx->sd_x1[k], clv));
+            PLF_CUDA(ctx, cudaMalloc(&ctx->sd_x2[k], clv));
+            PLF_CUDA(ctx, cudaMalloc(&ctx->sd_x3[k], clv));
+            PLF_CUDA(ctx, cudaMalloc(&ctx->sd_sc[k], chunk_sites));
+            PLF_CUDA(ctx, cudaMalloc(&ctx->sd_wgt[k], chunk_sites * sizeof(int)));
+        }
+        ctx->stream_chunk = chunk_sites;
+    }
+    cudaStream_t s0 = ctx->s_stream[0];
+    float mats[144];
+    memcpy(mats, ev, 16 * sizeof(float));
+    memcpy(mats + 16, p_left, 64 * sizeof(float));
+    memcpy(mats + 80, p_right, 64 * sizeof(float));
+    PLF_CUDA(ctx, cudaMemcpyAsync(ctx->sd_mats, mats, sizeof mats, cudaMemcpyHostToDevice, s0));
+    PLF_CUDA(ctx, cudaMemsetAsync(ctx->sd_sum, 0, sizeof(unsigned long long), s0));
+    PLF_CUDA(ctx, cudaStreamSynchronize(s0));                        // `mats` is a stack temporary
+    plf_launch_opts opts;
+    opts.math_mode = ctx->math;
+    opts.variant = ctx->variant;
+    opts.threads_per_block = ctx->threads;
+    opts.blocks_per_sm = ctx->blocks_per_sm;
+    opts.ev_per_category = 0;
+    size_t k = 0;
+    for (size_t lo = 0; lo < n_sites; lo += chunk_sites, ++k) {
+        const int b = (int)(k % K);
+        cudaStream_t st = ctx->s_stream[b];
+        const size_t cnt = n_sites - lo < chunk_sites ? n_sites - lo : chunk_sites;
+        const size_t bytes = cnt * PLF_SITE_FLOATS * sizeof(float);
+        PLF_CUDA(ctx, cudaMemcpyAsync(ctx->sd_x1[b], x1 + lo * 16, bytes, cudaMemcpyHostToDevice, st));
+        PLF_CUDA(ctx, cudaMemcpyAsync(ctx->sd_x2[b], x2 + lo * 16, bytes, cudaMemcpyHostToDevice, st));
+        if (wgt) PLF_CUDA(ctx, cudaMemcpyAsync(ctx->sd_wgt[b], wgt + lo, cnt * sizeof(int), cudaMemcpyHostToDevice, st));
+        int rc = launch_newview(ctx, ctx->sd_x1[b], ctx->sd_x2[b], ctx->sd_x3[b], ctx->sd_sc[b], ctx->sd_mats,
+                                ctx->sd_mats + 16, ctx->sd_mats + 80, wgt ? ctx->sd_wgt[b] : nullptr, cnt, ctx->sd_sum,
+                                &opts, st);
+        if (rc != PLF_OK) return rc;
+        PLF_CUDA(ctx, cudaMemcpyAsync(x3 + lo * 16, ctx->sd_x3[b], bytes, cudaMemcpyDeviceToHost, st));
+        if (scaler) PLF_CUDA(ctx, cudaMemcpyAsync(scaler + lo, ctx->sd_sc[b], cnt, cudaMemcpyDeviceToHost, st));
+    }
+    for (int b = 0; b < K; ++b) PLF_CUDA(ctx, cudaStreamSynchronize(ctx->s_stream[b]));
+    PLF_CUDA(ctx, cudaMemcpy(ctx->sh_sum, ctx->sd_sum, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (increment) *increment = (long long)*ctx->sh_sum;
     return PLF_OK;
 }
 

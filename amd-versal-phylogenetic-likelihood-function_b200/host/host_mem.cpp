@@ -67,7 +67,7 @@ std::vector<int> parse_devices(const std::string &arg)
     return devs;
 }
 
-bool prerun_check()
+[[maybe_unused]] bool prerun_check()
 {
     // Same Y/n gate as the reference (app/src/utils.cpp:9-39); EOF counts as yes.
     for (;;) {

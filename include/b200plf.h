@@ -139,6 +139,18 @@ int plf_instance_device_ptrs(plf_ctx *ctx, unsigned inst, float **left, float **
                              float **out, unsigned char **scaler);
 int plf_instance_stream(plf_ctx *ctx, unsigned inst, void **stream);
 
+/* ---- streamed host path -------------------------------------------------
+ * One newview over HOST-resident, unpacked arrays (the arguments of plf(), plf.h:1-5): the site range is
+ * cut into chunks of chunk_sites (0 = 2 Mi) that flow through three device buffers on three streams, so
+ * the H2D copy of one chunk, the kernel of the previous one and the D2H copy of the one before overlap.
+ * The analogue of the reference's NO_INTERMEDIATE_RESULTS=1 round-trip mode (host_mem.cpp:327-382)
+ * without the packing pass, and not limited by device memory.  Blocks until x3 / scaler are complete.
+ * ev[16], p_left[64], p_right[64] host; x1, x2, x3 host n_sites*16 floats (pinned => asynchronous
+ * copies); scaler host n_sites chars or NULL; wgt host ints or NULL; increment may be NULL.           */
+int plf_newview_stream(plf_ctx *ctx, const float *ev, const float *p_left, const float *p_right,
+                       const float *x1, const float *x2, float *x3, char *scaler, const int *wgt,
+                       size_t n_sites, size_t chunk_sites, long long *increment);
+
 /* ---- pinned host memory -------------------------------------------------------------------- */
 int plf_host_alloc(void **ptr, size_t bytes);
 int plf_host_free(void *ptr);

@@ -479,3 +479,21 @@ def test_full_size_properties(pkg, gpu, coracle, n_sites):
     torch.cuda.synchronize()
     assert d3.view(torch.int32).to(torch.int64).sum().item() == first
     assert torch.isfinite(d3).all()
+
+
+@pytest.mark.parametrize("n,chunk", [(1, 0), (300001, 65536), (70000, 1 << 20), (262144, 65536)])
+def test_streamed_host_path_matches_oracle(pkg, gpu, coracle, n, chunk):
+    """plf_newview_stream: chunked / overlapped round trip over unpacked host arrays, bit-exact, incl.
+    a ragged last chunk, weights and the scaler bytes; buffers are reused across calls and resized."""
+    ev, left, right, x1, x2, wgt = signed_inputs(n, seed=n + 7)
+    o3, osc, oinc = coracle.newview(x1, x2, ev, left, right, wgt)
+    with pkg.Context(0, 1) as ctx:
+        for _ in range(2):
+            x3 = np.full((n, 16), np.nan, np.float32)
+            sc = np.full(n, 7, np.uint8)
+            inc = ctx.newview_stream(ev, left, right, x1, x2, x3, sc, wgt, chunk_sites=chunk)
+            assert inc == oinc and np.array_equal(sc, osc)
+            assert np.array_equal(bits(x3), bits(o3)), first_mismatch(x3, o3)
+        x3b = np.empty((n, 16), np.float32)
+        assert ctx.newview_stream(ev, left, right, x1, x2, x3b, None, None, chunk_sites=max(256, chunk // 2)) == int(osc.sum())
+        assert np.array_equal(bits(x3b), bits(o3))

@@ -115,3 +115,24 @@ def test_host_gen_runs(hosts, sink):
     r = run(hosts[1], CFG_GEN, 0, 1 << 20, 3, 4, env={"PLF_GEN_SINK": sink})
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "G sites/s" in r.stdout and "scalerIncrement (instance 0, last call): 0" in r.stdout
+
+
+HOST_STREAM = os.path.join(PKG_DIR, "host_stream.exe")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sites,calls,chunk", [(100, 1, 0), (300001, 2, 65536), (1 << 20, 2, 0), (5000000, 1, 1 << 20)])
+def test_host_stream_end_to_end(hosts, sites, calls, chunk):
+    """The streamed round trip: chunked, triple-buffered H2D / kernel / D2H over unpacked host
+    arrays, verified exactly against the host's CPU golden."""
+    args = [CFG_COMB, 0, sites, calls] + ([chunk] if chunk else [])
+    r = run(HOST_STREAM, *args)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "Test result: Passed" in r.stdout
+    assert f"scalerIncrement (last call): {(sites + 3) // 4}" in r.stdout
+
+
+def test_host_stream_argument_errors(hosts):
+    assert run(HOST_STREAM).returncode == 2
+    r = run(HOST_STREAM, CFG_GEN, 0, 100, 1)
+    assert r.returncode == 2 and "INPUT_SRC=mem" in r.stderr
