@@ -1,8 +1,8 @@
-"""Developer stress test: repeat small tree traversals with poisoned device memory and report any
+"""Test helper (run by hand on a GPU box: python tests/stress_tree.py 150): stress test: repeat small tree traversals with poisoned device memory and report any
 mismatch against the oracle (site list, which categories, tuning)."""
 import os, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))   # tests/ -> repo root
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import bench, oracle, torch
 from oracle import tree_oracle

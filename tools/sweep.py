@@ -30,10 +30,9 @@ def main():
 
     import torch
     pkg = bench.load_pkg()
-    import oracle
     dev = torch.device("cuda", 0)
     n = args.sites
-    ev, left, right, *_ = oracle.host_mem_inputs(1, seed=42)
+    ev, left, right = bench.stimulus_matrices(42)
     d_ev, d_pl, d_pr = (torch.from_numpy(a).to(dev) for a in (ev, left, right))
     x1 = torch.empty((n, 16), device=dev)
     x2 = torch.empty((n, 16), device=dev)
