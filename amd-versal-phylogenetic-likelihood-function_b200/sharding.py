@@ -57,3 +57,36 @@ def max_over_ranks(value: float, device=None, group=None) -> float:
     t = torch.tensor([float(value)], dtype=torch.float64, device=device or "cpu")
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return float(t.item())
+
+
+def bind_host_to_device(device_index: int) -> dict:
+    """Pin the calling process to the CPUs NVML reports as local to GPU `device_index`, so that pinned
+    host buffers allocated afterwards land on the GPU's own NUMA node (first touch) and the copy
+    engines do not cross the socket interconnect.  Pure plumbing for the host<->device legs of a
+    multi-GPU box; a no-op (returns {"bound": False, ...}) when NVML, the affinity mask or
+    sched_setaffinity are unavailable, or when the mask would be empty inside this cgroup."""
+    import os
+    info = {"bound": False, "device": device_index}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = device_index
+        if visible:
+            entry = visible.split(",")[device_index].strip()
+            if entry.isdigit():
+                idx = int(entry)
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64 + 1)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        target = cpus & allowed
+        info["gpu_local_cpus"] = len(cpus)
+        info["allowed_cpus"] = len(allowed)
+        if target and target != allowed:
+            os.sched_setaffinity(0, target)
+            info["bound"] = True
+        info["cpus"] = len(target or allowed)
+    except Exception as e:  # no NVML / not permitted: leave the process where it is
+        info["error"] = f"{type(e).__name__}: {e}"[:120]
+    return info

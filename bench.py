@@ -336,6 +336,7 @@ def run_e2e(pkg, torch, args, local_rank, first, n, total_sites, world, math_mod
             device, ev, left, right):
     """Host buffers -> plf_write_* -> plf_run_async -> plf_read_* on NUM_ACCELERATORS instances."""
     inst = args.instances
+    numa = sharding.bind_host_to_device(local_rank) if world > 1 and not args.no_numa_bind else {"bound": False}
     tb = pkg.TestbenchInfo(n, inst)
     if not tb.valid():
         inst, tb = 1, pkg.TestbenchInfo(n, 1)
@@ -415,7 +416,7 @@ def run_e2e(pkg, torch, args, local_rank, first, n, total_sites, world, math_mod
         pkg.host_free(p)
     return {"value": total_sites * e2e_steps / dt, "unit": "sites/s", "stream": stream,
             "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-            "instances": inst, "ms_per_step": dt / e2e_steps * 1e3,
+            "instances": inst, "ms_per_step": dt / e2e_steps * 1e3, "host_binding": numa,
             "timing": "host wall clock around plf_write/run/read/wait, barrier + device sync on both sides, max over ranks",
             "pcie_gbs_per_gpu": (h2d + d2h) * e2e_steps / dt / 1e9}
 
@@ -436,6 +437,7 @@ def main():
     ap.add_argument("--instances", type=int, default=9, help="NUM_ACCELERATORS for the e2e leg")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="N>1: do not pin each rank to its GPU's local CPUs")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: route everything libraries print on fd 1 (e.g. NCCL's
     # version banner) to stderr and restore the real stdout only around our own print.

@@ -75,3 +75,19 @@ def test_shard_rule_is_the_reference_instance_split(pkg):
     with pytest.raises(ValueError):
         sharding.shard_for_rank(10, 2, 2)
     assert sharding.reduce_scaler_increment(5) == 5       # no process group: identity
+
+
+def test_bind_host_to_device_never_narrows_to_nothing(pkg):
+    """The NUMA helper is best effort: without NVML it reports why and leaves the affinity mask alone."""
+    import importlib
+    sh = importlib.import_module(pkg.__name__ + ".sharding")
+    before = os.sched_getaffinity(0)
+    info = sh.bind_host_to_device(0)
+    after = os.sched_getaffinity(0)
+    try:
+        assert isinstance(info, dict) and "bound" in info
+        assert after and after <= before
+        if not info["bound"]:
+            assert after == before
+    finally:
+        os.sched_setaffinity(0, before)
