@@ -52,7 +52,7 @@ lib:
 CSRC := $(PKG)/csrc
 OBJDIR := $(PKG)/build
 KHDRS := $(CSRC)/plf_kernels.cuh $(CSRC)/plf_registry.h include/b200plf.h
-OBJS := $(OBJDIR)/plf_capi.o $(OBJDIR)/plf_tree.o $(OBJDIR)/plf_evaluate.o $(OBJDIR)/sel_ldg_strict.o $(OBJDIR)/sel_ldg_fma.o \
+OBJS := $(OBJDIR)/plf_capi.o $(OBJDIR)/plf_tree.o $(OBJDIR)/plf_evaluate.o $(OBJDIR)/plf_protein.o $(OBJDIR)/sel_ldg_strict.o $(OBJDIR)/sel_ldg_fma.o \
         $(OBJDIR)/sel_tma_strict.o $(OBJDIR)/sel_tma_fma.o $(OBJDIR)/sel_dyn_strict.o $(OBJDIR)/sel_dyn_fma.o
 
 $(OBJDIR)/plf_capi.o: $(CSRC)/plf_capi.cu $(KHDRS)
@@ -63,6 +63,10 @@ $(OBJDIR)/plf_tree.o: $(CSRC)/plf_tree.cu $(KHDRS)
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) -c -o $@ $<
 $(OBJDIR)/plf_evaluate.o: $(CSRC)/plf_evaluate.cu $(KHDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -c -o $@ $<
+
+$(OBJDIR)/plf_protein.o: $(CSRC)/plf_protein.cu $(KHDRS)
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) -c -o $@ $<
 

@@ -113,6 +113,11 @@ PROTOTYPES = {
     "plf_tree_last_ms": (_i, [_vp, ctypes.POINTER(ctypes.c_float)]),
     "plf_tree_evaluate_root": (_i, [_vp, _vp, ctypes.POINTER(ctypes.c_double)]),
     "plf_evaluate_device": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "plf_newview_states_device": (_i, [_i] + [_vp] * 8 + [_sz, _vp, ctypes.POINTER(LaunchOpts), _vp]),
+    "plf_generate_states_device": (_i, [_i, _vp, _vp, _sz, _sz, ctypes.c_uint64, _vp]),
+    "plf_generate_states_host": (_i, [_i, _vp, _vp, _sz, _sz, ctypes.c_uint64]),
+    "plf_states_kernel_info": (_i, [_i, _i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_sz),
+                                    ctypes.POINTER(_i)]),
     "plf_kernel_info": (_i, [_i, _i] + [ctypes.POINTER(_i)] * 4),
     "plf_launch_count": (ctypes.c_ulonglong, []),
 }
@@ -470,6 +475,44 @@ def kernel_info(variant: int = 0, math_mode: int = MATH_STRICT, threads: int = 0
     _check(load().plf_kernel_info(variant, math_mode, ctypes.byref(regs), ctypes.byref(thr),
                                   ctypes.byref(bps), ctypes.byref(sms)))
     return {"regs": regs.value, "threads": thr.value, "blocks_per_sm": bps.value, "sms": sms.value}
+
+
+# ---- general state count: the reference's STATES knob (4 = DNA, 20 = protein; README.md:36,67,202) ----
+STATES_DNA, STATES_PROTEIN = 4, 20
+
+
+def newview_states_device(states: int, x1, x2, x3, scaler, ev, p_left, p_right, wgt, n: int, scaler_sum,
+                          opts: LaunchOpts | None = None, stream: int = 0):
+    """plf() for `states` states.  CLVs / scaler / wgt / scaler_sum are DEVICE pointers (ints); ev [S*S],
+    p_left / p_right [4*S*S] are HOST numpy arrays (they travel as kernel arguments).  For 20 states
+    opts.variant = sites per lane (1, 2, 4; 0 = default for the math mode)."""
+    S = int(states)
+    mats = []
+    for a, k in ((ev, S * S), (p_left, 4 * S * S), (p_right, 4 * S * S)):
+        a = np.ascontiguousarray(a, np.float32).reshape(-1)
+        if a.size != k:
+            raise ValueError(f"matrix has {a.size} floats, expected {k} for {S} states")
+        mats.append(a)
+    _check(load().plf_newview_states_device(S, x1, x2, x3, scaler, _ptr(mats[0]), _ptr(mats[1]), _ptr(mats[2]), wgt, n,
+                                            scaler_sum, ctypes.byref(opts) if opts is not None else None, stream or None))
+
+
+def generate_states_device(states: int, x1, x2, first_site: int, n: int, seed: int, stream: int = 0):
+    _check(load().plf_generate_states_device(states, x1, x2, first_site, n, seed, stream or None))
+
+
+def generate_states_host(states: int, first_site: int, n: int, seed: int):
+    x1 = np.empty((n, 4 * states), np.float32)
+    x2 = np.empty((n, 4 * states), np.float32)
+    _check(load().plf_generate_states_host(states, _ptr(x1), _ptr(x2), first_site, n, seed))
+    return x1, x2
+
+
+def states_kernel_info(states: int = STATES_PROTEIN, math_mode: int = MATH_STRICT, variant: int = 0, threads: int = 0):
+    regs, thr, smem, tile = _i(0), _i(0), _sz(0), _i(0)
+    _check(load().plf_states_kernel_info(states, math_mode, variant, threads, ctypes.byref(regs), ctypes.byref(thr),
+                                         ctypes.byref(smem), ctypes.byref(tile)))
+    return {"regs": regs.value, "threads": thr.value, "smem_bytes": smem.value, "tile_sites": tile.value}
 
 
 def host_alloc(nbytes: int, dtype=np.uint8):

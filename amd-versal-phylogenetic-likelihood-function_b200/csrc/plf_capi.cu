@@ -994,6 +994,70 @@ int plf_evaluate_device(const float *x1, const float *x2, const int *cnt1, const
     return PLF_OK;
 }
 
+int plf_newview_states_device(int states, const float *x1, const float *x2, float *x3, unsigned char *scaler,
+                              const float *ev, const float *p_left, const float *p_right, const int *wgt, size_t n,
+                              unsigned long long *scaler_sum, const plf_launch_opts *opts, void *stream)
+{
+    if (states != 4 && states != 20)
+        return fail(nullptr, PLF_ERR_INVALID, "STATES=%d is not supported (4 = DNA, 20 = protein)", states);
+    if (n == 0) return PLF_OK;
+    if (!x1 || !x2 || !x3 || !ev || !p_left || !p_right) return fail(nullptr, PLF_ERR_INVALID, "newview: NULL pointer");
+    if (((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)x3) & 15u)
+        return fail(nullptr, PLF_ERR_INVALID, "newview: CLV pointers must be 16-byte aligned");
+    const int math = opts ? opts->math_mode : PLF_MATH_STRICT;
+    if (math != PLF_MATH_STRICT && math != PLF_MATH_FMA) return fail(nullptr, PLF_ERR_INVALID, "unknown math mode %d", math);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (states == 4) {
+        // the matrices are HOST arrays in this entry point: stage them on the stream for the DNA kernel
+        float *d_m = nullptr;
+        PLF_CUDA(nullptr, cudaMallocAsync(&d_m, 144 * sizeof(float), st));
+        cudaError_t e = cudaMemcpyAsync(d_m, ev, 16 * sizeof(float), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_m + 16, p_left, 64 * sizeof(float), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_m + 80, p_right, 64 * sizeof(float), cudaMemcpyHostToDevice, st);
+        int rc = e == cudaSuccess ? launch_newview(nullptr, x1, x2, x3, scaler, d_m, d_m + 16, d_m + 80, wgt, n, scaler_sum, opts, st)
+                                  : fail(nullptr, PLF_ERR_CUDA, "matrix upload failed: %s", cudaGetErrorString(e));
+        cudaFreeAsync(d_m, st);
+        return rc;
+    }
+    if (opts && opts->ev_per_category) return fail(nullptr, PLF_ERR_INVALID, "ev_per_category is a DNA gen-mode option");
+    int rc = plf::launch_newview_aa(x1, x2, x3, scaler, ev, p_left, p_right, wgt, n, scaler_sum, math,
+                                    opts ? opts->variant : 0, opts ? opts->threads_per_block : 0, st);
+    if (rc == PLF_ERR_INVALID)
+        return fail(nullptr, rc, "no 20-state kernel for variant %d / threads %d", opts ? opts->variant : 0,
+                    opts ? opts->threads_per_block : 0);
+    if (rc != PLF_OK) return fail(nullptr, rc, "20-state newview launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return PLF_OK;
+}
+
+int plf_generate_states_device(int states, float *x1, float *x2, size_t first_site, size_t n, uint64_t seed, void *stream)
+{
+    if (states != 4 && states != 20) return fail(nullptr, PLF_ERR_INVALID, "STATES=%d is not supported (4 = DNA, 20 = protein)", states);
+    if (n == 0) return PLF_OK;
+    if (!x1 || !x2 || (((uintptr_t)x1 | (uintptr_t)x2) & 15u))
+        return fail(nullptr, PLF_ERR_INVALID, "generate: x1/x2 must be 16-byte aligned device pointers");
+    int rc = plf::launch_generate_states(states, x1, x2, first_site, n, seed, static_cast<cudaStream_t>(stream));
+    if (rc != PLF_OK) return fail(nullptr, rc, "generator launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return PLF_OK;
+}
+
+int plf_generate_states_host(int states, float *x1, float *x2, size_t first_site, size_t n, uint64_t seed)
+{
+    if (states != 4 && states != 20) return fail(nullptr, PLF_ERR_INVALID, "STATES=%d is not supported (4 = DNA, 20 = protein)", states);
+    if (!x1 || !x2) return fail(nullptr, PLF_ERR_INVALID, "NULL argument");
+    plf::generate_states_host(states, x1, x2, first_site, n, seed);
+    return PLF_OK;
+}
+
+int plf_states_kernel_info(int states, int math_mode, int variant, int threads_per_block, int *regs_per_thread,
+                           int *block_threads, size_t *smem_bytes, int *tile_sites)
+{
+    if (states != 20) return fail(nullptr, PLF_ERR_INVALID, "plf_states_kernel_info: STATES=%d (use plf_kernel_info for DNA)", states);
+    int rc = plf::aa_kernel_info(math_mode, variant, threads_per_block, regs_per_thread, block_threads, smem_bytes, tile_sites);
+    if (rc == PLF_ERR_INVALID) return fail(nullptr, rc, "no 20-state kernel for variant %d / threads %d", variant, threads_per_block);
+    if (rc != PLF_OK) return fail(nullptr, rc, "cudaFuncGetAttributes failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return PLF_OK;
+}
+
 int plf_kernel_info(int variant, int math_mode, int *regs_per_thread, int *threads_per_block,
                     int *blocks_per_sm, int *num_sms)
 {

@@ -15,6 +15,7 @@
 
 #include <cuda_runtime.h>
 #include <stddef.h>
+#include <stdint.h>
 
 namespace plf {
 
@@ -41,6 +42,14 @@ KernelSel select_tma_dyn_fma(int u, int d, int b, int threads);
 // root log-likelihood kernel (plf_evaluate.cu); returns a plf_status
 int launch_evaluate(const float *x1, const float *x2, const int *cnt1, const int *cnt2, const int *wgt,
                     const float *diag, size_t n, double *lnl, cudaStream_t stream);
+
+// 20-state (protein) newview and the S-state stimulus generator (plf_protein.cu); return a plf_status
+int launch_newview_aa(const float *x1, const float *x2, float *x3, unsigned char *scaler, const float *ev,
+                      const float *pl, const float *pr, const int *wgt, size_t n, unsigned long long *scaler_sum,
+                      int math, int variant, int threads, cudaStream_t stream);
+int aa_kernel_info(int math, int variant, int threads, int *regs, int *block_threads, size_t *smem, int *tile_sites);
+int launch_generate_states(int states, float *x1, float *x2, size_t first_site, size_t n, uint64_t seed, cudaStream_t stream);
+void generate_states_host(int states, float *x1, float *x2, size_t first_site, size_t n, uint64_t seed);
 
 // process-wide count of kernel launches issued by this library (plf_launch_count)
 void count_launches(unsigned long long n);

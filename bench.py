@@ -421,13 +421,71 @@ def run_e2e(pkg, torch, args, local_rank, first, n, total_sites, world, math_mod
             "pcie_gbs_per_gpu": (h2d + d2h) * e2e_steps / dt / 1e9}
 
 
+def run_protein_arm(args):
+    """`--workload protein`: the 20-state newview on one GPU, device-resident CLVs, with the CPU
+    restatement (reference plf() loop nest at S = 20, all host threads) timed beside it.  Not the headline line:
+    the reference has no protein path, so there is no reference arm for it."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import protein_bench
+    pkg = load_pkg()
+    torch.cuda.set_device(0)
+    n = args.sites or (4 << 20)
+    K = max(3, args.steps)
+    from tools.clocks import ClockSampler
+    sampler = ClockSampler(0)
+    sampler.start()
+    sampler.begin()
+    res = protein_bench.measure(pkg, torch, n, K, shapes=[(0, 0)], maths=(0, 1), verbose=False)
+    sampler.end()
+    clk = sampler.stop()
+    strict, fma = res["rows"]
+    assert strict["ok"] and fma["ok"], "20-state run failed its self-checks"
+    cpu = None
+    if not args.no_cpu_baseline:
+        import oracle                                   # cpu_baseline leg
+        cores = os.cpu_count() or 1
+        sample = 1 << 18
+        rng = np.random.RandomState(SEED)
+        ev, left, right = (rng.random_sample(k).astype(np.float32) for k in (400, 1600, 1600))
+        x1, x2 = pkg.generate_states_host(20, 0, sample, SEED)
+        co = oracle.COracle()
+        best = {}
+        for thr in (1, cores):
+            ts = []
+            for _ in range(2):
+                t0 = time.perf_counter()
+                _, _, inc = co.newview_states(20, x1, x2, ev, left, right, nthreads=thr)
+                ts.append(time.perf_counter() - t0)
+            assert inc == sample // 4
+            best[thr] = sample / min(ts)
+        cpu = {"value": best[cores], "unit": "sites/s", "cores": cores, "kind": "port",
+               "sample": f"{sample} sites, best of 2, reference plf() loop nest with 20 states (-O2 -ffp-contract=off)",
+               "single_thread_sites_per_s": best[1]}
+    line = {"metric": "plf_sites_per_s", "value": strict["gsites"] * 1e9, "unit": "sites/s", "n_gpus": 1, "steps": K,
+            "warmup": 2, "ms_per_step": strict["ms_mean"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "STATES=protein: 20 states x 4 rate categories, device-resident CLVs (SURVEY 8f.3)",
+                       "total_sites": n, "math": "strict", "bytes_per_site": res["bytes_per_site"],
+                       "muladd_per_site": res["muladd_per_site"], "kernel": {k: strict[k] for k in ("regs", "threads", "smem_bytes")},
+                       "l2": f"inputs {2 * n * 320 >> 20} MiB >> 126 MB L2"},
+            "roofline": {"bound": "hbm", "achieved": strict["gbs"], "peak": res["peak_gbs"], "unit": "GB/s",
+                         "frac": strict["gbs"] / res["peak_gbs"], "traffic": None,
+                         "note": "on the ridge: 4800 multiply-adds and 961 B per site; fp32 rate "
+                                 f"{strict['tmuladd_per_s']:.1f} T mul-add/s of ~34 T/s (117/clk/SM measured)"},
+            "fma_mode": {"value": fma["gsites"] * 1e9, "gbs": fma["gbs"], "frac": fma["gbs"] / res["peak_gbs"],
+                         "tmuladd_per_s": fma["tmuladd_per_s"], "kernel": {k: fma[k] for k in ("regs", "threads", "smem_bytes")}},
+            "cpu_baseline": cpu, "e2e": None, "gpu_launches": 2 * (K + 2) + 1, "clocks": clk}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg3", choices=list(TOTAL_SITES))
+    ap.add_argument("--workload", default="cfg3", choices=list(TOTAL_SITES) + ["protein"])
     ap.add_argument("--sites", type=int, default=0, help="override total site count")
     ap.add_argument("--math", default="strict", choices=["strict", "fma"])
     ap.add_argument("--variant", type=int, default=0)
@@ -445,7 +503,11 @@ def main():
     real_stdout = os.dup(1)
     os.dup2(2, 1)
     sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
-    if args.impl == "reference":
+    if args.workload == "protein":
+        if args.impl == "reference" or int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            raise SystemExit("--workload protein is a single-GPU b200-arm measurement")
+        run_protein_arm(args)
+    elif args.impl == "reference":
         run_reference_arm(args)
     else:
         run_b200_arm(args)

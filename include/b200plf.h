@@ -274,6 +274,36 @@ int plf_evaluate_device(const float *x1, const float *x2, const int *cnt1, const
  * Must follow a completed plf_tree_run_async (the children's buffers are still intact then).  */
 int plf_tree_evaluate_root(plf_tree *tree, const float *diag, double *lnl);
 
+/* ---- general state count: the STATES knob ---------------------------
+ * The reference builds with STATES=DNA only (Makefile knob, README.md:67); "any other type of data
+ * with more or fewer states" is anticipated (README.md:36) and "Implement protein-based PLF" is an
+ * open to-do (README.md:202).  These entry points run plf() (app/src/plf.cpp:19-65) with the state
+ * count S in {4 (DNA), 20 (protein)}:
+ *   x1,x2,x3 : DEVICE float[n*4*S]  [site][category][state], 16-byte aligned
+ *   ev       : HOST float[S*S]      [k][l]
+ *   p_left/p_right : HOST float[4*S*S] [category][k][l]
+ *   scaler   : DEVICE uint8[n] or NULL; wgt DEVICE int32[n] or NULL; scaler_sum DEVICE counter or NULL
+ * The matrices are HOST arrays (they are host arrays in the reference's host too, host_mem.cpp:183-197): the
+ * 20-state kernel receives them as a kernel argument and reads them through the constant bank; they are
+ * consumed before the call returns.  A site rescales when all 4*S entries are below 2^-32.  S = 4 runs the DNA
+ * kernel of plf_newview_device.  For S = 20, opts->variant is the number of sites per lane of the register tile
+ * (1, 2 or 4; threads_per_block 512 / 256,384 / 128,256); 0 = the fastest measured shape for the math mode.   */
+int plf_newview_states_device(int states, const float *x1, const float *x2, float *x3,
+                              unsigned char *scaler, const float *ev, const float *p_left,
+                              const float *p_right, const int *wgt, size_t n,
+                              unsigned long long *scaler_sum, const plf_launch_opts *opts,
+                              void *stream);
+/* Stimulus of host_mem.cpp:198-204 for S states (uniform(0,1); the left CLV of every 4th site
+ * tiny, so exactly ceil(n/4) sites rescale): identical to plf_generate_device for S = 4.        */
+int plf_generate_states_device(int states, float *x1, float *x2, size_t first_site, size_t n,
+                               uint64_t seed, void *stream);
+int plf_generate_states_host(int states, float *x1, float *x2, size_t first_site, size_t n,
+                             uint64_t seed);
+/* Introspection of the 20-state kernel chosen for (math_mode, variant, threads_per_block). */
+int plf_states_kernel_info(int states, int math_mode, int variant, int threads_per_block,
+                           int *regs_per_thread, int *block_threads, size_t *smem_bytes,
+                           int *tile_sites);
+
 /* Largest tile the library was compiled for, number of SMs etc. -- introspection for benches. */
 int plf_kernel_info(int variant, int math_mode, int *regs_per_thread, int *threads_per_block,
                     int *blocks_per_sm, int *num_sms);

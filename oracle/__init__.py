@@ -70,6 +70,10 @@ class COracle:
         L.plf_oracle_transpose4.argtypes = [_f32p, _f32p]
         L.plf_oracle_newview_mt.restype = ctypes.c_int64
         L.plf_oracle_newview_mt.argtypes = L.plf_oracle_newview.argtypes + [ctypes.c_int]
+        L.plf_oracle_newview_states.restype = ctypes.c_int64
+        L.plf_oracle_newview_states.argtypes = [ctypes.c_int] + L.plf_oracle_newview.argtypes
+        L.plf_oracle_newview_states_mt.restype = ctypes.c_int64
+        L.plf_oracle_newview_states_mt.argtypes = L.plf_oracle_newview_states.argtypes + [ctypes.c_int]
 
     def newview(self, x1, x2, ev, left, right, wgt=None, nthreads: int = 1, ev4: bool = False):
         """Returns (x3[n,16] f32, scaler[n] u8, scaler_increment int)."""
@@ -90,6 +94,26 @@ class COracle:
             inc = self.lib.plf_oracle_newview_mt(*args, nthreads)
         else:
             inc = self.lib.plf_oracle_newview(*args)
+        return x3, sc, int(inc)
+
+    def newview_states(self, states: int, x1, x2, ev, left, right, wgt=None, nthreads: int = 1):
+        """General state count (4 = DNA, 20 = protein).  Returns (x3[n,4*S] f32, scaler[n] u8, increment)."""
+        x1, x2, ev, left, right = map(_f32, (x1, x2, ev, left, right))
+        S = int(states)
+        n = x1.size // (4 * S)
+        assert x1.size == n * 4 * S and x2.size == x1.size
+        assert ev.size == S * S and left.size == 4 * S * S and right.size == 4 * S * S
+        if wgt is not None:
+            wgt = np.ascontiguousarray(wgt, dtype=np.int32)
+            assert wgt.size == n
+        x3 = np.empty((n, 4 * S), dtype=np.float32)
+        sc = np.empty(n, dtype=np.uint8)
+        args = [S, _ptr(x1, _f32p), _ptr(x2, _f32p), _ptr(x3, _f32p), _ptr(ev, _f32p), n,
+                _ptr(left, _f32p), _ptr(right, _f32p), _ptr(wgt, _i32p), _ptr(sc, _u8p)]
+        inc = (self.lib.plf_oracle_newview_states_mt(*args, nthreads) if nthreads > 1
+               else self.lib.plf_oracle_newview_states(*args))
+        if inc < 0:
+            raise ValueError(f"unsupported state count {S}")
         return x3, sc, int(inc)
 
     def newview_packed(self, left_buf, right_buf, layout: int, n: int, wgt=None):

@@ -196,3 +196,104 @@ int64_t plf_oracle_newview_mt(const float *x1, const float *x2, float *x3,
     free(tids);
     return total;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * General state count (the reference's STATES knob, README.md:36,67; "Implement protein-based
+ * PLF" is an open to-do there, README.md:202).  The loops of app/src/plf.cpp:19-65 with every
+ * literal 4 that means "states" replaced by S (and 16 by S*S / 4*S): same accumulation order
+ * (x3 zeroed, l-then-k for the branch sums, "x3[j*S+l] += p[k]*EV[S*k+l]" with k outer), same
+ * threshold on all 4*S entries of the site.  Parity status: PINNED for S = 4 (tests assert it
+ * is bit-identical to the reference's plf()); for S = 20 it is the same code path -- there is
+ * no protein implementation in the reference to pin against.
+ * ------------------------------------------------------------------------------------------ */
+int64_t plf_oracle_newview_states(int S, const float *x1, const float *x2, float *x3,
+                                  const float *ev, size_t n,
+                                  const float *left, const float *right,
+                                  const int *wgt, unsigned char *scaler)
+{
+    if (S < 1 || S > 64)
+        return -1;
+    const size_t site = (size_t)PLF_CATS * (size_t)S;
+    int64_t total = 0;
+    float p[64];
+    for (size_t i = 0; i < n; ++i) {
+        const float *s1 = x1 + i * site, *s2 = x2 + i * site;
+        float *s3 = x3 + i * site;
+        for (size_t e = 0; e < site; ++e)
+            s3[e] = 0.0f;
+        for (int j = 0; j < PLF_CATS; ++j) {
+            for (int k = 0; k < S; ++k) {
+                float a = 0.0f, b = 0.0f;
+                for (int l = 0; l < S; ++l) {
+                    float pa = s1[j * S + l] * left[(j * S + k) * S + l];
+                    float pb = s2[j * S + l] * right[(j * S + k) * S + l];
+                    a = a + pa;
+                    b = b + pb;
+                }
+                p[k] = a * b;
+            }
+            for (int k = 0; k < S; ++k)
+                for (int l = 0; l < S; ++l) {
+                    float prod = p[k] * ev[S * k + l];
+                    s3[j * S + l] = s3[j * S + l] + prod;
+                }
+        }
+        int scale = 1;
+        for (size_t e = 0; scale && e < site; ++e) {
+            float mag = s3[e] < 0 ? -s3[e] : s3[e];
+            scale = mag < kMinLikelihood;
+        }
+        if (scale) {
+            for (size_t e = 0; e < site; ++e)
+                s3[e] = s3[e] * kTwoToThe32;
+            total += wgt ? (int64_t)wgt[i] : 1;
+        }
+        if (scaler)
+            scaler[i] = (unsigned char)scale;
+    }
+    return total;
+}
+
+struct states_job {
+    int S;
+    const float *x1, *x2, *ev, *left, *right;
+    float *x3;
+    const int *wgt;
+    unsigned char *scaler;
+    size_t n;
+    int64_t result;
+};
+
+static void *states_worker(void *arg)
+{
+    struct states_job *j = (struct states_job *)arg;
+    j->result = plf_oracle_newview_states(j->S, j->x1, j->x2, j->x3, j->ev, j->n, j->left, j->right, j->wgt, j->scaler);
+    return NULL;
+}
+
+int64_t plf_oracle_newview_states_mt(int S, const float *x1, const float *x2, float *x3,
+                                     const float *ev, size_t n, const float *left, const float *right,
+                                     const int *wgt, unsigned char *scaler, int nthreads)
+{
+    if (nthreads < 1) nthreads = 1;
+    if ((size_t)nthreads > n) nthreads = n ? (int)n : 1;
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)nthreads);
+    struct states_job *jobs = (struct states_job *)malloc(sizeof(struct states_job) * (size_t)nthreads);
+    const size_t per = (n + (size_t)nthreads - 1) / (size_t)nthreads, site = (size_t)PLF_CATS * (size_t)S;
+    for (int t = 0; t < nthreads; ++t) {
+        size_t lo = per * (size_t)t < n ? per * (size_t)t : n;
+        size_t cnt = lo + per <= n ? per : n - lo;
+        struct states_job job = {S, x1 + lo * site, x2 + lo * site, ev, left, right, x3 + lo * site,
+                                 wgt ? wgt + lo : NULL, scaler ? scaler + lo : NULL, cnt, 0};
+        jobs[t] = job;
+        pthread_create(&th[t], NULL, states_worker, &jobs[t]);
+    }
+    int64_t total = 0;
+    for (int t = 0; t < nthreads; ++t) {
+        pthread_join(th[t], NULL);
+        total += jobs[t].result;
+    }
+    free(th);
+    free(jobs);
+    return total;
+}

@@ -1,0 +1,101 @@
+#!/usr/bin/env python
+"""tools/protein_bench.py -- 20-state (STATES=protein) newview on one B200: shapes x arithmetic modes.
+
+Device-resident synthetic CLVs (plf_generate_states_device), CUDA events around back-to-back launches on the
+launching stream, inputs far larger than L2.  Prints sites/s, GB/s at 961 algorithmic bytes per site
+(2 x 320 read + 320 + 1 written), the fraction of the measured copy peak, and the fp32 rate (4800 multiply-adds
+per site).  Every strict shape is compared bit for bit with the first one.
+
+    python tools/protein_bench.py --sites 4194304 --reps 10 --out gpurun_out/protein.json
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+
+S = 20
+SITE = 4 * S
+BYTES_PER_SITE = 3 * SITE * 4 + 1
+MULADD_PER_SITE = 4 * 3 * S * S
+SHAPES = [(0, 0), (4, 256), (4, 128), (2, 384), (2, 256), (1, 512)]
+
+
+def measure(pkg, torch, n, reps, shapes=SHAPES, maths=(0, 1), seed=42, verbose=True):
+    import numpy as np
+    dev = torch.device("cuda", torch.cuda.current_device())
+    rng = np.random.RandomState(seed)
+    ev, left, right = (rng.random_sample(k).astype(np.float32) for k in (S * S, 4 * S * S, 4 * S * S))
+    x1 = torch.empty(n * SITE, device=dev)
+    x2 = torch.empty(n * SITE, device=dev)
+    x3 = torch.empty(n * SITE, device=dev)
+    sc = torch.empty(n, dtype=torch.uint8, device=dev)
+    dsum = torch.zeros(1, dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    pkg.generate_states_device(S, x1.data_ptr(), x2.data_ptr(), 0, n, seed, stream)
+    peak, _ = bench.measured_peak()
+    rows, ref3 = [], None
+    for math in maths:
+        for t, threads in shapes:
+            opts = pkg.make_opts(math, t, threads)
+            info = pkg.states_kernel_info(S, math, t, threads)
+            a = (S, x1.data_ptr(), x2.data_ptr(), x3.data_ptr(), sc.data_ptr(), ev, left, right, None, n, dsum.data_ptr(),
+                 opts, stream)
+            x3.zero_()
+            dsum.zero_()
+            for _ in range(2):
+                pkg.newview_states_device(*a)
+            torch.cuda.synchronize()
+            ok = int(dsum.item()) == 2 * ((n + 3) // 4)
+            if math == 0:
+                if ref3 is None:
+                    ref3 = x3.clone()
+                else:
+                    ok = ok and bool(torch.equal(x3.view(torch.int32), ref3.view(torch.int32)))
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+            evs[0].record()
+            for i in range(reps):
+                pkg.newview_states_device(*a)
+                evs[i + 1].record()
+            torch.cuda.synchronize()
+            ts = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(reps))
+            mean = evs[0].elapsed_time(evs[-1]) / reps
+            gs = n / (mean * 1e-3) / 1e9
+            row = {"variant": t, "threads": threads, "math": "fma" if math else "strict", "regs": info["regs"],
+                   "smem_bytes": info["smem_bytes"], "ms_mean": mean, "ms_min": ts[0], "gsites": gs,
+                   "gbs": gs * BYTES_PER_SITE, "frac_measured": gs * BYTES_PER_SITE / peak,
+                   "tmuladd_per_s": gs * MULADD_PER_SITE / 1e3, "ok": ok}
+            rows.append(row)
+            if verbose:
+                print(f"variant={t:2d} threads={threads:3d} {row['math']:6s} regs={info['regs']:3d} smem={info['smem_bytes'] >> 10:3d}K "
+                      f"mean={mean:8.4f} ms min={ts[0]:8.4f}  {gs:6.3f} G sites/s  {row['gbs']:6.0f} GB/s "
+                      f"({row['frac_measured']:.3f} of measured copy)  {row['tmuladd_per_s']:.1f} T mul-add/s  "
+                      f"{'ok' if ok else 'MISMATCH'}", file=sys.stderr, flush=True)
+    return {"sites": n, "reps": reps, "bytes_per_site": BYTES_PER_SITE, "muladd_per_site": MULADD_PER_SITE,
+            "peak_gbs": peak, "rows": rows}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--sites", type=int, default=1 << 22)
+    ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--out", default="")
+    args = ap.parse_args()
+    import torch
+    pkg = bench.load_pkg()
+    res = measure(pkg, torch, args.sites, args.reps)
+    if args.out:
+        os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
+        with open(args.out, "w") as f:
+            json.dump(res, f, indent=1)
+    best = max((r for r in res["rows"] if r["ok"]), key=lambda r: r["gsites"], default=None)
+    print(json.dumps({"best": best}))
+
+
+if __name__ == "__main__":
+    main()
