@@ -44,7 +44,9 @@ constexpr int kAaMatPitch = kAaMat + 4;           // 404 = 20 mod 32: categories
 // STRICT: every product and every sum rounded on its own, in the reference's order.  Products are packed
 // (FMUL2); the sums are scalar __fadd_rn on the two halves: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one
 // FFMA2 (seen in the SASS), which __fadd_rn forbids, and FADD issues on the other fp32 pipe anyway (97 vs 58
-// mul-add/clk/SM for FMUL2 + 2 FADD against FMUL2 + an unfused packed add, tools/microbench_sm.cu).
+// mul-add/clk/SM for FMUL2 + 2 FADD against FMUL2 + an unfused packed add, tools/microbench_sm.cu).  Moving 4 of
+// every 10 sums back to the FMA pipe as prod * 1.0 + acc (run-time 1.0) was tried and changed nothing: strict mode is
+// bound by the same shared-memory traffic as FMA mode plus twice the issue slots, not by the ALU pipe.
 // The leading "+0 +" of a sum is dropped in the branch products and kept in the back-transform: the argument of
 // plf_kernels.cuh (MathStrict) does not depend on the number of terms.
 struct AaStrict {

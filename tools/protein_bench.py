@@ -66,7 +66,7 @@ def measure(pkg, torch, n, reps, shapes=SHAPES, maths=(0, 1), seed=42, verbose=T
             ts = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(reps))
             mean = evs[0].elapsed_time(evs[-1]) / reps
             gs = n / (mean * 1e-3) / 1e9
-            row = {"variant": t, "threads": threads, "math": "fma" if math else "strict", "regs": info["regs"],
+            row = {"variant": t, "threads": info["threads"], "math": "fma" if math else "strict", "regs": info["regs"],
                    "smem_bytes": info["smem_bytes"], "ms_mean": mean, "ms_min": ts[0], "gsites": gs,
                    "gbs": gs * BYTES_PER_SITE, "frac_measured": gs * BYTES_PER_SITE / peak,
                    "tmuladd_per_s": gs * MULADD_PER_SITE / 1e3, "ok": ok}
