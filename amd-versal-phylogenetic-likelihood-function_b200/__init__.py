@@ -477,6 +477,56 @@ def kernel_info(variant: int = 0, math_mode: int = MATH_STRICT, threads: int = 0
     return {"regs": regs.value, "threads": thr.value, "blocks_per_sm": bps.value, "sms": sms.value}
 
 
+# ---- the packed buffers as files (host/plfb_file.h) ------------------------------------------
+PLFB_LEFT, PLFB_RIGHT, PLFB_OUT, PLFB_SCALER = 0, 1, 2, 3
+_PLFB_HEADER = "<4sIIIIIQQ24s"          # magic, version, kind, layout, states, categories, sites, payload bytes, reserved
+
+
+def plfb_payload_bytes(kind: int, layout: int, sites: int) -> int:
+    if kind == PLFB_LEFT:
+        return (80 + 16 * sites) * 4
+    if kind == PLFB_RIGHT:
+        return ((80 if layout == LAYOUT_COMB else 64) + 16 * sites) * 4
+    if kind == PLFB_OUT:
+        return 16 * sites * 4
+    if kind == PLFB_SCALER:
+        return sites
+    raise ValueError(f"unknown PLFB buffer kind {kind}")
+
+
+def save_plfb(path: str, kind: int, layout: int, sites: int, array) -> None:
+    """Write one packed buffer ([EV|P|CLV] input, CLV output or scaler bytes) as a PLFB file."""
+    import struct
+    a = np.ascontiguousarray(array, dtype=np.uint8 if kind == PLFB_SCALER else np.float32)
+    nbytes = plfb_payload_bytes(kind, layout, sites)
+    if a.nbytes != nbytes:
+        raise ValueError(f"buffer has {a.nbytes} bytes, kind {kind} / layout {layout} / {sites} sites needs {nbytes}")
+    with open(path, "wb") as f:
+        f.write(struct.pack(_PLFB_HEADER, b"PLFB", 1, kind, layout, 4, 4, sites, nbytes, b""))
+        f.write(a.tobytes())
+
+
+def load_plfb(path: str):
+    """Read and validate a PLFB file -> {"kind", "layout", "sites", "data" (float32 or uint8 array)}."""
+    import struct
+    with open(path, "rb") as f:
+        raw = f.read(64)
+        if len(raw) != 64:
+            raise ValueError(f"{path} is not a PLFB file")
+        magic, version, kind, layout, states, cats, sites, nbytes, _ = struct.unpack(_PLFB_HEADER, raw)
+        if magic != b"PLFB":
+            raise ValueError(f"{path} is not a PLFB file")
+        if version != 1 or states != 4 or cats != 4:
+            raise ValueError(f"{path}: unsupported version/states/categories {version}/{states}/{cats}")
+        if nbytes != plfb_payload_bytes(kind, layout, sites):
+            raise ValueError(f"{path}: payload size does not match kind/layout/sites")
+        payload = f.read(nbytes)
+    if len(payload) != nbytes:
+        raise ValueError(f"{path} is truncated")
+    data = np.frombuffer(payload, dtype=np.uint8 if kind == PLFB_SCALER else np.float32).copy()
+    return {"kind": kind, "layout": layout, "sites": sites, "data": data}
+
+
 # ---- general state count: the reference's STATES knob (4 = DNA, 20 = protein; README.md:36,67,202) ----
 STATES_DNA, STATES_PROTEIN = 4, 20
 

@@ -26,6 +26,7 @@
 
 #include "b200plf.h"
 #include "golden_plf.h"
+#include "plfb_file.h"
 #include "tb_info.h"
 #include "timing_report.h"
 
@@ -204,6 +205,29 @@ int main(int argc, char *argv[])
         alignmentsleft[j] = static_cast<float>(dis(gen) * scale);
         alignmentsright[j] = static_cast<float>(dis(gen));
     }
+    // PLF_LOAD_DIR=<dir>: take the stimulus from <dir>/left.plfb and <dir>/right.plfb (whole-run packed buffers,
+    // host/plfb_file.h) instead of the generator
+    if (const char *dir = std::getenv("PLF_LOAD_DIR")) {
+        try {
+            std::vector<char> lb, rb;
+            const PlfbHeader hl = read_plfb(std::string(dir) + "/left.plfb", lb);
+            const PlfbHeader hr = read_plfb(std::string(dir) + "/right.plfb", rb);
+            if (hl.kind != PLFB_LEFT || hr.kind != PLFB_RIGHT) die("PLF_LOAD_DIR: left.plfb / right.plfb hold the wrong buffer kind");
+            if (hl.sites != tb.alignment_sites || hr.sites != tb.alignment_sites)
+                die("PLF_LOAD_DIR: the files hold " + std::to_string(hl.sites) + " sites, the run asks for " +
+                    std::to_string(tb.alignment_sites));
+            const float *l = reinterpret_cast<const float *>(lb.data()), *r = reinterpret_cast<const float *>(rb.data());
+            std::copy(l, l + 16, ev);
+            std::copy(l + 16, l + 80, branchleft);
+            std::copy(l + 80, l + 80 + tb.elements_per_plf(), alignmentsleft.begin());
+            const size_t roff = hr.layout == 0 ? 16 : 0;
+            std::copy(r + roff, r + roff + 64, branchright);
+            std::copy(r + roff + 64, r + roff + 64 + tb.elements_per_plf(), alignmentsright.begin());
+            std::cout << "Stimulus loaded from " << dir << std::endl;
+        } catch (const std::exception &e) {
+            die(e.what());
+        }
+    }
     std::vector<int> wgt(tb.alignment_sites, 1);
 
     // results per call (pinned so the reads are asynchronous)
@@ -300,6 +324,28 @@ int main(int argc, char *argv[])
         execution_ms.end[i] = t.elapsed_ms();
     }
 #endif
+
+    // PLF_DUMP_DIR=<dir>: the whole-run packed inputs and the outputs of call 0 as PLFB files
+    if (const char *dir = std::getenv("PLF_DUMP_DIR")) {
+        try {
+            const size_t n = tb.alignment_sites, roff = tb.layout == PLF_LAYOUT_COMB ? 16 : 0;
+            std::vector<float> lb(80 + 16 * n), rb(roff + 64 + 16 * n);
+            std::copy(ev, ev + 16, lb.begin());
+            std::copy(branchleft, branchleft + 64, lb.begin() + 16);
+            std::copy(alignmentsleft.begin(), alignmentsleft.end(), lb.begin() + 80);
+            if (roff) std::copy(ev, ev + 16, rb.begin());
+            std::copy(branchright, branchright + 64, rb.begin() + roff);
+            std::copy(alignmentsright.begin(), alignmentsright.end(), rb.begin() + roff + 64);
+            const uint32_t lay = tb.layout == PLF_LAYOUT_COMB ? 0u : 1u;
+            write_plfb(std::string(dir) + "/left.plfb", PLFB_LEFT, lay, n, lb.data());
+            write_plfb(std::string(dir) + "/right.plfb", PLFB_RIGHT, lay, n, rb.data());
+            write_plfb(std::string(dir) + "/out.plfb", PLFB_OUT, lay, n, result[0]);
+            write_plfb(std::string(dir) + "/scaler.plfb", PLFB_SCALER, lay, n, scalerVector[0]);
+            std::cout << "Buffers written to " << dir << std::endl;
+        } catch (const std::exception &e) {
+            die(e.what());
+        }
+    }
 
     // ---- Check: CPU golden, exact comparison (host_mem.cpp:403-442) --------------------------------
     TimingData reference_ms(tb.plf_calls);

@@ -136,3 +136,71 @@ def test_host_stream_argument_errors(hosts):
     assert run(HOST_STREAM).returncode == 2
     r = run(HOST_STREAM, CFG_GEN, 0, 100, 1)
     assert r.returncode == 2 and "INPUT_SRC=mem" in r.stderr
+
+
+# ---- the packed buffers as files (host/plfb_file.h) -------------------------------------------
+def test_plfb_python_round_trip_and_validation(pkg, tmp_path):
+    rng = np.random.RandomState(1)
+    n = 37
+    left = rng.random_sample(80 + 16 * n).astype(np.float32)
+    right_sep = rng.random_sample(64 + 16 * n).astype(np.float32)
+    sc = rng.randint(0, 2, n).astype(np.uint8)
+    pkg.save_plfb(str(tmp_path / "l.plfb"), pkg.PLFB_LEFT, pkg.LAYOUT_COMB, n, left)
+    pkg.save_plfb(str(tmp_path / "r.plfb"), pkg.PLFB_RIGHT, pkg.LAYOUT_SEP, n, right_sep)
+    pkg.save_plfb(str(tmp_path / "s.plfb"), pkg.PLFB_SCALER, pkg.LAYOUT_COMB, n, sc)
+    got = pkg.load_plfb(str(tmp_path / "l.plfb"))
+    assert (got["kind"], got["layout"], got["sites"]) == (pkg.PLFB_LEFT, pkg.LAYOUT_COMB, n) and np.array_equal(got["data"], left)
+    got = pkg.load_plfb(str(tmp_path / "r.plfb"))
+    assert got["layout"] == pkg.LAYOUT_SEP and np.array_equal(got["data"], right_sep)
+    assert np.array_equal(pkg.load_plfb(str(tmp_path / "s.plfb"))["data"], sc)
+    assert os.path.getsize(tmp_path / "l.plfb") == 64 + left.nbytes
+    with pytest.raises(ValueError):                                   # Comb right buffer is 16 floats longer
+        pkg.save_plfb(str(tmp_path / "x.plfb"), pkg.PLFB_RIGHT, pkg.LAYOUT_COMB, n, right_sep)
+    raw = (tmp_path / "l.plfb").read_bytes()
+    (tmp_path / "trunc.plfb").write_bytes(raw[:-8])
+    with pytest.raises(ValueError, match="truncated"):
+        pkg.load_plfb(str(tmp_path / "trunc.plfb"))
+    (tmp_path / "bad.plfb").write_bytes(b"NOPE" + raw[4:])
+    with pytest.raises(ValueError, match="not a PLFB"):
+        pkg.load_plfb(str(tmp_path / "bad.plfb"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg,layout", [(CFG_COMB, 0), (CFG_SEP, 1)])
+def test_host_mem_dumps_buffers_the_oracle_reproduces(hosts, pkg, coracle, tmp_path, cfg, layout):
+    """PLF_DUMP_DIR: the files hold exactly the packed inputs and the outputs; the oracle's packed front end maps
+    one onto the other bit for bit."""
+    n = 4099
+    r = run(hosts[0], cfg, 0, n, 1, 3, env={"PLF_DUMP_DIR": str(tmp_path)})
+    assert r.returncode == 0 and "Buffers written" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+    f = {k: pkg.load_plfb(str(tmp_path / f"{k}.plfb")) for k in ("left", "right", "out", "scaler")}
+    assert all(v["sites"] == n and v["layout"] == layout for v in f.values())
+    o3, osc, oinc = coracle.newview_packed(f["left"]["data"], f["right"]["data"], layout, n)
+    assert np.array_equal(bits(f["out"]["data"].reshape(n, 16)), bits(o3))
+    assert np.array_equal(f["scaler"]["data"], osc) and oinc == (n + 3) // 4
+
+
+@pytest.mark.gpu
+def test_host_mem_loads_stimulus_from_files(hosts, pkg, coracle, tmp_path):
+    """PLF_LOAD_DIR: a stimulus written by the Python package (signed values, no designed scaler pattern) runs
+    through the host, passes its exact verification, and the dumped output equals the oracle's."""
+    n = 3001
+    rng = np.random.RandomState(8)
+    mag = np.repeat(10.0 ** rng.uniform(-9, 0, n), 16)                 # per-site magnitudes: some sites rescale, some do not
+    left = np.concatenate([rng.standard_normal(80), rng.standard_normal(16 * n) * mag]).astype(np.float32)
+    right = np.concatenate([left[:16], rng.standard_normal(64), rng.standard_normal(16 * n) * mag]).astype(np.float32)
+    src, dst = tmp_path / "in", tmp_path / "out"
+    src.mkdir()
+    dst.mkdir()
+    pkg.save_plfb(str(src / "left.plfb"), pkg.PLFB_LEFT, pkg.LAYOUT_COMB, n, left)
+    pkg.save_plfb(str(src / "right.plfb"), pkg.PLFB_RIGHT, pkg.LAYOUT_COMB, n, right)
+    r = run(hosts[0], CFG_COMB, 0, n, 1, 2, env={"PLF_LOAD_DIR": str(src), "PLF_DUMP_DIR": str(dst)})
+    assert r.returncode == 0 and "Test result: Passed" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+    o3, osc, oinc = coracle.newview_packed(left, right, 0, n)
+    assert 0 < oinc < n
+    assert np.array_equal(bits(pkg.load_plfb(str(dst / "out.plfb"))["data"].reshape(n, 16)), bits(o3))
+    assert np.array_equal(pkg.load_plfb(str(dst / "scaler.plfb"))["data"], osc)
+    assert f"scalerIncrement (call 0): {oinc}" in r.stdout
+    # a file with the wrong site count is refused
+    r = run(hosts[0], CFG_COMB, 0, n + 1, 1, 2, env={"PLF_LOAD_DIR": str(src)})
+    assert r.returncode == 2 and "sites" in r.stderr
