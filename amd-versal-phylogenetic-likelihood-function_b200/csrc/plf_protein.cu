@@ -23,7 +23,7 @@
 // every matrix word fetched from shared memory feeds T multiply-adds.  That ratio is what bounds the kernel: an
 // LDS.128 always costs 4 wavefronts of the 128 B/clk shared-memory pipe (512 B of register write-back, broadcast or
 // not -- ncu "L1 Wavefronts Shared Ideal"), so a site costs (300 + 10T)*4/(8T) wavefronts: 68 at T = 2, 42.5 at
-// T = 4, against 41 clk of fp32 pipe.  T = 4 (255 registers, 8 warps) is the FMA default, T = 2 (12 warps) the strict one.
+// T = 4, against 41 clk of fp32 pipe.  T = 4 (232 registers, 8 warps) is the FMA default, T = 2 (12 warps) the strict one.
 // Every warp runs its own pipeline on one tile buffer: lane 0 bulk-copies (TMA, cp.async.bulk + mbarrier) the x1
 // half of the NEXT tile as soon as the left-branch products are done and the x2 half after the right-branch
 // products -- no block-wide synchronisation after the prologue.  The three matrices live in shared memory (P
@@ -50,6 +50,10 @@ constexpr int kAaMatPitch = kAaMat + 4;           // 404 = 20 mod 32: categories
 // The leading "+0 +" of a sum is dropped in the branch products and kept in the back-transform: the argument of
 // plf_kernels.cuh (MathStrict) does not depend on the number of terms.
 struct AaStrict {
+    // The branch sums start from a zeroed accumulator, exactly like the reference (plf.cpp:32-33), so the chunk loop
+    // can stay rolled (half the code per tile body).  Unrolled code could drop that leading "+0 +" (bit-neutral by the
+    // argument in plf_kernels.cuh), but the smaller code is worth more than the 5 % of additions.
+    static constexpr bool kRolled = true;
     static __device__ __forceinline__ unsigned long long add_halves(unsigned long long acc, unsigned long long prod)
     {
         float a0, a1, p0, p1;
@@ -68,6 +72,10 @@ struct AaStrict {
     }
 };
 struct AaFma {
+    // fma(m, x, +0) == m * x up to the sign of a zero, which the tolerance mode does not pin: the accumulators start
+    // at zero and the chunk loop of the two branch stages stays rolled -- half the code per tile body (22 KB instead
+    // of 43 KB), aimed at the instruction-fetch stalls of the T = 4 kernel (ncu no_instruction 0.42 warps per issue).
+    static constexpr bool kRolled = true;
     static __device__ __forceinline__ unsigned long long first(unsigned long long m, unsigned long long xx) { return f2_mul(m, xx); }
     static __device__ __forceinline__ unsigned long long mac(unsigned long long m, unsigned long long xx, unsigned long long acc)
     {
@@ -85,7 +93,13 @@ __device__ __forceinline__ unsigned aa_branch(const float *__restrict__ xs, cons
 {
     const float4 *m4 = reinterpret_cast<const float4 *>(mat_t);
     unsigned dep = 0;
+    if (M::kRolled) {
 #pragma unroll
+        for (int t = 0; t < T; ++t)
+#pragma unroll
+            for (int kp = 0; kp < 10; ++kp) acc[t][kp] = 0ull;
+    }
+#pragma unroll(M::kRolled ? 1 : 5)
     for (int q = 0; q < 5; ++q) {
         float4 xv[T];
 #pragma unroll
@@ -108,7 +122,8 @@ __device__ __forceinline__ unsigned aa_branch(const float *__restrict__ xs, cons
                 const float x = j == 0 ? xv[t].x : j == 1 ? xv[t].y : j == 2 ? xv[t].z : xv[t].w;
                 const unsigned long long xx = f2_pack(x, x);
 #pragma unroll
-                for (int kp = 0; kp < 10; ++kp) acc[t][kp] = l == 0 ? M::first(m[kp], xx) : M::mac(m[kp], xx, acc[t][kp]);
+                for (int kp = 0; kp < 10; ++kp)
+                    acc[t][kp] = (!M::kRolled && l == 0) ? M::first(m[kp], xx) : M::mac(m[kp], xx, acc[t][kp]);
             }
         }
     }
@@ -121,23 +136,35 @@ __device__ __forceinline__ void aa_backtransform(const float *__restrict__ ev_s,
                                                  unsigned long long (&out)[T][10])
 {
     const float4 *e4 = reinterpret_cast<const float4 *>(ev_s);
+    if (M::kRolled) {
 #pragma unroll
-    for (int k = 0; k < kAaStates; ++k) {
-        unsigned long long e[10];
+        for (int t = 0; t < T; ++t)
 #pragma unroll
-        for (int i = 0; i < 5; ++i) {
-            const float4 v = e4[k * 5 + i];
-            e[2 * i] = f2_pack(v.x, v.y);
-            e[2 * i + 1] = f2_pack(v.z, v.w);
-        }
+            for (int lp = 0; lp < 10; ++lp) out[t][lp] = 0ull;
+    }
+    // k runs in pairs (one packed p register each); always unrolled: p is indexed by k and must stay in registers
 #pragma unroll
-        for (int t = 0; t < T; ++t) {
-            float lo, hi;
-            f2_unpack(p[t][k >> 1], lo, hi);
-            const float pk = (k & 1) ? hi : lo;
-            const unsigned long long pp = f2_pack(pk, pk);
+    for (int k2 = 0; k2 < kAaStates / 2; ++k2) {
 #pragma unroll
-            for (int lp = 0; lp < 10; ++lp) out[t][lp] = k == 0 ? M::first_final(e[lp], pp) : M::mac(e[lp], pp, out[t][lp]);
+        for (int h = 0; h < 2; ++h) {
+            const int k = 2 * k2 + h;
+            unsigned long long e[10];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                const float4 v = e4[k * 5 + i];
+                e[2 * i] = f2_pack(v.x, v.y);
+                e[2 * i + 1] = f2_pack(v.z, v.w);
+            }
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                float lo, hi;
+                f2_unpack(p[t][k2], lo, hi);
+                const float pk = h ? hi : lo;
+                const unsigned long long pp = f2_pack(pk, pk);
+#pragma unroll
+                for (int lp = 0; lp < 10; ++lp)
+                    out[t][lp] = (!M::kRolled && k == 0) ? M::first_final(e[lp], pp) : M::mac(e[lp], pp, out[t][lp]);
+            }
         }
     }
 }
@@ -273,7 +300,7 @@ plf_newview_aa(const __grid_constant__ AaMats mats, const float *__restrict__ x1
 // clk per SM, but only with immediate constant offsets (UR-indexed LDCU collapses to 1-13 per clk) and 16-32 warps
 // per SM to cover ~27 clk per LDCU per warp; a lane = site mapping then needs 640 B of staged CLV per site in flight
 // (four warps sharing a tile, block-wide barriers, four copies of the code), and end to end it reached 3.1 G sites/s
-// against 4.3 for the register-tile kernel below.  tools/microbench_const.cu, profiles/r01_protein.md.
+// against 4.3 (now 5.0) for the register-tile kernel below.  tools/microbench_const.cu, profiles/r01_protein.md.
 
 // ---- stimulus for S states: the recipe of host_mem.cpp:198-204 carried over (every 4th site has a tiny left child,
 // so exactly ceil(n/4) sites rescale).  The 20-state sums are 25x larger than the 4-state ones, hence 1e-14 instead
