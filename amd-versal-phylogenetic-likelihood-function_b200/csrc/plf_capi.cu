@@ -913,7 +913,14 @@ int plf_newview_stream(plf_ctx *ctx, const float *ev, const float *p_left, const
     if (!ev || !p_left || !p_right) return fail(ctx, PLF_ERR_INVALID, "stream: NULL matrix");
     if (n_sites && (!x1 || !x2 || !x3)) return fail(ctx, PLF_ERR_INVALID, "stream: NULL host CLV");
     PLF_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (chunk_sites == 0) chunk_sites = (size_t)2 << 20;            // 128 MiB per CLV chunk
+    if (chunk_sites == 0) {
+        // auto: about 16 chunks per call, between 256 Ki sites (16 MiB per CLV copy: still far above the per-copy
+        // overhead) and 2 Mi sites (128 MiB).  The pipeline drains for one chunk's D2H at the end of a call, so a
+        // 7 Mi-site call cut into four 2 Mi chunks ran at 2/3 of the PCIe rate; sixteen chunks lose 6 %.
+        chunk_sites = (n_sites + 15) / 16;
+        if (chunk_sites < ((size_t)256 << 10)) chunk_sites = (size_t)256 << 10;
+        if (chunk_sites > ((size_t)2 << 20)) chunk_sites = (size_t)2 << 20;
+    }
     if (chunk_sites > n_sites && n_sites > 0) chunk_sites = n_sites;
     chunk_sites = (chunk_sites + 255) & ~(size_t)255;
     constexpr int K = plf_ctx::kStreamSlots;

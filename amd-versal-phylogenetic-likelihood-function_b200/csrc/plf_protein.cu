@@ -300,7 +300,7 @@ plf_newview_aa(const __grid_constant__ AaMats mats, const float *__restrict__ x1
 // clk per SM, but only with immediate constant offsets (UR-indexed LDCU collapses to 1-13 per clk) and 16-32 warps
 // per SM to cover ~27 clk per LDCU per warp; a lane = site mapping then needs 640 B of staged CLV per site in flight
 // (four warps sharing a tile, block-wide barriers, four copies of the code), and end to end it reached 3.1 G sites/s
-// against 4.3 (now 5.0) for the register-tile kernel below.  tools/microbench_const.cu, profiles/r01_protein.md.
+// against 4.3 (now 5.0) for the register-tile kernel above.  tools/microbench_const.cu, profiles/r01_protein.md.
 
 // ---- stimulus for S states: the recipe of host_mem.cpp:198-204 carried over (every 4th site has a tiny left child,
 // so exactly ceil(n/4) sites rescale).  The 20-state sums are 25x larger than the 4-state ones, hence 1e-14 instead

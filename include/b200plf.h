@@ -141,7 +141,7 @@ int plf_instance_stream(plf_ctx *ctx, unsigned inst, void **stream);
 
 /* ---- streamed host path -------------------------------------------------
  * One newview over HOST-resident, unpacked arrays (the arguments of plf(), plf.h:1-5): the site range is
- * cut into chunks of chunk_sites (0 = 2 Mi) that flow through three device buffers on three streams, so
+ * cut into chunks of chunk_sites (0 = auto: n/16 clamped to 256 Ki .. 2 Mi sites) that flow through three device buffers on three streams, so
  * the H2D copy of one chunk, the kernel of the previous one and the D2H copy of the one before overlap.
  * The analogue of the reference's NO_INTERMEDIATE_RESULTS=1 round-trip mode (host_mem.cpp:327-382)
  * without the packing pass, and not limited by device memory.  Blocks until x3 / scaler are complete.
