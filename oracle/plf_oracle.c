@@ -203,8 +203,8 @@ int64_t plf_oracle_newview_mt(const float *x1, const float *x2, float *x3,
  * literal 4 that means "states" replaced by S (and 16 by S*S / 4*S): same accumulation order
  * (x3 zeroed, l-then-k for the branch sums, "x3[j*S+l] += p[k]*EV[S*k+l]" with k outer), same
  * threshold on all 4*S entries of the site.  Parity status: PINNED for S = 4 (tests assert it
- * is bit-identical to the reference's plf()); for S = 20 it is the same code path -- there is
- * no protein implementation in the reference to pin against.
+ * is bit-identical to the reference's plf()); PARITY UNPINNED for S = 20 -- the same code path,
+ * but there is no protein implementation, golden vector or test in the reference to pin against.
  * ------------------------------------------------------------------------------------------ */
 int64_t plf_oracle_newview_states(int S, const float *x1, const float *x2, float *x3,
                                   const float *ev, size_t n,

@@ -74,8 +74,8 @@ int64_t plf_oracle_newview_mt(const float *x1, const float *x2, float *x3,
 /* General state count S (4 = DNA, 20 = protein; the reference's STATES knob, README.md:36,67,202):
  * plf.cpp:19-65 with "4 states" replaced by S.  x1,x2,x3: float[n*4*S] [site][category][state];
  * ev: float[S*S] [k][l]; left/right: float[4*S*S] [j][k][l].  PINNED for S = 4 (bit-identical to
- * the reference's plf(), tests/test_oracle.py); S = 20 is the same code path (the reference has no
- * protein implementation).  Returns -1 for an unsupported S.                                      */
+ * the reference's plf(), tests/test_protein.py); PARITY UNPINNED for S = 20: the same code path, but
+ * the reference has no protein implementation to pin against.  Returns -1 for an unsupported S.   */
 int64_t plf_oracle_newview_states(int S, const float *x1, const float *x2, float *x3,
                                   const float *ev, size_t n,
                                   const float *left, const float *right,
