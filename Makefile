@@ -94,7 +94,7 @@ $(OBJDIR)/sel_dyn_fma.o: $(CSRC)/plf_sel_tma.cu $(KHDRS)
 $(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS)
 
-host: $(PKG)/host_mem.exe $(PKG)/host_gen.exe $(PKG)/host_stream.exe
+host: $(PKG)/host_mem.exe $(PKG)/host_gen.exe $(PKG)/host_stream.exe $(PKG)/host_states.exe
 
 $(PKG)/host_mem.exe: $(PKG)/host/host_mem.cpp $(PKG)/host/golden_plf.cpp $(wildcard $(PKG)/host/*.h) $(LIB)
 	$(CXX) $(HOSTFLAGS) -o $@ $(PKG)/host/host_mem.cpp $(PKG)/host/golden_plf.cpp \
@@ -107,6 +107,10 @@ $(PKG)/host_stream.exe: $(PKG)/host/host_stream.cpp $(PKG)/host/golden_plf.cpp $
 	$(CXX) $(HOSTFLAGS) -o $@ $(PKG)/host/host_stream.cpp $(PKG)/host/golden_plf.cpp \
 	    -L$(PKG) -lb200plf -Wl,-rpath,'$$ORIGIN'
 
+$(PKG)/host_states.exe: $(PKG)/host/host_states.cpp $(PKG)/host/golden_plf.cpp $(wildcard $(PKG)/host/*.h) $(LIB)
+	$(CXX) $(HOSTFLAGS) -o $@ $(PKG)/host/host_states.cpp $(PKG)/host/golden_plf.cpp \
+	    -L$(PKG) -lb200plf -Wl,-rpath,'$$ORIGIN'
+
 oracle:
 	$(MAKE) -C oracle all
 
@@ -114,7 +118,7 @@ run: host
 	./$(PKG)/host_$(INPUT_SRC).exe $(CONFIG) $(DEVICE) $(ALIGNMENTS) $(PLF_CALLS) $(INSTANCES_USED)
 
 clean:
-	rm -rf $(LIB) $(PKG)/build $(PKG)/host_mem.exe $(PKG)/host_gen.exe $(PKG)/host_stream.exe
+	rm -rf $(LIB) $(PKG)/build $(PKG)/host_mem.exe $(PKG)/host_gen.exe $(PKG)/host_stream.exe $(PKG)/host_states.exe
 	$(MAKE) -C oracle clean
 
 .PHONY: all lib host oracle run clean

@@ -118,6 +118,12 @@ PROTOTYPES = {
     "plf_generate_states_host": (_i, [_i, _vp, _vp, _sz, _sz, ctypes.c_uint64]),
     "plf_states_kernel_info": (_i, [_i, _i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(_sz),
                                     ctypes.POINTER(_i)]),
+    "plf_device_malloc": (_i, [_i, ctypes.POINTER(_vp), _sz]),
+    "plf_device_free": (_i, [_vp]),
+    "plf_memcpy_h2d": (_i, [_vp, _vp, _sz, _vp]),
+    "plf_memcpy_d2h": (_i, [_vp, _vp, _sz, _vp]),
+    "plf_memset_device": (_i, [_vp, _i, _sz, _vp]),
+    "plf_stream_sync": (_i, [_vp]),
     "plf_kernel_info": (_i, [_i, _i] + [ctypes.POINTER(_i)] * 4),
     "plf_launch_count": (ctypes.c_ulonglong, []),
 }

@@ -1065,6 +1065,51 @@ int plf_states_kernel_info(int states, int math_mode, int variant, int threads_p
     return PLF_OK;
 }
 
+int plf_device_malloc(int device, void **ptr, size_t bytes)
+{
+    if (!ptr) return fail(nullptr, PLF_ERR_INVALID, "NULL out-pointer");
+    *ptr = nullptr;
+    PLF_CUDA(nullptr, cudaSetDevice(device));
+    PLF_CUDA(nullptr, cudaMalloc(ptr, bytes ? bytes : 1));
+    return PLF_OK;
+}
+
+int plf_device_free(void *ptr)
+{
+    if (ptr) PLF_CUDA(nullptr, cudaFree(ptr));
+    return PLF_OK;
+}
+
+int plf_memcpy_h2d(void *dst_device, const void *src_host, size_t bytes, void *stream)
+{
+    if (bytes == 0) return PLF_OK;
+    if (!dst_device || !src_host) return fail(nullptr, PLF_ERR_INVALID, "memcpy: NULL pointer");
+    PLF_CUDA(nullptr, cudaMemcpyAsync(dst_device, src_host, bytes, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+    return PLF_OK;
+}
+
+int plf_memcpy_d2h(void *dst_host, const void *src_device, size_t bytes, void *stream)
+{
+    if (bytes == 0) return PLF_OK;
+    if (!dst_host || !src_device) return fail(nullptr, PLF_ERR_INVALID, "memcpy: NULL pointer");
+    PLF_CUDA(nullptr, cudaMemcpyAsync(dst_host, src_device, bytes, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+    return PLF_OK;
+}
+
+int plf_memset_device(void *dst_device, int value, size_t bytes, void *stream)
+{
+    if (bytes == 0) return PLF_OK;
+    if (!dst_device) return fail(nullptr, PLF_ERR_INVALID, "memset: NULL pointer");
+    PLF_CUDA(nullptr, cudaMemsetAsync(dst_device, value, bytes, static_cast<cudaStream_t>(stream)));
+    return PLF_OK;
+}
+
+int plf_stream_sync(void *stream)
+{
+    PLF_CUDA(nullptr, cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    return PLF_OK;
+}
+
 int plf_kernel_info(int variant, int math_mode, int *regs_per_thread, int *threads_per_block,
                     int *blocks_per_sm, int *num_sms)
 {

@@ -13,4 +13,10 @@ void golden_plf(const float *x1, const float *x2, float *x3, const float *ev, si
                 const float *left, const float *right, const int *wgt, long long &scaler_increment,
                 unsigned char *scaler = nullptr);
 
+// The same loop nest with the state count as a parameter (4 = DNA, 20 = AA): x1,x2,x3 float[n*4*S]
+// [site][category][state], ev float[S*S] [k][l], left/right float[4*S*S] [category][k][l].  S <= 32.
+void golden_plf_states(unsigned S, const float *x1, const float *x2, float *x3, const float *ev, size_t n,
+                       const float *left, const float *right, const int *wgt, long long &scaler_increment,
+                       unsigned char *scaler = nullptr);
+
 }  // namespace plfhost

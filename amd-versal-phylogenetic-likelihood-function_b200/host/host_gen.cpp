@@ -59,6 +59,7 @@ int main(int argc, char *argv[])
     } catch (const std::exception &e) {
         die(e.what());
     }
+    if (cfg.n_states != 4) die("STATES=" + cfg.states + " runs through host_states.exe (this host is the DNA drop-in)");
     if (cfg.input_src != PLF_INPUT_GEN) die("configuration '" + cfg.name + "' is INPUT_SRC=mem: use host_mem.exe");
     int device = 0;
     if (plf_device_from_string(argv[2], &device) != PLF_OK) die(plf_last_error(nullptr));

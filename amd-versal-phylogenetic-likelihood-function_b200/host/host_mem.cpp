@@ -111,6 +111,7 @@ int main(int argc, char *argv[])
     } catch (const std::exception &e) {
         die(e.what());
     }
+    if (cfg.n_states != 4) die("STATES=" + cfg.states + " runs through host_states.exe (this host is the DNA drop-in)");
     if (cfg.input_src != PLF_INPUT_MEM) die("configuration '" + cfg.name + "' is INPUT_SRC=gen: use host_gen.exe");
     const std::vector<int> devices = parse_devices(argv[2]);
 

@@ -22,7 +22,8 @@ struct AcceleratorConfig {
     std::string name;
     std::string aie_name, pl_name;
     unsigned num_accelerators = 9;    // NUM_ACCELERATORS
-    std::string states = "DNA";       // STATES
+    std::string states = "DNA";       // STATES: "DNA" (4 states) or "AA" (20 states, host_states.exe only)
+    unsigned n_states = 4;
     bool window = true;               // AIE_TYPE
     size_t window_size = 8192;        // WINDOW_SIZE (bytes per lane window; informational on GPU)
     int layout = PLF_LAYOUT_COMB;     // PLIO_LAYOUT
@@ -67,8 +68,15 @@ inline AcceleratorConfig parse_config(const std::string &arg)
     if (c.pl_name.find("window") != std::string::npos) c.window = true;
     else if (c.pl_name.find("stream") != std::string::npos) c.window = false;
     else throw std::runtime_error("PL name '" + c.pl_name + "' names neither window nor stream");
-    if (c.pl_name.find("DNA") == std::string::npos)
-        throw std::runtime_error("only STATES=DNA is implemented (got '" + c.pl_name + "')");
+    if (c.pl_name.find("DNA") != std::string::npos) {
+        c.states = "DNA";
+        c.n_states = 4;
+    } else if (c.pl_name.find("AA") != std::string::npos) {
+        c.states = "AA";
+        c.n_states = 20;
+    } else {
+        throw std::runtime_error("STATES must be DNA or AA (got '" + c.pl_name + "')");
+    }
 
     // AIE part: 128x<N>DNA<window<W>|stream><Comb|Sep>
     const size_t x = c.aie_name.find('x');

@@ -304,6 +304,18 @@ int plf_states_kernel_info(int states, int math_mode, int variant, int threads_p
                            int *regs_per_thread, int *block_threads, size_t *smem_bytes,
                            int *tile_sites);
 
+/* ---- device memory for callers that own their buffers ------------------------------------------
+ * The instance API keeps device memory inside the context (the xrt::bo role).  The *_device entry points
+ * (plf_newview_device, plf_newview_states_device, plf_evaluate_device) work on caller-owned device memory;
+ * a C/C++ host without its own CUDA code gets it here.  Copies are asynchronous on `stream` when the host
+ * side is pinned (plf_host_alloc); stream NULL = the default stream.                                  */
+int plf_device_malloc(int device, void **ptr, size_t bytes);
+int plf_device_free(void *ptr);
+int plf_memcpy_h2d(void *dst_device, const void *src_host, size_t bytes, void *stream);
+int plf_memcpy_d2h(void *dst_host, const void *src_device, size_t bytes, void *stream);
+int plf_memset_device(void *dst_device, int value, size_t bytes, void *stream);
+int plf_stream_sync(void *stream);
+
 /* Largest tile the library was compiled for, number of SMs etc. -- introspection for benches. */
 int plf_kernel_info(int variant, int math_mode, int *regs_per_thread, int *threads_per_block,
                     int *blocks_per_sm, int *num_sms);

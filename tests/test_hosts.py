@@ -204,3 +204,83 @@ def test_host_mem_loads_stimulus_from_files(hosts, pkg, coracle, tmp_path):
     # a file with the wrong site count is refused
     r = run(hosts[0], CFG_COMB, 0, n + 1, 1, 2, env={"PLF_LOAD_DIR": str(src)})
     assert r.returncode == 2 and "sites" in r.stderr
+
+
+# ---- STATES knob at the host level (host/host_states.cpp) --------------------------------------
+HOST_STATES = os.path.join(PKG_DIR, "host_states.exe")
+CFG_AA = "plf_128x9AAwindow8192Comb_memAAwindowComb"
+
+
+def test_host_golden_states_equals_oracle(tmp_path, coracle):
+    """host/golden_plf.cpp with the state count as a parameter == the general-S oracle (S = 4 and 20), and at
+    S = 4 == the DNA golden of the same file."""
+    shim = tmp_path / "shim.cpp"
+    shim.write_text('#include "golden_plf.h"\nextern "C" long long g(unsigned S,const float*a,const float*b,float*c,'
+                    'const float*e,unsigned long n,const float*l,const float*r,const int*w,unsigned char*s){long long i=0;'
+                    'plfhost::golden_plf_states(S,a,b,c,e,n,l,r,w,i,s);return i;}\n')
+    so = tmp_path / "libgolden_states.so"
+    subprocess.run(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-fPIC", "-shared",
+                    f"-I{os.path.join(PKG_DIR, 'host')}", "-o", str(so), str(shim),
+                    os.path.join(PKG_DIR, "host", "golden_plf.cpp")], check=True)
+    lib = ctypes.CDLL(str(so))
+    lib.g.restype = ctypes.c_longlong
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    for S, n in ((4, 5000), (20, 700)):
+        rng = np.random.RandomState(S)
+        x1 = (rng.standard_normal((n, 4 * S)) * 10.0 ** rng.uniform(-13, 1, (n, 1))).astype(np.float32)
+        x2 = (rng.standard_normal((n, 4 * S)) * 10.0 ** rng.uniform(-3, 1, (n, 1))).astype(np.float32)
+        ev, left, right = (rng.standard_normal(k).astype(np.float32) for k in (S * S, 4 * S * S, 4 * S * S))
+        wgt = rng.randint(0, 9, n).astype(np.int32)
+        out = np.empty((n, 4 * S), np.float32)
+        sc = np.empty(n, np.uint8)
+        inc = lib.g(S, p(x1), p(x2), p(out), p(ev), ctypes.c_ulong(n), p(left), p(right), p(wgt), p(sc))
+        o3, osc, oinc = coracle.newview_states(S, x1, x2, ev, left, right, wgt)
+        assert inc == oinc and 0 < oinc and np.array_equal(sc, osc) and np.array_equal(bits(out), bits(o3)), S
+        if S == 4:
+            d3, dsc, dinc = coracle.newview(x1, x2, ev, left, right, wgt)
+            assert np.array_equal(bits(out), bits(d3)) and inc == dinc
+
+
+def test_host_states_argument_errors(hosts):
+    assert run(HOST_STATES).returncode == 2
+    r = run(HOST_STATES, "plf_128x9RNAwindow8192Comb_memRNAwindowComb", 0, 100, 1)
+    assert r.returncode == 2 and "DNA or AA" in r.stderr
+    r = run(HOST_STATES, "plf_128x9AAwindow8192Comb_genAAwindowComb", 0, 100, 1)
+    assert r.returncode == 2 and "INPUT_SRC=mem" in r.stderr
+    for exe in (hosts[0], hosts[1], HOST_STREAM):                         # the DNA drop-ins refuse an AA configuration
+        r = run(exe, CFG_AA, 0, 100, 1, 1)
+        assert r.returncode == 2 and ("host_states" in r.stderr or "Usage" in r.stderr)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg,sites,calls", [(CFG_AA, 100, 1), (CFG_AA, 200003, 2), (CFG_COMB, 100000, 2)])
+def test_host_states_end_to_end(hosts, cfg, sites, calls):
+    r = run(HOST_STATES, cfg, 0, sites, calls)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "Test result: Passed (exact compare)" in r.stdout
+    assert f"scalerIncrement (last call): {(sites + 3) // 4}" in r.stdout
+    assert "G sites/s" in r.stdout
+
+
+@pytest.mark.gpu
+def test_host_states_fma_mode(hosts):
+    r = run(HOST_STATES, CFG_AA, 0, 50000, 1, env={"PLF_MATH": "fma"})
+    assert r.returncode == 0 and "Test result: Passed (1e-5 relative)" in r.stdout, r.stdout[-1500:]
+
+
+@pytest.mark.gpu
+def test_device_memory_helpers(pkg):
+    lib = pkg.load()
+    p = ctypes.c_void_p()
+    assert lib.plf_device_malloc(0, ctypes.byref(p), 4096) == 0 and p.value
+    src = np.arange(1024, dtype=np.float32)
+    dst = np.zeros(1024, np.float32)
+    assert lib.plf_memcpy_h2d(p, src.ctypes.data_as(ctypes.c_void_p), 4096, None) == 0
+    assert lib.plf_memcpy_d2h(dst.ctypes.data_as(ctypes.c_void_p), p, 4096, None) == 0
+    assert lib.plf_stream_sync(None) == 0 and np.array_equal(src, dst)
+    assert lib.plf_memset_device(p, 0, 4096, None) == 0
+    assert lib.plf_memcpy_d2h(dst.ctypes.data_as(ctypes.c_void_p), p, 4096, None) == 0
+    assert lib.plf_stream_sync(None) == 0 and not dst.any()
+    assert lib.plf_device_free(p) == 0
+    assert lib.plf_memcpy_h2d(None, src.ctypes.data_as(ctypes.c_void_p), 16, None) != 0
+    assert lib.plf_device_malloc(99, ctypes.byref(p), 16) != 0
