@@ -1,5 +1,7 @@
 // tools/microbench_sm.cu -- developer microbenchmark (not part of the product): per-SM issue rates that decide
-// the shape of the 20-state kernel.  One CTA per SM, clock64 around an unrolled loop, results per SM-clock.
+// the shape of the 20-state kernel.  One CTA per SM.  LDS.128 patterns are timed over the whole kernel with CUDA
+// events (and every loaded component is consumed: ptxas narrows the load otherwise -- an earlier version of this
+// file measured LDS.32 that way); the fp32 mixes use clock64 around an unrolled loop.
 //   nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o microbench_sm tools/microbench_sm.cu
 #include <cstdio>
 #include <cstdlib>
@@ -38,7 +40,10 @@ __global__ void lds_kernel(int mode, int iters, long long *cycles, float *sink)
     if (mode == 0) base = 0;
     else if (mode == 1) base = (lane & 3) * 101;
     else if (mode == 2) base = (lane & 3) * 100;
-    else base = lane;
+    else if (mode == 3) base = lane;
+    else if (mode == 4) base = lane & 3;            // 4 addresses inside one 64-byte segment
+    else if (mode == 5) base = lane & 7;            // 8 addresses inside one 128-byte row
+    else base = (lane & 1) * 101;                   // 2 addresses, distinct banks
     unsigned x = 0;
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(sm);
     long long t0 = clock64();
@@ -48,7 +53,7 @@ __global__ void lds_kernel(int mode, int iters, long long *cycles, float *sink)
             float4 v;
             const unsigned addr = sbase + (unsigned)(base + ((it + j) & 15) * 32) * 16u;
             asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-            x ^= __float_as_uint(v.x) ^ __float_as_uint(v.w);
+            x ^= __float_as_uint(v.x) ^ __float_as_uint(v.y) ^ __float_as_uint(v.z) ^ __float_as_uint(v.w);   // all four: ptxas narrows the load otherwise
         }
     }
     long long t1 = clock64();
@@ -146,17 +151,25 @@ int main()
     CK(cudaMalloc(&cyc, 1024 * sizeof(long long)));
     CK(cudaMalloc(&sink, 16));
     long long h[1024];
-    const int iters = 4096;
+    const int iters = 16384;
     CK(cudaFuncSetAttribute(lds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-    const char *lname[] = {"uniform", "4 addr distinct banks", "4 addr same banks", "32 distinct"};
-    for (int warps : {4, 8, 16}) {
-        for (int mode = 0; mode < 4; ++mode) {
-            lds_kernel<<<148, warps * 32, 65536>>>(mode, iters, cyc, sink);
-            CK(cudaDeviceSynchronize());
-            CK(cudaMemcpy(h, cyc, 148 * sizeof(long long), cudaMemcpyDeviceToHost));
-            double c = (double)h[0];
-            printf("LDS.128 %-24s warps=%2d : %.3f clk per warp-instruction per SM\n", lname[mode], warps,
-                   c / ((double)iters * 16 * warps));
+    const char *lname[] = {"uniform", "4 addr distinct banks", "4 addr same banks", "32 distinct", "4 addr in one 64 B", "8 addr in one 128 B", "2 addr distinct banks"};
+    // whole-kernel time (CUDA events): a single warp's clock64 span flatters whatever the arbiter favours
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    for (int warps : {8, 16}) {
+        for (int mode = 0; mode < 7; ++mode) {
+            float ms = 0;
+            for (int rep = 0; rep < 2; ++rep) {
+                cudaEventRecord(e0);
+                lds_kernel<<<148, warps * 32, 65536>>>(mode, iters, cyc, sink);
+                cudaEventRecord(e1);
+                CK(cudaDeviceSynchronize());
+                cudaEventElapsedTime(&ms, e0, e1);
+            }
+            printf("LDS.128 %-24s warps=%2d : %.3f clk per warp-instruction per SM (events, 1.965 GHz)\n", lname[mode], warps,
+                   ms * 1e-3 * 1.965e9 / ((double)iters * 16 * warps));
         }
     }
     float hinit[128];
@@ -164,7 +177,7 @@ int main()
     float *init;
     CK(cudaMalloc(&init, sizeof hinit));
     CK(cudaMemcpy(init, hinit, sizeof hinit, cudaMemcpyHostToDevice));
-    for (int warps : {4, 8, 12, 16, 32}) {
+    for (int warps : {4, 8, 12, 16}) {
         run_fma<0>("FFMA (scalar)", warps, iters, cyc, sink, init);
         run_fma<1>("FFMA2", warps, iters, cyc, sink, init);
         run_fma<6>("FFMA2 (scalar bcast operand)", warps, iters, cyc, sink, init);
