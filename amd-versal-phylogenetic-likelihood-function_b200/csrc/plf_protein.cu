@@ -13,7 +13,7 @@
 // Layouts: x1,x2,x3 float[n*80] [site][category j][state l]; left/right float[4*400] [j][k][l]; EV float[400] [k][l].
 //
 // Roofline.  961 algorithmic bytes and 4800 multiply-adds per site: 5.0 mul-add per byte, against a B200 balance
-// of 117 mul-add/clk/SM * 148 SMs * 1.965 GHz / 7.1 TB/s = 4.8 (tools/microbench_sm.cu, profiles/r01_protein.md).
+// of 116 mul-add/clk/SM * 148 SMs * 1.965 GHz / 7.1 TB/s = 4.8 (tools/microbench_sm.cu, profiles/r01_protein.md).
 // Unlike the DNA kernel this one sits ON the ridge: the fp32 pipe and HBM saturate together at about 7 G sites/s.
 // Tensor cores stay unused: tf32 inputs (10-bit mantissa) cannot meet the 1e-5 tolerance, and the 3xTF32 split
 // would need the operands re-packed through shared memory twice per site.
@@ -43,8 +43,8 @@ constexpr int kAaMatPitch = kAaMat + 4;           // 404 = 20 mod 32: categories
 
 // STRICT: every product and every sum rounded on its own, in the reference's order.  Products are packed
 // (FMUL2); the sums are scalar __fadd_rn on the two halves: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one
-// FFMA2 (seen in the SASS), which __fadd_rn forbids, and FADD issues on the other fp32 pipe anyway (97 vs 58
-// mul-add/clk/SM for FMUL2 + 2 FADD against FMUL2 + an unfused packed add, tools/microbench_sm.cu).  Moving 4 of
+// FFMA2 (seen in the SASS), which __fadd_rn forbids, and FADD issues on the other fp32 pipe anyway (97 mul-add/clk/SM for
+// FMUL2 + 2 FADD in tools/microbench_sm.cu, against 116 for FFMA2).  Moving 4 of
 // every 10 sums back to the FMA pipe as prod * 1.0 + acc (run-time 1.0) was tried and changed nothing: strict mode is
 // bound by the same shared-memory traffic as FMA mode plus twice the issue slots, not by the ALU pipe.
 // The leading "+0 +" of a sum is dropped in the branch products and kept in the back-transform: the argument of

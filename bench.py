@@ -473,7 +473,7 @@ def run_protein_arm(args):
             "roofline": {"bound": "hbm", "achieved": strict["gbs"], "peak": res["peak_gbs"], "unit": "GB/s",
                          "frac": strict["gbs"] / res["peak_gbs"], "traffic": None,
                          "note": "on the ridge: 4800 multiply-adds and 961 B per site; fp32 rate "
-                                 f"{strict['tmuladd_per_s']:.1f} T mul-add/s of ~34 T/s (117/clk/SM measured)"},
+                                 f"{strict['tmuladd_per_s']:.1f} T mul-add/s of ~34 T/s (116/clk/SM measured)"},
             "fma_mode": {"value": fma["gsites"] * 1e9, "gbs": fma["gbs"], "frac": fma["gbs"] / res["peak_gbs"],
                          "tmuladd_per_s": fma["tmuladd_per_s"], "kernel": {k: fma[k] for k in ("regs", "threads", "smem_bytes")}},
             "cpu_baseline": cpu, "e2e": None, "gpu_launches": 2 * (K + 2) + 1, "clocks": clk}

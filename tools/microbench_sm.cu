@@ -1,7 +1,7 @@
 // tools/microbench_sm.cu -- developer microbenchmark (not part of the product): per-SM issue rates that decide
 // the shape of the 20-state kernel.  One CTA per SM.  LDS.128 patterns are timed over the whole kernel with CUDA
 // events (and every loaded component is consumed: ptxas narrows the load otherwise -- an earlier version of this
-// file measured LDS.32 that way); the fp32 mixes use clock64 around an unrolled loop.
+// file measured LDS.32 that way); the fp32 mixes likewise.
 //   nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o microbench_sm tools/microbench_sm.cu
 #include <cstdio>
 #include <cstdlib>
@@ -137,11 +137,22 @@ __global__ void fma_kernel(int iters, long long *cycles, float *sink, const floa
 template <int MODE>
 void run_fma(const char *name, int warps, int iters, long long *cyc, float *sink, const float *init)
 {
-    long long h[148];
-    fma_kernel<MODE><<<148, warps * 32>>>(iters, cyc, sink, init);
-    CK(cudaDeviceSynchronize());
-    CK(cudaMemcpy(h, cyc, 148 * sizeof(long long), cudaMemcpyDeviceToHost));
-    printf("%-28s warps=%2d : %.2f mul-add/clk/SM\n", name, warps, (double)iters * 16 * warps * 32 * (MODE == 0 ? 1 : 2) / (double)h[0]);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float ms = 0;
+    for (int rep = 0; rep < 2; ++rep) {
+        cudaEventRecord(e0);
+        fma_kernel<MODE><<<148, warps * 32>>>(iters, cyc, sink, init);
+        cudaEventRecord(e1);
+        CK(cudaDeviceSynchronize());
+        cudaEventElapsedTime(&ms, e0, e1);
+    }
+    // whole-kernel time: one warp's clock64 span overstates the rate when the arbiter favours that warp
+    printf("%-28s warps=%2d : %.2f mul-add/clk/SM (events, 1.965 GHz)\n", name, warps,
+           (double)iters * 16 * warps * 32 * (MODE == 0 ? 1 : 2) / (ms * 1e-3 * 1.965e9));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
 }
 
 int main()
@@ -151,7 +162,7 @@ int main()
     CK(cudaMalloc(&cyc, 1024 * sizeof(long long)));
     CK(cudaMalloc(&sink, 16));
     long long h[1024];
-    const int iters = 16384;
+    const int iters = 16384;       // long enough that launch overhead is < 1 %
     CK(cudaFuncSetAttribute(lds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
     const char *lname[] = {"uniform", "4 addr distinct banks", "4 addr same banks", "32 distinct", "4 addr in one 64 B", "8 addr in one 128 B", "2 addr distinct banks"};
     // whole-kernel time (CUDA events): a single warp's clock64 span flatters whatever the arbiter favours
