@@ -41,47 +41,32 @@ constexpr int kAaSite = 4 * kAaStates;            // floats per site (320 B)
 constexpr int kAaMat = kAaStates * kAaStates;     // 400
 constexpr int kAaMatPitch = kAaMat + 4;           // 404 = 20 mod 32: categories land in disjoint 4-bank groups
 
-// STRICT: every product and every sum rounded on its own, in the reference's order.  Products are packed
-// (FMUL2); the sums are scalar __fadd_rn on the two halves: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one
-// FFMA2 (seen in the SASS), which __fadd_rn forbids, and FADD issues on the other fp32 pipe anyway (97 mul-add/clk/SM for
-// FMUL2 + 2 FADD in tools/microbench_sm.cu, against 116 for FFMA2).  Moving 4 of
-// every 10 sums back to the FMA pipe as prod * 1.0 + acc (run-time 1.0) was tried and changed nothing: strict mode is
-// bound by the same shared-memory traffic as FMA mode plus twice the issue slots, not by the ALU pipe.
-// The leading "+0 +" of a sum is dropped in the branch products and kept in the back-transform: the argument of
-// plf_kernels.cuh (MathStrict) does not depend on the number of terms.
+// Arithmetic policies: acc <- acc + m * x on packed pairs.  Every sum starts from a zeroed accumulator, exactly like
+// the reference (plf.cpp:25-27,32-33), so there is no special first term and the chunk loop of the two branch stages
+// stays rolled: half the code per tile body (22 KB instead of 43 KB), which removed the instruction-fetch stalls of
+// the T = 4 kernel (ncu no_instruction 0.42 warps per issue, +15 %).
+//
+// STRICT: every product and every sum rounded on its own, in the reference's order.  Products are packed (FMUL2);
+// the sums are scalar __fadd_rn on the two halves, because ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into one
+// FFMA2 (seen in the SASS) and __fadd_rn forbids that.  Three instructions per pair instead of one: strict mode is
+// bound by the fp32 pipe and the issue slots (tools/microbench_sm.cu: 97 multiply-adds per clk per SM for this mix
+// against 116 for FFMA2).  Moving 4 of every 10 sums to prod * 1.0 + acc (run-time 1.0, FFMA2) kept the bits and
+// changed nothing.
 struct AaStrict {
-    // The branch sums start from a zeroed accumulator, exactly like the reference (plf.cpp:32-33), so the chunk loop
-    // can stay rolled (half the code per tile body).  Unrolled code could drop that leading "+0 +" (bit-neutral by the
-    // argument in plf_kernels.cuh), but the smaller code is worth more than the 5 % of additions.
-    static constexpr bool kRolled = true;
-    static __device__ __forceinline__ unsigned long long add_halves(unsigned long long acc, unsigned long long prod)
+    static __device__ __forceinline__ unsigned long long mac(unsigned long long m, unsigned long long xx, unsigned long long acc)
     {
         float a0, a1, p0, p1;
         f2_unpack(acc, a0, a1);
-        f2_unpack(prod, p0, p1);
+        f2_unpack(f2_mul(m, xx), p0, p1);
         return f2_pack(__fadd_rn(a0, p0), __fadd_rn(a1, p1));
     }
-    static __device__ __forceinline__ unsigned long long first(unsigned long long m, unsigned long long xx) { return f2_mul(m, xx); }
-    static __device__ __forceinline__ unsigned long long mac(unsigned long long m, unsigned long long xx, unsigned long long acc)
-    {
-        return add_halves(acc, f2_mul(m, xx));
-    }
-    static __device__ __forceinline__ unsigned long long first_final(unsigned long long m, unsigned long long xx)
-    {
-        return add_halves(f2_pack(0.0f, 0.0f), f2_mul(m, xx));
-    }
 };
+// FMA: one FFMA2 per pair; fma(m, x, +0) == m * x up to the sign of a zero, which the tolerance mode does not pin.
 struct AaFma {
-    // fma(m, x, +0) == m * x up to the sign of a zero, which the tolerance mode does not pin: the accumulators start
-    // at zero and the chunk loop of the two branch stages stays rolled -- half the code per tile body (22 KB instead
-    // of 43 KB), aimed at the instruction-fetch stalls of the T = 4 kernel (ncu no_instruction 0.42 warps per issue).
-    static constexpr bool kRolled = true;
-    static __device__ __forceinline__ unsigned long long first(unsigned long long m, unsigned long long xx) { return f2_mul(m, xx); }
     static __device__ __forceinline__ unsigned long long mac(unsigned long long m, unsigned long long xx, unsigned long long acc)
     {
         return f2_fma(m, xx, acc);
     }
-    static __device__ __forceinline__ unsigned long long first_final(unsigned long long m, unsigned long long xx) { return f2_mul(m, xx); }
 };
 
 // acc[t][kp] = (a[2kp], a[2kp+1]) of site row t:  a[k] = sum_l x[l] * P[k][l], P^T in shared memory as [l][k].
@@ -93,13 +78,11 @@ __device__ __forceinline__ unsigned aa_branch(const float *__restrict__ xs, cons
 {
     const float4 *m4 = reinterpret_cast<const float4 *>(mat_t);
     unsigned dep = 0;
-    if (M::kRolled) {
 #pragma unroll
-        for (int t = 0; t < T; ++t)
+    for (int t = 0; t < T; ++t)
 #pragma unroll
-            for (int kp = 0; kp < 10; ++kp) acc[t][kp] = 0ull;
-    }
-#pragma unroll(M::kRolled ? 1 : 5)
+        for (int kp = 0; kp < 10; ++kp) acc[t][kp] = 0ull;      // bits of (+0.0f, +0.0f)
+#pragma unroll 1
     for (int q = 0; q < 5; ++q) {
         float4 xv[T];
 #pragma unroll
@@ -122,8 +105,7 @@ __device__ __forceinline__ unsigned aa_branch(const float *__restrict__ xs, cons
                 const float x = j == 0 ? xv[t].x : j == 1 ? xv[t].y : j == 2 ? xv[t].z : xv[t].w;
                 const unsigned long long xx = f2_pack(x, x);
 #pragma unroll
-                for (int kp = 0; kp < 10; ++kp)
-                    acc[t][kp] = (!M::kRolled && l == 0) ? M::first(m[kp], xx) : M::mac(m[kp], xx, acc[t][kp]);
+                for (int kp = 0; kp < 10; ++kp) acc[t][kp] = M::mac(m[kp], xx, acc[t][kp]);
             }
         }
     }
@@ -136,13 +118,11 @@ __device__ __forceinline__ void aa_backtransform(const float *__restrict__ ev_s,
                                                  unsigned long long (&out)[T][10])
 {
     const float4 *e4 = reinterpret_cast<const float4 *>(ev_s);
-    if (M::kRolled) {
 #pragma unroll
-        for (int t = 0; t < T; ++t)
+    for (int t = 0; t < T; ++t)
 #pragma unroll
-            for (int lp = 0; lp < 10; ++lp) out[t][lp] = 0ull;
-    }
-    // k runs in pairs (one packed p register each); always unrolled: p is indexed by k and must stay in registers
+        for (int lp = 0; lp < 10; ++lp) out[t][lp] = 0ull;
+    // k runs in pairs (one packed p register each); unrolled: p is indexed by k and must stay in registers
 #pragma unroll
     for (int k2 = 0; k2 < kAaStates / 2; ++k2) {
 #pragma unroll
@@ -162,8 +142,7 @@ __device__ __forceinline__ void aa_backtransform(const float *__restrict__ ev_s,
                 const float pk = h ? hi : lo;
                 const unsigned long long pp = f2_pack(pk, pk);
 #pragma unroll
-                for (int lp = 0; lp < 10; ++lp)
-                    out[t][lp] = (!M::kRolled && k == 0) ? M::first_final(e[lp], pp) : M::mac(e[lp], pp, out[t][lp]);
+                for (int lp = 0; lp < 10; ++lp) out[t][lp] = M::mac(e[lp], pp, out[t][lp]);
             }
         }
     }
