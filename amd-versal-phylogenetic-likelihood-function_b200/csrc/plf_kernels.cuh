@@ -212,18 +212,23 @@ __device__ __forceinline__ void load_cat_const(CatConst &c, const float *__restr
 
 // One (site, category): a = P_l x1, b = P_r x2 (plf.cpp:29-39), p = a.b (:41),
 // x3[l] = sum_k p[k] EV[k][l] (:45-50).  Returns true when all four |x3| < 2^-32 (:53-56).
+// Split in two so that a branch product can also come from a table (tip children, see the batch kernel):
+//   category_branch : a[k] = sum_l x[l] P[k][l]          category_finish : p = a.b, x3 = p EV, threshold test
 template <class M>
-__device__ __forceinline__ bool category_newview(const CatConst &c, const float4 &u, const float4 &v,
-                                                 float4 &o)
+__device__ __forceinline__ float4 category_branch(const float (&P)[16], const float4 &x)
 {
-    float a[4], b[4], p[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        a[k] = M::dot4_inner(u.x, u.y, u.z, u.w, c.L[4 * k], c.L[4 * k + 1], c.L[4 * k + 2], c.L[4 * k + 3]);
-        b[k] = M::dot4_inner(v.x, v.y, v.z, v.w, c.R[4 * k], c.R[4 * k + 1], c.R[4 * k + 2], c.R[4 * k + 3]);
-    }
-    M::mul_pair(a[0], a[1], b[0], b[1], p[0], p[1]);
-    M::mul_pair(a[2], a[3], b[2], b[3], p[2], p[3]);
+    return make_float4(M::dot4_inner(x.x, x.y, x.z, x.w, P[0], P[1], P[2], P[3]),
+                       M::dot4_inner(x.x, x.y, x.z, x.w, P[4], P[5], P[6], P[7]),
+                       M::dot4_inner(x.x, x.y, x.z, x.w, P[8], P[9], P[10], P[11]),
+                       M::dot4_inner(x.x, x.y, x.z, x.w, P[12], P[13], P[14], P[15]));
+}
+
+template <class M>
+__device__ __forceinline__ bool category_finish(const CatConst &c, const float4 &a, const float4 &b, float4 &o)
+{
+    float p[4];
+    M::mul_pair(a.x, a.y, b.x, b.y, p[0], p[1]);
+    M::mul_pair(a.z, a.w, b.z, b.w, p[2], p[3]);
     o.x = M::dot4_final(p[0], p[1], p[2], p[3], c.E[0], c.E[1], c.E[2], c.E[3]);
     o.y = M::dot4_final(p[0], p[1], p[2], p[3], c.E[4], c.E[5], c.E[6], c.E[7]);
     o.z = M::dot4_final(p[0], p[1], p[2], p[3], c.E[8], c.E[9], c.E[10], c.E[11]);
@@ -231,6 +236,13 @@ __device__ __forceinline__ bool category_newview(const CatConst &c, const float4
     // NaN compares false, exactly like ABS(x) < minlikelihood on the CPU.
     return (fabsf(o.x) < kMinLikelihood) & (fabsf(o.y) < kMinLikelihood) &
            (fabsf(o.z) < kMinLikelihood) & (fabsf(o.w) < kMinLikelihood);
+}
+
+template <class M>
+__device__ __forceinline__ bool category_newview(const CatConst &c, const float4 &u, const float4 &v,
+                                                 float4 &o)
+{
+    return category_finish<M>(c, category_branch<M>(c.L, u), category_branch<M>(c.R, v), o);
 }
 
 __device__ __forceinline__ void rescale(float4 &o)
@@ -744,6 +756,9 @@ plf_newview_tma_dyn(const float4 *__restrict__ x1, const float4 *__restrict__ x2
 // late under a saturated DRAM queue and stall the warp that issued them.
 // Count vectors must be 16-byte aligned and padded to a multiple of 4 ints.
 // ---------------------------------------------------------------------------------------------
+struct cuda_true { static constexpr bool value = true; };
+struct cuda_false { static constexpr bool value = false; };
+
 struct BatchOp {
     const float4 *x1;
     const float4 *x2;
@@ -766,7 +781,8 @@ struct BatchOp {
 template <int U, int WARPS, int DEPTH>
 constexpr size_t batch_smem_bytes()
 {
-    return tma_smem_bytes<U, WARPS, DEPTH>() + (size_t)DEPTH * (WARPS * 8 * U) * (sizeof(int) * 2 + 2) + 256;   // tma_smem_bytes already holds the barriers + stage indices
+    return tma_smem_bytes<U, WARPS, DEPTH>() + (size_t)DEPTH * (WARPS * 8 * U) * (sizeof(int) * 2 + 2) + 256 +   // tma_smem_bytes already holds the barriers + stage indices
+           (size_t)WARPS * 2 * 64 * sizeof(float4);                                                               // per-warp tip product tables
 }
 
 template <class M, int U, int WARPS, int DEPTH, int MINB>
@@ -789,7 +805,8 @@ plf_newview_batch(const BatchOp *__restrict__ ops, int n_ops, size_t n,
     unsigned char *k1s = reinterpret_cast<unsigned char *>(c2 + (size_t)DEPTH * STAGE);   // [DEPTH][STAGE] tip codes
     unsigned char *k2s = k1s + (size_t)DEPTH * STAGE;
     float4 *tv = reinterpret_cast<float4 *>(k2s + (size_t)DEPTH * STAGE);                 // [16] tip vector table
-    uint64_t *full = reinterpret_cast<uint64_t *>(tv + 16);
+    float4 *tabs = tv + 16;                                                               // [WARPS][2][64] tip product tables
+    uint64_t *full = reinterpret_cast<uint64_t *>(tabs + (size_t)WARPS * 128);
     uint64_t *empty = full + DEPTH;
     volatile uint32_t *stage_of = reinterpret_cast<volatile uint32_t *>(empty + DEPTH);   // [DEPTH] global stage index
 
@@ -877,6 +894,7 @@ plf_newview_batch(const BatchOp *__restrict__ ops, int n_ops, size_t n,
         const int cat = lane & 3;
         const int site_in_row = lane >> 2;
         const uint32_t tile_off = warp * (TILE * 4) + lane;
+        float4 *my_tab = tabs + warp * 128;
         CatConst c;
         BatchOp o;
         uint32_t cur_op = 0xffffffffu, op_base = 0;
@@ -894,59 +912,108 @@ plf_newview_batch(const BatchOp *__restrict__ ops, int n_ops, size_t n,
                 st = g - op_base;
                 o = ops[cur_op];
                 load_cat_const(c, o.ev, o.pl, o.pr, cat, 0);
+                // Tip children: the branch product a[k] = sum_l tipvec[code][l] P[k][l] depends only on (code, category),
+                // so it is computed ONCE per op for the 16 codes (RAxML's umpX tables) with the very function the
+                // per-site path uses -- same inputs, same bits -- and a tip child then costs one table read per site
+                // instead of a 16-byte CLV read and 28 fp32 operations.  Tables are private to the warp (no block
+                // barrier); rows are stored at code ^ (code >> 1) so that the four nucleotide codes 1, 2, 4, 8 fall on
+                // both halves of the banks.
+                if (o.tip1 || o.tip2) {
+                    __syncwarp();                              // every lane is done with the previous op's tables
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int code = 8 * h + site_in_row;
+                        const int row = code ^ (code >> 1);
+                        if (o.tip1) my_tab[row * 4 + cat] = category_branch<M>(c.L, tv[code]);
+                        if (o.tip2) my_tab[64 + row * 4 + cat] = category_branch<M>(c.R, tv[code]);
+                    }
+                    __syncwarp();
+                }
             }
             const size_t s0 = (size_t)st * STAGE + (size_t)warp * TILE;   // first site of this warp's tile
             const size_t s_lane = s0 + lane;                              // the site whose count this lane owns
             const bool complete = st < full_stages;
             const bool lane_live = lane < TILE && (complete || s_lane < n);
-            float4 a[U], b[U], r[U];
-            unsigned ballots[U];
-            const uint32_t code_off = slot * STAGE + warp * TILE + site_in_row;
+            // The rest of the stage, compiled once per (child 1 is a tip, child 2 is a tip): o.tip1 / o.tip2 are
+            // warp-uniform run-time values, and left as such the compiler predicates both sides -- every dense stage
+            // then also executes the tip path's byte and table reads, and the other way round.
+            auto stage_body = [&](auto tip1_c, auto tip2_c) {
+                constexpr bool TIP1 = decltype(tip1_c)::value, TIP2 = decltype(tip2_c)::value;
+                float4 a[U], b[U], r[U];
+                unsigned ballots[U];
+                const uint32_t code_off = slot * STAGE + warp * TILE + site_in_row;
+                // a[u] / b[u]: the child's CLV slice, or for a tip child already its branch product from the table
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                a[u] = o.tip1 ? tv[k1s[code_off + 8 * u] & 15] : t1[32 * u];
-                b[u] = o.tip2 ? tv[k2s[code_off + 8 * u] & 15] : t2[32 * u];
-            }
-            int cnt = 0;
-            if (lane_live) {
-                if (o.cnt1) cnt = c1[slot * STAGE + warp * TILE + lane];
-                if (o.cnt2) cnt += c2[slot * STAGE + warp * TILE + lane];
-            }
-            unsigned dep = (unsigned)cnt ^ g;
+                for (int u = 0; u < U; ++u) {
+                    if constexpr (TIP1) {
+                        const unsigned code = k1s[code_off + 8 * u] & 15u;
+                        a[u] = my_tab[((code ^ (code >> 1)) << 2) + cat];
+                    } else {
+                        a[u] = t1[32 * u];
+                    }
+                    if constexpr (TIP2) {
+                        const unsigned code = k2s[code_off + 8 * u] & 15u;
+                        b[u] = my_tab[64 + ((code ^ (code >> 1)) << 2) + cat];
+                    } else {
+                        b[u] = t2[32 * u];
+                    }
+                }
+                int cnt = 0;
+                if (lane_live) {
+                    if (o.cnt1) cnt = c1[slot * STAGE + warp * TILE + lane];
+                    if (o.cnt2) cnt += c2[slot * STAGE + warp * TILE + lane];
+                }
+                unsigned dep = (unsigned)cnt ^ g;
 #pragma unroll
-            for (int u = 0; u < U; ++u) dep ^= __float_as_uint(a[u].x) ^ __float_as_uint(b[u].w);
-            mbar_release_slot(&empty[slot], lane, dep);
+                for (int u = 0; u < U; ++u) dep ^= __float_as_uint(a[u].x) ^ __float_as_uint(b[u].w);
+                mbar_release_slot(&empty[slot], lane, dep);
+                float4 *out = o.x3 + s0 * 4 + lane;
+                auto finish = [&](int u) {
+                    float4 av, bv;
+                    if constexpr (TIP1) av = a[u]; else av = category_branch<M>(c.L, a[u]);
+                    if constexpr (TIP2) bv = b[u]; else bv = category_branch<M>(c.R, b[u]);
+                    return category_finish<M>(c, av, bv, r[u]);
+                };
+                if (complete) {                    // no bounds predicates on the hot path
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const bool small = finish(u);
+                        ballots[u] = __ballot_sync(0xffffffffu, small);
+                        if (nibble_all(ballots[u], site_in_row)) rescale(r[u]);
+                        st_stream(out + 32 * u, r[u]);
+                    }
+                } else {                           // the single ragged stage at the end of an op's site range
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const bool live = s0 + 8 * u + site_in_row < n;
+                        const bool small = finish(u);
+                        ballots[u] = __ballot_sync(0xffffffffu, small && live);
+                        if (nibble_all(ballots[u], site_in_row)) rescale(r[u]);
+                        if (live) st_stream(out + 32 * u, r[u]);
+                    }
+                }
+                if (lane_live) {
+                    unsigned bal = ballots[0];
+#pragma unroll
+                    for (int u = 1; u < U; ++u) bal = (lane >> 3) == u ? ballots[u] : bal;
+                    const bool scaled = nibble_all(bal, lane & 7);
+                    if (o.scaler) o.scaler[s_lane] = scaled ? 1 : 0;
+                    if (o.cnt3) o.cnt3[s_lane] = cnt + (scaled ? 1 : 0);
+                    if (scaled) my_sum += wgt ? (unsigned long long)(long long)wgt[s_lane] : 1ull;
+                }
+            };
+            using yes = cuda_true;
+            using no = cuda_false;
+            if (o.tip1) {
+                if (o.tip2) stage_body(yes{}, yes{});
+                else stage_body(yes{}, no{});
+            } else {
+                if (o.tip2) stage_body(no{}, yes{});
+                else stage_body(no{}, no{});
+            }
             if (++slot == DEPTH) {
                 slot = 0;
                 phase ^= 1u;
-            }
-            float4 *out = o.x3 + s0 * 4 + lane;
-            if (complete) {
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    bool small = category_newview<M>(c, a[u], b[u], r[u]);
-                    ballots[u] = __ballot_sync(0xffffffffu, small);
-                    if (nibble_all(ballots[u], site_in_row)) rescale(r[u]);
-                    st_stream(out + 32 * u, r[u]);
-                }
-            } else {
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const bool live = s0 + 8 * u + site_in_row < n;
-                    bool small = category_newview<M>(c, a[u], b[u], r[u]);
-                    ballots[u] = __ballot_sync(0xffffffffu, small && live);
-                    if (nibble_all(ballots[u], site_in_row)) rescale(r[u]);
-                    if (live) st_stream(out + 32 * u, r[u]);
-                }
-            }
-            if (lane_live) {
-                unsigned bal = ballots[0];
-#pragma unroll
-                for (int u = 1; u < U; ++u) bal = (lane >> 3) == u ? ballots[u] : bal;
-                const bool scaled = nibble_all(bal, lane & 7);
-                if (o.scaler) o.scaler[s_lane] = scaled ? 1 : 0;
-                if (o.cnt3) o.cnt3[s_lane] = cnt + (scaled ? 1 : 0);
-                if (scaled) my_sum += wgt ? (unsigned long long)(long long)wgt[s_lane] : 1ull;
             }
         }
     }
