@@ -95,14 +95,22 @@ template <class M, class M15>
 BatchSel batch_sel(int u)
 {
     // u = 1: 16 consumer warps, 128-site stages x 4;  u = 2: 16 consumer warps, 256-site stages x 3;
-    // u = 3 (default for all but tiny levels): 15 consumer warps, 240-site stages x 3.  Registers are
-    // allocated per 4 warps: 16 + 1 warps are charged as 20 (96 registers per thread, the batch kernel
-    // spills), 15 + 1 get 128 -- room for the packed strict arithmetic; 2-3 % faster traversals.
+    // u = 3: 15 consumer warps, 240-site stages x 3;  u = 4: 11 consumer warps, 4 rows per warp, 352-site stages x 2;
+    // u = 0 (default): 11 consumer warps, 4 rows per warp, 352-site stages x 3.
+    // Registers are allocated per 4 warps: 16 + 1 warps are charged as 20 (96 registers per thread: scalar strict
+    // arithmetic, the packed one spills), 15 + 1 get 128, 11 + 1 get 170 -- room for four rows per warp in flight.
+    // Four rows per warp and stage spread the per-stage bookkeeping (barrier waits, op check, addresses, the count and
+    // scaler stores) over twice the sites: against u = 3 the 1024-tip traversal is 5 % faster with dense tips, 12 %
+    // with compressed tips, 13 % for small levels (256 tips x 8192 sites), profiles/r01_tree.md.
     if (u == 1)
         return {plf::plf_newview_batch<M, 1, 16, 4, 1>, 17 * 32, plf::batch_smem_bytes<1, 16, 4>(), 128};
     if (u == 2)
         return {plf::plf_newview_batch<M, 2, 16, 3, 1>, 17 * 32, plf::batch_smem_bytes<2, 16, 3>(), 256};
-    return {plf::plf_newview_batch<M15, 2, 15, 3, 1>, 16 * 32, plf::batch_smem_bytes<2, 15, 3>(), 240};
+    if (u == 3)
+        return {plf::plf_newview_batch<M15, 2, 15, 3, 1>, 16 * 32, plf::batch_smem_bytes<2, 15, 3>(), 240};
+    if (u == 4)
+        return {plf::plf_newview_batch<M15, 4, 11, 2, 1>, 12 * 32, plf::batch_smem_bytes<4, 11, 2>(), 352};
+    return {plf::plf_newview_batch<M15, 4, 11, 3, 1>, 12 * 32, plf::batch_smem_bytes<4, 11, 3>(), 352};
 }
 
 BatchSel pick_batch(int math, int u)
@@ -180,9 +188,9 @@ int build_graph(plf_tree *t)
 {
     int u = t->tune_u;
     if (u == 0) {
-        // 240-site stages unless even the widest level would leave most SMs with < 4 stages
+        // 352-site stages (4 rows per warp) unless even the widest level would leave most SMs with < 4 stages
         const size_t widest = t->levels.empty() ? 1 : t->levels[0].size();
-        u = ((t->n_sites + 239) / 240) * widest >= (size_t)t->num_sms * 4 ? 3 : 1;
+        u = ((t->n_sites + 351) / 352) * widest >= (size_t)t->num_sms * 4 ? 0 : 1;
     }
     const BatchSel k = pick_batch(t->math, u);
     TREE_CUDA(t, cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.smem));
@@ -395,7 +403,7 @@ int plf_tree_set_math(plf_tree *t, int math_mode)
 int plf_tree_set_tuning(plf_tree *t, int u, int chunk)
 {
     if (!t) return tfail(nullptr, PLF_ERR_INVALID, "NULL tree");
-    if (u < 0 || u > 3) return tfail(t, PLF_ERR_INVALID, "tuning u must be 0..3");
+    if (u < 0 || u > 4) return tfail(t, PLF_ERR_INVALID, "tuning u must be 0..4");
     if (chunk < 0) return tfail(t, PLF_ERR_INVALID, "chunk must be >= 0");
     t->tune_u = u;
     t->tune_chunk = chunk;

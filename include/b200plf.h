@@ -234,7 +234,8 @@ int plf_tree_write_tip_vector(plf_tree *tree, const float *tip_vector);
 int plf_tree_destroy(plf_tree *tree);
 const char *plf_tree_last_error(const plf_tree *tree);
 int plf_tree_set_math(plf_tree *tree, int math_mode);
-/* u: 0 = automatic, else the batch kernel shape (1: 128-site stages, 2: 256-site, 3: 240-site stages).
+/* u: 0 = automatic (352-site stages, 4 rows per warp, 3 deep), else the batch kernel shape (1: 128-site stages,
+ * 2: 256-site, 3: 240-site stages with 2 rows per warp, 4: 352-site stages 2 deep).
  * chunk: 0 = automatic, else consecutive stages dealt to a CTA at a time (1 = fully interleaved). */
 int plf_tree_set_tuning(plf_tree *tree, int u, int chunk);
 /* Device pointer of a tip CLV (n_sites*16 floats) for callers that produce tips on the device. */

@@ -45,7 +45,7 @@ def test_tree_oracle_counts_are_sums_of_bytes(coracle):
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape,n_tips,n", [("balanced", 64, 3001), ("random", 33, 1000), ("balanced", 2, 129),
                                              ("random", 257, 517), ("caterpillar", 12, 4096)])
-@pytest.mark.parametrize("u,chunk", [(0, 0), (1, 1), (2, 1), (2, 3), (1, 1000), (3, 0), (3, 7)])
+@pytest.mark.parametrize("u,chunk", [(0, 0), (1, 1), (2, 1), (2, 3), (1, 1000), (3, 0), (3, 7), (4, 0), (4, 2), (0, 5)])
 def test_tree_traversal_matches_oracle(pkg, coracle, shape, n_tips, n, u, chunk):
     if shape == "balanced":
         left, right = pkg.balanced_tree(n_tips)
@@ -127,7 +127,7 @@ def test_tree_stress_single_busy_cta_with_poisoned_memory(pkg, coracle):
         del poison
         torch.cuda.empty_cache()
         for left, right, n_tips, n, tips, ev, pl, pr, wgt, (o_root, o_cnt, o_total) in cases:
-            for u in (1, 2, 3):
+            for u in (1, 2, 3, 4, 0):
                 with pkg.Tree(left, right, n) as t:
                     t.set_tuning(u, 1000)
                     for i in range(n_tips):
@@ -150,7 +150,7 @@ def expand_tip_codes(codes, tip_vector):
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape,n_tips,n", [("balanced", 64, 3001), ("random", 33, 1000), ("balanced", 2, 129),
                                              ("random", 257, 517), ("caterpillar", 12, 4099)])
-@pytest.mark.parametrize("u,chunk", [(0, 0), (1, 1), (2, 3), (1, 1000), (3, 5)])
+@pytest.mark.parametrize("u,chunk", [(0, 0), (1, 1), (2, 3), (1, 1000), (3, 5), (4, 1)])
 def test_tree_with_compressed_tips_matches_dense_oracle(pkg, coracle, shape, n_tips, n, u, chunk):
     """tips stored as one state code per site + a 16x4 tip-vector table give exactly the
     traversal of the expanded dense tips (tip-tip, tip-inner and inner-inner nodes all occur)."""
