@@ -253,3 +253,28 @@ def test_protein_rejects_bad_arguments(pkg, gpu):
     assert info["tile_sites"] == 16 and info["threads"] == 384 and info["smem_bytes"] <= 227 * 1024
     info = pkg.states_kernel_info(S, pkg.MATH_FMA)
     assert info["tile_sites"] == 32 and info["threads"] == 256 and info["regs"] <= 255
+
+
+# ---------------------------------------------------------------------------------------------
+# regression fixtures (tests/golden/aa_cases.npz, made by tests/golden/make_golden_states.py; NOT reference-derived)
+# ---------------------------------------------------------------------------------------------
+def aa_cases():
+    import os
+    from conftest import GOLDEN
+    d = np.load(os.path.join(GOLDEN, "aa_cases.npz"))
+    for name in sorted({k.split("__")[0] for k in d.files}):
+        yield name, {k.split("__")[1]: d[k] for k in d.files if k.startswith(name + "__")}
+
+
+def test_states_oracle_reproduces_committed_fixtures(coracle):
+    for name, c in aa_cases():
+        x3, sc, inc = coracle.newview_states(S, c["x1"], c["x2"], c["ev"], c["left"], c["right"], c.get("wgt"))
+        assert np.array_equal(bits(x3), bits(c["x3"])) and np.array_equal(sc, c["scaler"]) and inc == int(c["inc"]), name
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", SHAPES)
+def test_protein_matches_committed_fixtures(pkg, gpu, shape):
+    for name, c in aa_cases():
+        g3, gsc, ginc = run_states(pkg, gpu, S, c["ev"], c["left"], c["right"], c["x1"], c["x2"], wgt=c.get("wgt"), shape=shape)
+        assert np.array_equal(bits(g3), bits(c["x3"])) and np.array_equal(gsc, c["scaler"]) and ginc == int(c["inc"]), name
