@@ -28,7 +28,7 @@
 // half of the NEXT tile as soon as the left-branch products are done and the x2 half after the right-branch
 // products -- no block-wide synchronisation after the prologue.  The three matrices live in shared memory (P
 // transposed to [l][k], categories 404 floats apart so that the four categories of a quarter-warp hit disjoint bank
-// groups).  Arithmetic is packed fp32x2 (FFMA2; FMUL2 + scalar FADD on the other fp32 pipe in strict mode): pairs
+// groups).  Arithmetic is packed fp32x2 (FFMA2; FMUL2 + scalar FADD in strict mode): pairs
 // run over k (branch products) and over l (back-transform), the per-site scalar enters as the broadcast operand.
 #include "../../include/b200plf.h"
 #include "plf_kernels.cuh"
