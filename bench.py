@@ -17,6 +17,9 @@ e2e        the same sites through the reference-facing host API (plf_write_left/
 roofline   193 algorithmic bytes/site x sites per launch / mean launch time, against the measured
            HBM copy bandwidth in MEASURED_PEAKS.json.
 cpu_baseline  oracle/_ref (the reference's plf.cpp compiled in place) on all host cores.
+
+Side workloads (not the headline line): --workload cfg2 (1 Mi sites, one instance; --buffer-sets 1 for the
+"same buffers" variant) and --workload protein (the 20-state kernel, single GPU, its own CPU baseline).
 """
 from __future__ import annotations
 
