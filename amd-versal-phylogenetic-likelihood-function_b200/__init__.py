@@ -33,6 +33,7 @@ INPUT_MEM, INPUT_GEN = 0, 1
 MATH_STRICT, MATH_FMA = 0, 1
 GEN_WRITE, GEN_DISCARD = 0, 1
 MARK_BEGIN, MARK_T1, MARK_T2, MARK_END = 0, 1, 2, 3
+LAUNCH_NO_PDL, LAUNCH_FENCED_RELEASE, LAUNCH_DEP_RELEASE = 1, 2, 4
 
 # Algorithmic HBM bytes per site: read 64 (x1) + 64 (x2), write 64 (x3) + 1 scaler byte.
 BYTES_PER_SITE = 193
@@ -47,7 +48,7 @@ class PlfError(RuntimeError):
 class LaunchOpts(ctypes.Structure):
     _fields_ = [("math_mode", ctypes.c_int), ("variant", ctypes.c_int),
                 ("threads_per_block", ctypes.c_int), ("blocks_per_sm", ctypes.c_int),
-                ("ev_per_category", ctypes.c_int)]
+                ("ev_per_category", ctypes.c_int), ("flags", ctypes.c_int)]
 
 
 _vp = ctypes.c_void_p
@@ -126,6 +127,7 @@ PROTOTYPES = {
     "plf_stream_sync": (_i, [_vp]),
     "plf_kernel_info": (_i, [_i, _i] + [ctypes.POINTER(_i)] * 4),
     "plf_launch_count": (ctypes.c_ulonglong, []),
+    "plf_set_release_mode": (_i, [_i]),
 }
 
 _lib = None
@@ -173,6 +175,11 @@ def device_info(device: int = 0):
     bdf = ctypes.create_string_buffer(32)
     _check(load().plf_device_info(device, name, 256, bdf, 32))
     return name.value.decode(), bdf.value.decode()
+
+
+def set_release_mode(mode: int) -> None:
+    """Ring-slot release of the bulk-copy kernels: 1 fenced everywhere, 0 data dependency everywhere, -1 defaults."""
+    _check(load().plf_set_release_mode(mode))
 
 
 def launch_count() -> int:
@@ -440,8 +447,8 @@ class Context:
 
 
 def make_opts(math_mode: int = MATH_STRICT, variant: int = 0, threads: int = 0,
-              blocks_per_sm: int = 0, ev_per_category: int = 0) -> LaunchOpts:
-    return LaunchOpts(math_mode, variant, threads, blocks_per_sm, ev_per_category)
+              blocks_per_sm: int = 0, ev_per_category: int = 0, flags: int = 0) -> LaunchOpts:
+    return LaunchOpts(math_mode, variant, threads, blocks_per_sm, ev_per_category, flags)
 
 
 def newview_device(x1, x2, x3, scaler, ev, p_left, p_right, wgt, n: int, scaler_sum,

@@ -11,6 +11,7 @@
 #include "plf_registry.h"
 
 #include <atomic>
+#include <map>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -105,6 +106,13 @@ int fail(plf_ctx *ctx, int code, const char *fmt, ...)
 // B200 (profiles/r01_sweep.md, "static vs dynamic").
 constexpr int kDefaultVariant = 1432;
 constexpr int kDefaultThreads = 512;
+// Small launches (fewer than kSmallLaunchSites sites) default to a shape of which TWO CTAs fit on an SM (8 consumer
+// warps + 1, 96 registers, 3 stages of 256 sites = 96 KB), so that independent instances (NUM_ACCELERATORS streams,
+// host_mem.cpp:287-325) run side by side instead of queueing behind full-SM CTAs, and with programmatic dependent
+// launch the ramp of a launch overlaps the tail of its predecessor in the stream.  0 disables the rule.
+constexpr size_t kSmallLaunchSites = (size_t)8 << 20;
+constexpr int kSmallVariant = 0;
+constexpr int kSmallThreads = 256;
 
 using plf::KernelSel;
 using plf::NewviewFn;
@@ -123,18 +131,62 @@ KernelSel pick_kernel(int math, int variant, int threads)
 
 int device_sms(int *sms)
 {
+    static std::atomic<int> cached[64];      // SM count per device ordinal, 0 = not read yet
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    if (dev >= 0 && dev < 64) {
+        const int c = cached[dev].load(std::memory_order_relaxed);
+        if (c > 0) {
+            *sms = c;
+            return 0;
+        }
+    }
     if (cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    if (dev >= 0 && dev < 64) cached[dev].store(*sms, std::memory_order_relaxed);
     return 0;
+}
+
+// Per (device, kernel): the > 48 KB shared-memory opt-in has been made and the occupancy is known.  Filled on the
+// first launch, so the run path of a 30 us kernel does not pay three runtime queries per launch.
+struct KernelState {
+    bool prepared = false;
+    int occupancy = 0;
+};
+std::mutex g_kstate_mu;
+std::map<std::pair<int, const void *>, KernelState> g_kstate;
+
+int kernel_state(plf_ctx *ctx, const KernelSel &k, KernelState *out)
+{
+    int dev = 0;
+    PLF_CUDA(ctx, cudaGetDevice(&dev));
+    const auto key = std::make_pair(dev, reinterpret_cast<const void *>(k.fn));
+    {
+        std::lock_guard<std::mutex> g(g_kstate_mu);
+        auto it = g_kstate.find(key);
+        if (it != g_kstate.end()) {
+            *out = it->second;
+            return PLF_OK;
+        }
+    }
+    KernelState st;
+    if (k.smem > 48u * 1024u)
+        PLF_CUDA(ctx, cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.smem));
+    st.prepared = true;
+    PLF_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&st.occupancy, k.fn, k.threads, k.smem));
+    if (st.occupancy <= 0) st.occupancy = 1;
+    {
+        std::lock_guard<std::mutex> g(g_kstate_mu);
+        g_kstate[key] = st;
+    }
+    *out = st;
+    return PLF_OK;
 }
 
 // Opt in to > 48 KB of dynamic shared memory once per kernel and device.
 int prepare_kernel(plf_ctx *ctx, const KernelSel &k)
 {
-    if (k.smem > 48u * 1024u)
-        PLF_CUDA(ctx, cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k.smem));
-    return PLF_OK;
+    KernelState st;
+    return kernel_state(ctx, k, &st);
 }
 
 // Resolves defaults and the persistent grid size: SMs x resident blocks per SM, capped by the
@@ -142,8 +194,16 @@ int prepare_kernel(plf_ctx *ctx, const KernelSel &k)
 int resolve_launch(plf_ctx *ctx, const plf_launch_opts *opts, size_t n, KernelSel *sel, int *grid)
 {
     int math = opts ? opts->math_mode : PLF_MATH_STRICT;
-    int variant = opts && opts->variant ? opts->variant : kDefaultVariant;
-    int thr = opts && opts->threads_per_block ? opts->threads_per_block : kDefaultThreads;
+    int variant = opts ? opts->variant : 0;
+    int thr = opts ? opts->threads_per_block : 0;
+    if (variant == 0 && thr == 0) {
+        const bool small = kSmallVariant != 0 && n < kSmallLaunchSites;
+        variant = small ? kSmallVariant : kDefaultVariant;
+        thr = small ? kSmallThreads : kDefaultThreads;
+    } else {
+        if (variant == 0) variant = kDefaultVariant;
+        if (thr == 0) thr = kDefaultThreads;
+    }
     int bps = opts ? opts->blocks_per_sm : 0;
     if (math != PLF_MATH_STRICT && math != PLF_MATH_FMA)
         return fail(ctx, PLF_ERR_INVALID, "unknown math mode %d", math);
@@ -152,13 +212,10 @@ int resolve_launch(plf_ctx *ctx, const plf_launch_opts *opts, size_t n, KernelSe
         return fail(ctx, PLF_ERR_INVALID, "unknown kernel variant %d / threads %d", variant, thr);
     int sms = 0;
     if (device_sms(&sms) != 0) return fail(ctx, PLF_ERR_CUDA, "no CUDA device");
-    int rc = prepare_kernel(ctx, k);
+    KernelState st;
+    int rc = kernel_state(ctx, k, &st);
     if (rc != PLF_OK) return rc;
-    if (bps <= 0) {
-        int occ = 0;
-        PLF_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k.fn, k.threads, k.smem));
-        bps = occ > 0 ? occ : 1;
-    }
+    if (bps <= 0) bps = st.occupancy;
     const size_t per_iter = (size_t)k.sites_per_block_iter;
     const size_t blocks_needed = (n + per_iter - 1) / per_iter;
     size_t g = (size_t)sms * (size_t)bps;
@@ -169,30 +226,62 @@ int resolve_launch(plf_ctx *ctx, const plf_launch_opts *opts, size_t n, KernelSe
     return PLF_OK;
 }
 
-// Work-counter pairs for the dynamically scheduled kernels: one ring per device, zeroed once; every
-// launch takes the next pair and the kernel's last CTA leaves it zeroed again (self-cleaning), so
-// concurrent launches on different streams never share a pair unless kWorkPairs launches are in flight.
-constexpr unsigned kWorkPairs = 4096;
-std::mutex g_work_mu;
-unsigned long long *g_work_dev[64] = {nullptr};
-std::atomic<unsigned> g_work_next{0};
+// Per-stream device scratch: the work-counter pair of the dynamically scheduled kernels, the ticket and the
+// per-block partial sums of the deterministic log-likelihood reduction, and a staging slot for host matrices.
+// Launches on one stream are serialised, so a stream's launches can share one record; every (device, stream) pair
+// gets its own on first use, so concurrent launches on different streams never share a work counter however many
+// are in flight.  The slab holds kScratchSlots records per device; past that, streams share records round-robin.
+constexpr unsigned kScratchSlots = 1024;
+std::mutex g_scratch_mu;
+plf::StreamScratch *g_scratch_dev[64] = {nullptr};
+std::map<std::pair<int, cudaStream_t>, unsigned> g_scratch_of;
+unsigned g_scratch_next[64] = {0};
 
-int work_pair(plf_ctx *ctx, unsigned long long **out)
+}  // namespace
+
+int plf::stream_scratch(cudaStream_t stream, plf::StreamScratch **out)
 {
     int dev = 0;
-    PLF_CUDA(ctx, cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64) return fail(ctx, PLF_ERR_INVALID, "device ordinal %d out of range", dev);
-    {
-        std::lock_guard<std::mutex> g(g_work_mu);
-        if (!g_work_dev[dev]) {
-            unsigned long long *d = nullptr;
-            PLF_CUDA(ctx, cudaMalloc(&d, 2 * kWorkPairs * sizeof(unsigned long long)));
-            PLF_CUDA(ctx, cudaMemset(d, 0, 2 * kWorkPairs * sizeof(unsigned long long)));
-            g_work_dev[dev] = d;
-        }
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return PLF_ERR_CUDA;
+    std::lock_guard<std::mutex> g(g_scratch_mu);
+    if (!g_scratch_dev[dev]) {
+        plf::StreamScratch *d = nullptr;
+        if (cudaMalloc(&d, kScratchSlots * sizeof(plf::StreamScratch)) != cudaSuccess) return PLF_ERR_NOMEM;
+        if (cudaMemset(d, 0, kScratchSlots * sizeof(plf::StreamScratch)) != cudaSuccess) return PLF_ERR_CUDA;
+        g_scratch_dev[dev] = d;
     }
-    *out = g_work_dev[dev] + 2 * (g_work_next.fetch_add(1, std::memory_order_relaxed) % kWorkPairs);
+    const auto key = std::make_pair(dev, stream);
+    auto it = g_scratch_of.find(key);
+    unsigned slot;
+    if (it != g_scratch_of.end()) {
+        slot = it->second;
+    } else {
+        slot = g_scratch_next[dev]++ % kScratchSlots;
+        g_scratch_of[key] = slot;
+    }
+    *out = g_scratch_dev[dev] + slot;
     return PLF_OK;
+}
+
+namespace {
+
+int work_pair(plf_ctx *ctx, cudaStream_t stream, unsigned long long **out)
+{
+    plf::StreamScratch *sc = nullptr;
+    int rc = plf::stream_scratch(stream, &sc);
+    if (rc != PLF_OK) return fail(ctx, rc, "per-stream scratch allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    *out = sc->work;
+    return PLF_OK;
+}
+
+// Ring-slot release mechanism of the bulk-copy kernels (plf_kernels.cuh, mbar_release_slot*): the fenced release is
+// the default of the DRAM-bound kernels; PLF_SAFE_RELEASE=1 forces it everywhere (also the tree kernel), =0 forces the
+// data-dependency release everywhere, so a field failure can be bisected without a rebuild.
+int release_flag(const plf_launch_opts *opts, bool default_fenced)
+{
+    if (opts && (opts->flags & PLF_LAUNCH_FENCED_RELEASE)) return plf::kFlagFencedRelease;
+    if (opts && (opts->flags & PLF_LAUNCH_DEP_RELEASE)) return 0;
+    return plf::fenced_release(default_fenced) ? plf::kFlagFencedRelease : 0;
 }
 
 int launch_newview(plf_ctx *ctx, const float *x1, const float *x2, float *x3, unsigned char *scaler,
@@ -211,7 +300,7 @@ int launch_newview(plf_ctx *ctx, const float *x1, const float *x2, float *x3, un
     if (rc != PLF_OK) return rc;
     unsigned long long *work = nullptr;
     if (k.dynamic) {
-        rc = work_pair(ctx, &work);
+        rc = work_pair(ctx, stream, &work);
         if (rc != PLF_OK) return rc;
     }
     // Programmatic dependent launch: the kernel's prologue may overlap the tail of the previous kernel
@@ -229,10 +318,11 @@ int launch_newview(plf_ctx *ctx, const float *x1, const float *x2, float *x3, un
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = use_pdl ? 1 : 0;
+    cfg.numAttrs = (use_pdl && !(opts && (opts->flags & PLF_LAUNCH_NO_PDL))) ? 1 : 0;
+    const int flags = ((opts && opts->ev_per_category) ? plf::kFlagEvPerCategory : 0) | release_flag(opts, true);
     PLF_CUDA(ctx, cudaLaunchKernelEx(&cfg, k.fn, reinterpret_cast<const float4 *>(x1),
                                      reinterpret_cast<const float4 *>(x2), reinterpret_cast<float4 *>(x3), scaler,
-                                     ev, pl, pr, wgt, n, sum, opts ? opts->ev_per_category : 0, work));
+                                     ev, pl, pr, wgt, n, sum, flags, work));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     PLF_CUDA(ctx, cudaGetLastError());
     return PLF_OK;
@@ -333,6 +423,14 @@ int gen_pattern_device(plf_ctx *ctx, float **out)
     return PLF_OK;
 }
 
+struct Mats144 {
+    float v[144];
+};
+__global__ void plf_store_mats(const __grid_constant__ Mats144 m, float *__restrict__ dst)
+{
+    if (threadIdx.x < 144) dst[threadIdx.x] = m.v[threadIdx.x];
+}
+
 int check_inst(plf_ctx *ctx, unsigned inst, bool need_alloc, Instance **out)
 {
     if (!ctx) return fail(nullptr, PLF_ERR_INVALID, "NULL context");
@@ -385,6 +483,27 @@ unsigned long long plf_launch_count(void) { return g_launches.load(); }
 }  // extern "C"
 
 void plf::count_launches(unsigned long long n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// -2: follow the environment (PLF_SAFE_RELEASE); -1 / 0 / 1 set by plf_set_release_mode
+static std::atomic<int> g_release_mode{-2};
+
+bool plf::fenced_release(bool family_default)
+{
+    static const int env = [] {
+        const char *e = getenv("PLF_SAFE_RELEASE");
+        return !e || !e[0] ? -1 : (e[0] == '0' ? 0 : 1);
+    }();
+    int v = g_release_mode.load(std::memory_order_relaxed);
+    if (v == -2) v = env;
+    return v < 0 ? family_default : v == 1;
+}
+
+extern "C" int plf_set_release_mode(int mode)
+{
+    if (mode < -1 || mode > 1) return fail(nullptr, PLF_ERR_INVALID, "release mode must be -1 (defaults), 0 (dependency) or 1 (fenced)");
+    g_release_mode.store(mode, std::memory_order_relaxed);
+    return PLF_OK;
+}
 
 extern "C" {
 
@@ -670,6 +789,7 @@ int plf_run_async(plf_ctx *ctx, unsigned inst, size_t sites)
     opts.threads_per_block = ctx->threads;
     opts.blocks_per_sm = ctx->blocks_per_sm;
     opts.ev_per_category = 0;
+    opts.flags = 0;
     if (ctx->input_src == PLF_INPUT_MEM) {
         const float *ev = I->d_left;                                   // mem[0]
         const float *pl = I->d_left + PLF_EV_FLOATS;                   // mem[1..4]
@@ -967,22 +1087,36 @@ int plf_newview_stream(plf_ctx *ctx, const float *ev, const float *p_left, const
     opts.threads_per_block = ctx->threads;
     opts.blocks_per_sm = ctx->blocks_per_sm;
     opts.ev_per_category = 0;
+    opts.flags = 0;
+    // A failure in the middle of the pipeline must not return while copies to or from the caller's host arrays are
+    // still in flight on the other streams: drain all of them first (secondary errors of the drain are ignored).
+    auto drain = [&](int rc) {
+        for (int b = 0; b < K; ++b) cudaStreamSynchronize(ctx->s_stream[b]);
+        cudaGetLastError();
+        return rc;
+    };
+#define PLF_CUDA_DRAIN(expr)                                                                                         \
+    do {                                                                                                             \
+        cudaError_t e__ = (expr);                                                                                    \
+        if (e__ != cudaSuccess) return drain(fail(ctx, PLF_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__))); \
+    } while (0)
     size_t k = 0;
     for (size_t lo = 0; lo < n_sites; lo += chunk_sites, ++k) {
         const int b = (int)(k % K);
         cudaStream_t st = ctx->s_stream[b];
         const size_t cnt = n_sites - lo < chunk_sites ? n_sites - lo : chunk_sites;
         const size_t bytes = cnt * PLF_SITE_FLOATS * sizeof(float);
-        PLF_CUDA(ctx, cudaMemcpyAsync(ctx->sd_x1[b], x1 + lo * 16, bytes, cudaMemcpyHostToDevice, st));
-        PLF_CUDA(ctx, cudaMemcpyAsync(ctx->sd_x2[b], x2 + lo * 16, bytes, cudaMemcpyHostToDevice, st));
-        if (wgt) PLF_CUDA(ctx, cudaMemcpyAsync(ctx->sd_wgt[b], wgt + lo, cnt * sizeof(int), cudaMemcpyHostToDevice, st));
+        PLF_CUDA_DRAIN(cudaMemcpyAsync(ctx->sd_x1[b], x1 + lo * 16, bytes, cudaMemcpyHostToDevice, st));
+        PLF_CUDA_DRAIN(cudaMemcpyAsync(ctx->sd_x2[b], x2 + lo * 16, bytes, cudaMemcpyHostToDevice, st));
+        if (wgt) PLF_CUDA_DRAIN(cudaMemcpyAsync(ctx->sd_wgt[b], wgt + lo, cnt * sizeof(int), cudaMemcpyHostToDevice, st));
         int rc = launch_newview(ctx, ctx->sd_x1[b], ctx->sd_x2[b], ctx->sd_x3[b], ctx->sd_sc[b], ctx->sd_mats,
                                 ctx->sd_mats + 16, ctx->sd_mats + 80, wgt ? ctx->sd_wgt[b] : nullptr, cnt, ctx->sd_sum,
                                 &opts, st);
-        if (rc != PLF_OK) return rc;
-        PLF_CUDA(ctx, cudaMemcpyAsync(x3 + lo * 16, ctx->sd_x3[b], bytes, cudaMemcpyDeviceToHost, st));
-        if (scaler) PLF_CUDA(ctx, cudaMemcpyAsync(scaler + lo, ctx->sd_sc[b], cnt, cudaMemcpyDeviceToHost, st));
+        if (rc != PLF_OK) return drain(rc);
+        PLF_CUDA_DRAIN(cudaMemcpyAsync(x3 + lo * 16, ctx->sd_x3[b], bytes, cudaMemcpyDeviceToHost, st));
+        if (scaler) PLF_CUDA_DRAIN(cudaMemcpyAsync(scaler + lo, ctx->sd_sc[b], cnt, cudaMemcpyDeviceToHost, st));
     }
+#undef PLF_CUDA_DRAIN
     for (int b = 0; b < K; ++b) PLF_CUDA(ctx, cudaStreamSynchronize(ctx->s_stream[b]));
     PLF_CUDA(ctx, cudaMemcpy(ctx->sh_sum, ctx->sd_sum, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     if (increment) *increment = (long long)*ctx->sh_sum;
@@ -1015,16 +1149,21 @@ int plf_newview_states_device(int states, const float *x1, const float *x2, floa
     if (math != PLF_MATH_STRICT && math != PLF_MATH_FMA) return fail(nullptr, PLF_ERR_INVALID, "unknown math mode %d", math);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (states == 4) {
-        // the matrices are HOST arrays in this entry point: stage them on the stream for the DNA kernel
-        float *d_m = nullptr;
-        PLF_CUDA(nullptr, cudaMallocAsync(&d_m, 144 * sizeof(float), st));
-        cudaError_t e = cudaMemcpyAsync(d_m, ev, 16 * sizeof(float), cudaMemcpyHostToDevice, st);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_m + 16, p_left, 64 * sizeof(float), cudaMemcpyHostToDevice, st);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(d_m + 80, p_right, 64 * sizeof(float), cudaMemcpyHostToDevice, st);
-        int rc = e == cudaSuccess ? launch_newview(nullptr, x1, x2, x3, scaler, d_m, d_m + 16, d_m + 80, wgt, n, scaler_sum, opts, st)
-                                  : fail(nullptr, PLF_ERR_CUDA, "matrix upload failed: %s", cudaGetErrorString(e));
-        cudaFreeAsync(d_m, st);
-        return rc;
+        // The matrices are HOST arrays in this entry point.  They travel BY VALUE as the argument of a one-block
+        // upload kernel that writes them into the stream's scratch record (so they are consumed before the call
+        // returns, pinned or not, and the call can be captured into a CUDA graph: no allocation, no host copy),
+        // and the DNA kernel reads them from there.  Stream order keeps consecutive calls on one stream apart.
+        plf::StreamScratch *sc = nullptr;
+        int rc = plf::stream_scratch(st, &sc);
+        if (rc != PLF_OK) return fail(nullptr, rc, "per-stream scratch allocation failed");
+        Mats144 m;
+        memcpy(m.v, ev, 16 * sizeof(float));
+        memcpy(m.v + 16, p_left, 64 * sizeof(float));
+        memcpy(m.v + 80, p_right, 64 * sizeof(float));
+        plf_store_mats<<<1, 160, 0, st>>>(m, sc->mats);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        PLF_CUDA(nullptr, cudaGetLastError());
+        return launch_newview(nullptr, x1, x2, x3, scaler, sc->mats, sc->mats + 16, sc->mats + 80, wgt, n, scaler_sum, opts, st);
     }
     if (opts && opts->ev_per_category) return fail(nullptr, PLF_ERR_INVALID, "ev_per_category is a DNA gen-mode option");
     int rc = plf::launch_newview_aa(x1, x2, x3, scaler, ev, p_left, p_right, wgt, n, scaler_sum, math,

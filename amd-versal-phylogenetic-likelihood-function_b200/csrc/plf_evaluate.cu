@@ -9,8 +9,13 @@
 // x1, x2 are the CLVs at the two ends of the branch (eigen-space, as newview leaves them), diag[j,k]
 // = exp(lambda_k * rate_j * t) for the branch, cnt1/cnt2 the accumulated per-site scaler counts.
 // One thread per (site, category) as in the newview kernels: a 128-bit load per child, four fp64
-// products, two shuffles for the per-site sum; fp64 log and accumulation; block reduction and one
-// atomicAdd(double) per block.  HBM-bound: 128 B/site (+ 4 B per count vector and for wgt).
+// products, two shuffles for the per-site sum; fp64 log and accumulation.  HBM-bound: 128 B/site (+ 4 B per
+// count vector and for wgt).
+// The sum is REPRODUCIBLE run to run: every block leaves its partial sum in the stream's scratch record, the
+// last block to finish (a ticket counter) adds the partials in block order with a fixed reduction tree and
+// makes the single addition to *lnl.  The grid is a function of (n, SM count) only, so the same input on
+// the same device always takes the same summation order -- a likelihood that drives a tree search must not
+// flicker in its last digits.
 #include "../../include/b200plf.h"
 #include "plf_kernels.cuh"
 #include "plf_registry.h"
@@ -23,7 +28,7 @@ __global__ void __launch_bounds__(kEvalThreads)
 plf_evaluate_kernel(const float4 *__restrict__ x1, const float4 *__restrict__ x2,
                     const int *__restrict__ cnt1, const int *__restrict__ cnt2,
                     const int *__restrict__ wgt, const float *__restrict__ diag, size_t n,
-                    double *__restrict__ lnl)
+                    double *__restrict__ lnl, StreamScratch *__restrict__ scratch)
 {
     const int lane = threadIdx.x & 31;
     const int cat = lane & 3;
@@ -55,15 +60,35 @@ plf_evaluate_kernel(const float4 *__restrict__ x1, const float4 *__restrict__ x2
         }
     }
     __shared__ double warp_acc[kEvalThreads / 32];
+    __shared__ bool is_last;
+    auto block_sum = [&](double v) {             // fixed tree: shuffles within the warp, then across the warps
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) warp_acc[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x < 32) {
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        __syncthreads();
+        if (lane == 0) warp_acc[threadIdx.x >> 5] = v;
+        __syncthreads();
         double t = threadIdx.x < kEvalThreads / 32 ? warp_acc[threadIdx.x] : 0.0;
+        if (threadIdx.x < 32) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-        if (threadIdx.x == 0) atomicAdd(lnl, t);
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        }
+        return t;                                // valid in thread 0
+    };
+    const double mine = block_sum(acc);
+    if (threadIdx.x == 0) {
+        scratch->partials[blockIdx.x] = mine;
+        __threadfence();
+        is_last = atomicAdd(&scratch->ticket, 1ull) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double part = 0.0;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += kEvalThreads) part += __ldcg(&scratch->partials[b]);
+    const double total = block_sum(part);
+    if (threadIdx.x == 0) {
+        atomicAdd(lnl, total);                   // the launch's only addition
+        scratch->ticket = 0ull;                  // clean for the next launch on this stream
     }
 }
 
@@ -76,10 +101,13 @@ int launch_evaluate(const float *x1, const float *x2, const int *cnt1, const int
         return PLF_ERR_CUDA;
     size_t grid = (n * 4 + kEvalThreads - 1) / kEvalThreads;
     if (grid > (size_t)sms * 8) grid = (size_t)sms * 8;
+    if (grid > (size_t)kEvalMaxBlocks) grid = kEvalMaxBlocks;
     if (grid == 0) return PLF_OK;
+    StreamScratch *scratch = nullptr;
+    if (int rc = stream_scratch(stream, &scratch)) return rc;
     plf_evaluate_kernel<<<(int)grid, kEvalThreads, 0, stream>>>(reinterpret_cast<const float4 *>(x1),
                                                                 reinterpret_cast<const float4 *>(x2), cnt1, cnt2,
-                                                                wgt, diag, n, lnl);
+                                                                wgt, diag, n, lnl, scratch);
     count_launches(1);
     return cudaGetLastError() == cudaSuccess ? PLF_OK : PLF_ERR_CUDA;
 }

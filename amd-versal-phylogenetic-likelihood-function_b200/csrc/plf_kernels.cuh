@@ -25,6 +25,10 @@ namespace plf {
 constexpr float kMinLikelihood = 0x1p-32f;   // plf.cpp:5-6 (exact in fp32)
 constexpr float kTwoToThe32 = 0x1p+32f;      // plf.cpp:5
 
+// Kernel `flags` argument (bit 0 is the old ev_per_category int, so existing callers keep working).
+constexpr int kFlagEvPerCategory = 1;     // ev points to EV4[4][16], one matrix per category (gen mode)
+constexpr int kFlagFencedRelease = 2;     // release ring slots with fence.proxy.async instead of the data dependency
+
 // ---------------------------------------------------------------------------------------------
 // Arithmetic policies.
 // STRICT reproduces the reference's rounding: each product and each sum is rounded to fp32
@@ -291,7 +295,7 @@ plf_newview_ldg(const float4 *__restrict__ x1, const float4 *__restrict__ x2,
                 float4 *__restrict__ x3, unsigned char *__restrict__ scaler,
                 const float *__restrict__ ev, const float *__restrict__ pl,
                 const float *__restrict__ pr, const int *__restrict__ wgt, size_t n,
-                unsigned long long *__restrict__ scaler_sum, int ev_per_category,
+                unsigned long long *__restrict__ scaler_sum, int flags,
                 unsigned long long * /*work: unused, static schedule*/)
 {
     constexpr int TILE = 8 * U;                       // sites per warp tile
@@ -302,7 +306,7 @@ plf_newview_ldg(const float4 *__restrict__ x1, const float4 *__restrict__ x2,
     pdl_wait();
     pdl_launch_dependents();
     CatConst c;
-    load_cat_const(c, ev, pl, pr, cat, ev_per_category);
+    load_cat_const(c, ev, pl, pr, cat, flags & kFlagEvPerCategory);
 
     const size_t warps_total = (size_t)gridDim.x * (THREADS / 32);
     const size_t warp_id = (size_t)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
@@ -409,7 +413,6 @@ __device__ __forceinline__ void fence_proxy_async_smem()
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-__device__ __forceinline__ void mbar_release_slot(uint64_t *bar, int lane, unsigned dep);
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
@@ -425,6 +428,20 @@ __device__ __forceinline__ void mbar_release_slot(uint64_t *bar, int lane, unsig
             mbar_arrive(bar);
         }
     }
+}
+// The release written against the PTX memory model: EVERY lane orders its own generic-proxy reads of the
+// slot before later async-proxy writes (fence.proxy.async), the warp converges, one lane arrives.
+__device__ __forceinline__ void mbar_release_slot_fenced(uint64_t *bar, int lane)
+{
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+}
+template <bool = true>
+__device__ __forceinline__ void release_slot(uint64_t *bar, int lane, unsigned dep, int flags)
+{
+    if (flags & kFlagFencedRelease) mbar_release_slot_fenced(bar, lane);
+    else mbar_release_slot(bar, lane, dep);
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
 {
@@ -458,7 +475,7 @@ plf_newview_tma(const float4 *__restrict__ x1, const float4 *__restrict__ x2,
                 float4 *__restrict__ x3, unsigned char *__restrict__ scaler,
                 const float *__restrict__ ev, const float *__restrict__ pl,
                 const float *__restrict__ pr, const int *__restrict__ wgt, size_t n,
-                unsigned long long *__restrict__ scaler_sum, int ev_per_category,
+                unsigned long long *__restrict__ scaler_sum, int flags,
                 unsigned long long * /*work: unused, static schedule*/)
 {
     constexpr int THREADS = (WARPS + 1) * 32;
@@ -513,7 +530,7 @@ plf_newview_tma(const float4 *__restrict__ x1, const float4 *__restrict__ x2,
         const int cat = lane & 3;
         const int site_in_row = lane >> 2;
         CatConst c;
-        load_cat_const(c, ev, pl, pr, cat, ev_per_category);
+        load_cat_const(c, ev, pl, pr, cat, flags & kFlagEvPerCategory);
 
         const size_t last_full = n / STAGE;                 // stages [0, last_full) are complete
         const size_t stride_f4 = (size_t)gridDim.x * STAGE_F4;
@@ -539,7 +556,7 @@ plf_newview_tma(const float4 *__restrict__ x1, const float4 *__restrict__ x2,
             unsigned dep = 0;
 #pragma unroll
             for (int u = 0; u < U; ++u) dep ^= __float_as_uint(a[u].x) ^ __float_as_uint(b[u].w);
-            mbar_release_slot(&empty[slot], lane, dep);
+            release_slot(&empty[slot], lane, dep, flags);
             if (++slot == DEPTH) {
                 slot = 0;
                 phase ^= 1u;
@@ -603,9 +620,10 @@ constexpr size_t tma_smem_bytes()
 // the launch-to-launch spread of the static kernel shows it (8 Mi sites: mean 0.256 ms, min
 // 0.240 ms).  Here the producer of each CTA takes the next stage index from a global counter
 // (`work[0]`), publishes it to its consumers through shared memory together with the stage's
-// data, and a sentinel index ends the loop.  The fetch for stage k+1 is issued before the copies of
-// stage k, so the atomic's latency is off the critical path.  The last CTA to finish (`work[1]`
-// counts them) zeroes both words: the pair is clean for its next user without a memset.
+// data, and a sentinel index ends the loop.  The first DEPTH stages of a CTA are dealt statically and
+// two counter fetches are kept in flight, so neither the ramp of a launch nor its steady state waits
+// for an atomic round trip.  The last CTA to finish (`work[1]` counts them) zeroes both words: the
+// pair is clean for its next user without a memset.
 // ---------------------------------------------------------------------------------------------
 template <class M, int U, int WARPS, int DEPTH, int MINB>
 __global__ void __launch_bounds__((WARPS + 1) * 32, MINB)
@@ -613,7 +631,7 @@ plf_newview_tma_dyn(const float4 *__restrict__ x1, const float4 *__restrict__ x2
                     float4 *__restrict__ x3, unsigned char *__restrict__ scaler,
                     const float *__restrict__ ev, const float *__restrict__ pl,
                     const float *__restrict__ pr, const int *__restrict__ wgt, size_t n,
-                    unsigned long long *__restrict__ scaler_sum, int ev_per_category,
+                    unsigned long long *__restrict__ scaler_sum, int flags,
                     unsigned long long *work)
 {
     constexpr int THREADS = (WARPS + 1) * 32;
@@ -650,17 +668,29 @@ plf_newview_tma_dyn(const float4 *__restrict__ x1, const float4 *__restrict__ x2
     if (warp == WARPS) {
         // ===== producer =====
         if (lane == 0) {
+            // The first DEPTH stages of every CTA are dealt statically (stage blockIdx.x + i*gridDim.x): the whole
+            // ring is requested in the first microsecond of the launch instead of one stage per atomic round trip.
+            // The counter hands out the stages from DEPTH*gridDim.x on; two fetches are kept in flight, so a
+            // producer never waits for an atomic that it issued less than two stages ago.
             uint32_t slot = 0, phase = 0;
-            unsigned long long next = atomicAdd(work, 1ull);
-            for (;;) {
-                const unsigned long long st = next;
+            const unsigned long long base = (unsigned long long)DEPTH * gridDim.x;
+            unsigned long long next_a = base + atomicAdd(work, 1ull);
+            unsigned long long next_b = base + atomicAdd(work, 1ull);
+            for (unsigned long long it = 0;; ++it) {
+                unsigned long long st;
+                if (it < (unsigned long long)DEPTH) {
+                    st = blockIdx.x + it * gridDim.x;         // >= n_stages only if every dynamic index is too
+                } else {
+                    st = next_a;
+                    next_a = next_b;
+                    next_b = base + atomicAdd(work, 1ull);    // needed two iterations from now
+                }
                 mbar_wait(&empty[slot], phase ^ 1u);
                 if (st >= n_stages) {                     // out of work: tell the consumers and stop
                     stage_of[slot] = kDone;
                     mbar_arrive(&full[slot]);
                     break;
                 }
-                next = atomicAdd(work, 1ull);             // needed one iteration from now
                 stage_of[slot] = (uint32_t)st;
                 const size_t s0 = (size_t)st * STAGE;
                 const size_t left = n - s0;
@@ -673,13 +703,16 @@ plf_newview_tma_dyn(const float4 *__restrict__ x1, const float4 *__restrict__ x2
                     phase ^= 1u;
                 }
             }
+            // every fetch this producer issued has returned before the CTA reports itself finished: the last
+            // CTA zeroes the pair, and a straggling atomic would leave it dirty for the next launch
+            asm volatile("" :: "l"(next_a), "l"(next_b));
         }
     } else {
         // ===== consumers =====
         const int cat = lane & 3;
         const int site_in_row = lane >> 2;
         CatConst c;
-        load_cat_const(c, ev, pl, pr, cat, ev_per_category);
+        load_cat_const(c, ev, pl, pr, cat, flags & kFlagEvPerCategory);
         const size_t last_full = n / STAGE;
         const uint32_t tile_off = warp * (TILE * 4) + lane;
 
@@ -700,7 +733,7 @@ plf_newview_tma_dyn(const float4 *__restrict__ x1, const float4 *__restrict__ x2
             unsigned dep = st;
 #pragma unroll
             for (int u = 0; u < U; ++u) dep ^= __float_as_uint(a[u].x) ^ __float_as_uint(b[u].w);
-            mbar_release_slot(&empty[slot], lane, dep);
+            release_slot(&empty[slot], lane, dep, flags);
             if (++slot == DEPTH) {
                 slot = 0;
                 phase ^= 1u;
@@ -789,7 +822,7 @@ template <class M, int U, int WARPS, int DEPTH, int MINB>
 __global__ void __launch_bounds__((WARPS + 1) * 32, MINB)
 plf_newview_batch(const BatchOp *__restrict__ ops, int n_ops, size_t n,
                   const int *__restrict__ wgt, unsigned long long *__restrict__ scaler_sum,
-                  unsigned chunk, unsigned long long *work)
+                  unsigned chunk, unsigned long long *work, int flags)
 {
     constexpr int THREADS = (WARPS + 1) * 32;
     constexpr int TILE = 8 * U;
@@ -966,7 +999,7 @@ plf_newview_batch(const BatchOp *__restrict__ ops, int n_ops, size_t n,
                 unsigned dep = (unsigned)cnt ^ g;
 #pragma unroll
                 for (int u = 0; u < U; ++u) dep ^= __float_as_uint(a[u].x) ^ __float_as_uint(b[u].w);
-                mbar_release_slot(&empty[slot], lane, dep);
+                release_slot(&empty[slot], lane, dep, flags);
                 float4 *out = o.x3 + s0 * 4 + lane;
                 auto finish = [&](int u) {
                     float4 av, bv;

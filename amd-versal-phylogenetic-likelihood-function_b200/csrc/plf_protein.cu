@@ -166,7 +166,7 @@ template <class M, int T, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 plf_newview_aa(const __grid_constant__ AaMats mats, const float *__restrict__ x1, const float *__restrict__ x2,
                float *__restrict__ x3, unsigned char *__restrict__ scaler, const int *__restrict__ wgt, size_t n,
-               unsigned long long *__restrict__ scaler_sum)
+               unsigned long long *__restrict__ scaler_sum, int flags)
 {
     constexpr int TILE = 8 * T;                                   // sites per warp round
     constexpr int TILE_FLOATS = TILE * kAaSite;
@@ -203,7 +203,10 @@ plf_newview_aa(const __grid_constant__ AaMats mats, const float *__restrict__ x1
     // done, the x2 half after the right-branch products, so each copy has two thirds of a tile time to land.  The
     // refill must not start before every read of the half has been performed; `dep` (an XOR over a register of
     // every such read) exists only then, and the never-true comparison makes the copy wait for it.
+    // With kFlagFencedRelease (the default) every lane first orders its own reads of the half before later
+    // async-proxy writes with fence.proxy.async -- the release as the PTX memory model words it.
     auto fetch = [&](const float *src, float *dst, uint64_t *bar, size_t tl, unsigned dep) {
+        if (flags & kFlagFencedRelease) fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
             const size_t s0 = tl * TILE;
@@ -312,7 +315,7 @@ plf_generate_states_kernel(float4 *__restrict__ x1, float4 *__restrict__ x2, uin
 namespace {
 
 using AaFn = void (*)(const AaMats, const float *, const float *, float *, unsigned char *, const int *, size_t,
-                      unsigned long long *);
+                      unsigned long long *, int);
 struct AaSel {
     AaFn fn = nullptr;
     int t = 0, warps = 0;
@@ -380,7 +383,8 @@ int launch_newview_aa(const float *x1, const float *x2, float *x3, unsigned char
     const size_t tiles = (n + 8 * k.t - 1) / (8 * k.t);
     size_t grid = (tiles + k.warps - 1) / k.warps;
     if (grid > (size_t)sms) grid = sms;
-    k.fn<<<(int)grid, k.warps * 32, smem, stream>>>(m, x1, x2, x3, scaler, wgt, n, scaler_sum);
+    k.fn<<<(int)grid, k.warps * 32, smem, stream>>>(m, x1, x2, x3, scaler, wgt, n, scaler_sum,
+                                                    fenced_release(true) ? kFlagFencedRelease : 0);
     count_launches(1);
     return cudaGetLastError() == cudaSuccess ? PLF_OK : PLF_ERR_CUDA;
 }

@@ -54,4 +54,20 @@ void generate_states_host(int states, float *x1, float *x2, size_t first_site, s
 // process-wide count of kernel launches issued by this library (plf_launch_count)
 void count_launches(unsigned long long n);
 
+// Per-(device, stream) scratch record in device memory (plf_capi.cu): launches on one stream are serialised, so
+// they can share it; launches on different streams never do.
+constexpr int kEvalMaxBlocks = 2048;
+struct StreamScratch {
+    unsigned long long work[2];           // work-counter pair of the dynamically scheduled kernels (self-cleaning)
+    unsigned long long ticket;            // block ticket of the log-likelihood reduction (self-cleaning)
+    unsigned long long pad;
+    float mats[144];                      // EV[16] | P_left[64] | P_right[64] staged from host arrays
+    double partials[kEvalMaxBlocks];      // per-block partial sums, reduced in block order by the last block
+};
+int stream_scratch(cudaStream_t stream, StreamScratch **out);     // returns a plf_status
+
+// Slot-release mechanism of the ring kernels: PLF_SAFE_RELEASE=1 forces the fenced release everywhere, =0 the
+// data-dependency release everywhere; unset, every kernel family keeps its own default.
+bool fenced_release(bool family_default);
+
 }  // namespace plf

@@ -51,7 +51,7 @@ struct plf_tree {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaGraphExec_t exec = nullptr;
-    int exec_math = -1, exec_u = -1, exec_chunk = -1;
+    int exec_math = -1, exec_u = -1, exec_chunk = -1, exec_fenced = -1;
     bool exec_wgt = false;
     bool ran = false;
     std::string error;
@@ -82,7 +82,7 @@ int tfail(plf_tree *t, int code, const char *fmt, ...)
     } while (0)
 
 using BatchFn = void (*)(const plf::BatchOp *, int, size_t, const int *, unsigned long long *, unsigned,
-                         unsigned long long *);
+                         unsigned long long *, int);
 
 struct BatchSel {
     BatchFn fn;
@@ -178,7 +178,10 @@ int launch_level(plf_tree *t, const BatchSel &k, size_t level, cudaStream_t s)
     const plf::BatchOp *ops = t->d_ops + t->level_op_offset[level];
     const int *wgt = t->use_wgt ? t->d_wgt : nullptr;
     unsigned long long *work = t->dynamic ? t->d_work : nullptr;
-    TREE_CUDA(t, cudaLaunchKernelEx(&cfg, k.fn, ops, n_ops, t->n_sites, wgt, t->d_sum, (unsigned)chunk, work));
+    // slot release: data dependency by default (the fence caps the compressed-tip levels, plf_kernels.cuh);
+    // PLF_SAFE_RELEASE=1 selects the fenced release (read when the graph is captured)
+    const int flags = plf::fenced_release(false) ? plf::kFlagFencedRelease : 0;
+    TREE_CUDA(t, cudaLaunchKernelEx(&cfg, k.fn, ops, n_ops, t->n_sites, wgt, t->d_sum, (unsigned)chunk, work, flags));
     TREE_CUDA(t, cudaGetLastError());
     return PLF_OK;
 }
@@ -221,6 +224,7 @@ int build_graph(plf_tree *t)
     t->exec_u = t->tune_u;
     t->exec_chunk = t->tune_chunk;
     t->exec_wgt = t->use_wgt;
+    t->exec_fenced = plf::fenced_release(false) ? 1 : 0;
     return PLF_OK;
 }
 
@@ -489,7 +493,8 @@ int plf_tree_run_async(plf_tree *t)
 {
     if (!t) return tfail(nullptr, PLF_ERR_INVALID, "NULL tree");
     TREE_CUDA(t, cudaSetDevice(t->device));
-    if (!t->exec || t->exec_math != t->math || t->exec_u != t->tune_u || t->exec_chunk != t->tune_chunk || t->exec_wgt != t->use_wgt) {
+    if (!t->exec || t->exec_math != t->math || t->exec_u != t->tune_u || t->exec_chunk != t->tune_chunk || t->exec_wgt != t->use_wgt ||
+        t->exec_fenced != (plf::fenced_release(false) ? 1 : 0)) {
         int rc = build_graph(t);
         if (rc != PLF_OK) return rc;
     }

@@ -168,7 +168,19 @@ typedef struct plf_launch_opts {
     int threads_per_block;  /* 0 = default                                                       */
     int blocks_per_sm;      /* 0 = default (persistent grid = SMs x blocks_per_sm)               */
     int ev_per_category;    /* 0: ev is EV[16]; 1: ev is EV4[4][16], one matrix per category     */
+    int flags;              /* plf_launch_flags, 0 = defaults                                    */
 } plf_launch_opts;
+
+/* plf_launch_opts.flags.  The ring kernels hand a shared-memory slot back to the bulk-copy engine either behind
+ * fence.proxy.async (FENCED: the release as the PTX memory model words it; default of the DRAM-bound kernels) or
+ * behind a data dependency on the loaded registers (DEP: no fence; default of the tree kernel, whose compressed-tip
+ * levels the fence slows down).  The environment variable PLF_SAFE_RELEASE=1 / =0 forces one of them for every
+ * kernel of the process, so a suspected slot race can be bisected in the field without a rebuild.               */
+typedef enum plf_launch_flags {
+    PLF_LAUNCH_NO_PDL = 1,          /* do not launch with programmatic stream serialization            */
+    PLF_LAUNCH_FENCED_RELEASE = 2,
+    PLF_LAUNCH_DEP_RELEASE = 4
+} plf_launch_flags;
 
 /* Newview of n sites.  ALL pointers are device pointers on `device`'s current context:
  *   x1,x2,x3 : 16 floats per site, 16-byte aligned; x3 may alias neither input
@@ -316,6 +328,10 @@ int plf_memcpy_h2d(void *dst_device, const void *src_host, size_t bytes, void *s
 int plf_memcpy_d2h(void *dst_host, const void *src_device, size_t bytes, void *stream);
 int plf_memset_device(void *dst_device, int value, size_t bytes, void *stream);
 int plf_stream_sync(void *stream);
+
+/* Process-wide override of the ring-slot release mechanism (see plf_launch_flags): 1 = fenced everywhere,
+ * 0 = data dependency everywhere, -1 = every kernel family's own default (also what PLF_SAFE_RELEASE unset means). */
+int plf_set_release_mode(int mode);
 
 /* Largest tile the library was compiled for, number of SMs etc. -- introspection for benches. */
 int plf_kernel_info(int variant, int math_mode, int *regs_per_thread, int *threads_per_block,
