@@ -128,6 +128,7 @@ PROTOTYPES = {
     "plf_kernel_info": (_i, [_i, _i] + [ctypes.POINTER(_i)] * 4),
     "plf_launch_count": (ctypes.c_ulonglong, []),
     "plf_set_release_mode": (_i, [_i]),
+    "plf_probe_host_link": (_i, [_i, _vp, _sz, _vp, _sz, _i, _i, ctypes.POINTER(ctypes.c_double)]),
 }
 
 _lib = None
@@ -180,6 +181,19 @@ def device_info(device: int = 0):
 def set_release_mode(mode: int) -> None:
     """Ring-slot release of the bulk-copy kernels: 1 fenced everywhere, 0 data dependency everywhere, -1 defaults."""
     _check(load().plf_set_release_mode(mode))
+
+
+def probe_host_link(device: int, host_in=None, host_out=None, h2d_bytes: int = 0, d2h_bytes: int = 0, reps: int = 4,
+                    pieces: int = 1) -> float:
+    """Seconds for `reps` rounds of bare pinned H2D + D2H copies issued together (no kernels).  host_in / host_out:
+    pinned numpy arrays (host_alloc) or None (allocated inside, h2d_bytes / d2h_bytes give the sizes)."""
+    sec = ctypes.c_double(0.0)
+    pi = _ptr(host_in) if host_in is not None else None
+    po = _ptr(host_out) if host_out is not None else None
+    nb_in = host_in.nbytes if host_in is not None else h2d_bytes
+    nb_out = host_out.nbytes if host_out is not None else d2h_bytes
+    _check(load().plf_probe_host_link(device, pi, nb_in, po, nb_out, reps, pieces, ctypes.byref(sec)))
+    return sec.value
 
 
 def launch_count() -> int:

@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <mutex>
 #include <new>
 #include <string>
@@ -1246,6 +1247,59 @@ int plf_memset_device(void *dst_device, int value, size_t bytes, void *stream)
 int plf_stream_sync(void *stream)
 {
     PLF_CUDA(nullptr, cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    return PLF_OK;
+}
+
+// Bare host-link probe (no kernels): what the platform gives plain pinned copies in both directions at once.
+int plf_probe_host_link(int device, void *host_in, size_t h2d_bytes, void *host_out, size_t d2h_bytes, int reps, int pieces,
+                        double *seconds)
+{
+    if (!seconds || reps < 1 || pieces < 1 || pieces > 64) return fail(nullptr, PLF_ERR_INVALID, "probe: bad arguments");
+    PLF_CUDA(nullptr, cudaSetDevice(device));
+    char *h_in = static_cast<char *>(host_in), *h_out = static_cast<char *>(host_out), *d_in = nullptr, *d_out = nullptr;
+    const bool own_in = h2d_bytes && !h_in, own_out = d2h_bytes && !h_out;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (own_in) e = cudaMallocHost(&h_in, h2d_bytes);
+    if (e == cudaSuccess && own_out) e = cudaMallocHost(&h_out, d2h_bytes);
+    if (e == cudaSuccess && h2d_bytes) e = cudaMalloc(&d_in, h2d_bytes);
+    if (e == cudaSuccess && d2h_bytes) e = cudaMalloc(&d_out, d2h_bytes);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking);
+    if (e == cudaSuccess && own_in) memset(h_in, 1, h2d_bytes);
+    if (e == cudaSuccess && own_out) memset(h_out, 1, d2h_bytes);
+    auto round = [&]() {
+        for (int k = 0; k < pieces && e == cudaSuccess; ++k) {
+            const size_t ci = (h2d_bytes / pieces) & ~(size_t)255, co = (d2h_bytes / pieces) & ~(size_t)255;
+            if (h2d_bytes) e = cudaMemcpyAsync(d_in + k * ci, h_in + k * ci, k == pieces - 1 ? h2d_bytes - k * ci : ci, cudaMemcpyHostToDevice, s_in);
+            if (e == cudaSuccess && d2h_bytes)
+                e = cudaMemcpyAsync(h_out + k * co, d_out + k * co, k == pieces - 1 ? d2h_bytes - k * co : co, cudaMemcpyDeviceToHost, s_out);
+        }
+    };
+    double dt = 0.0;
+    if (e == cudaSuccess) {
+        round();                                               // warm-up round
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s_in);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s_out);
+        timespec t0, t1;
+        clock_gettime(CLOCK_MONOTONIC, &t0);
+        for (int r = 0; r < reps && e == cudaSuccess; ++r) round();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s_in);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s_out);
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        dt = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+    }
+    if (s_in) cudaStreamDestroy(s_in);
+    if (s_out) cudaStreamDestroy(s_out);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    if (own_in && h_in) cudaFreeHost(h_in);
+    if (own_out && h_out) cudaFreeHost(h_out);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(nullptr, e == cudaErrorMemoryAllocation ? PLF_ERR_NOMEM : PLF_ERR_CUDA, "host-link probe failed: %s", cudaGetErrorString(e));
+    }
+    *seconds = dt;
     return PLF_OK;
 }
 

@@ -18,8 +18,14 @@ roofline   193 algorithmic bytes/site x sites per launch / mean launch time, aga
            HBM copy bandwidth in MEASURED_PEAKS.json.
 cpu_baseline  oracle/_ref (the reference's plf.cpp compiled in place) on all host cores.
 
-Side workloads (not the headline line): --workload cfg2 (1 Mi sites, one instance; --buffer-sets 1 for the
-"same buffers" variant) and --workload protein (the 20-state kernel, single GPU, its own CPU baseline).
+side       the other BASELINE.json configurations and the rows SURVEY.md section 8f adds, measured in the same
+           run after the headline (about a minute in total; --no-side skips them), each with its own roofline:
+           cfg2 (1 Mi sites, one instance: cold = rotating buffer sets, warm = one set, K launches between two
+           events), cfg2_instances (the same 1 Mi sites split over NUM_ACCELERATORS=9 instance streams), cfg4a / cfg4b
+           (INPUT_SRC=gen, sink write / discard), cfg5 (1024-taxon tree, 1 Mi sites split over the ranks, dense tips
+           and state-code tips), protein (20 states, strict and FMA) and evaluate (root log-likelihood kernel).
+
+Stand-alone side runs: --workload cfg2 (--buffer-sets 1 for the "same buffers" variant) and --workload protein.
 """
 from __future__ import annotations
 
@@ -46,6 +52,22 @@ BYTES_PER_SITE = 193
 NOMINAL_HBM_GBS = 8000.0
 FALLBACK_HBM_GBS = 6650.0
 SEED = 42
+
+
+def buffer_sets_for(n_per_gpu: int, requested: int = 0) -> int:
+    """cfg2's 192 MiB working set is only ~1.5x L2: rotate buffer sets so every step reads cold data."""
+    return requested if requested > 0 else (1 if n_per_gpu * 128 >= (1 << 30) else 6)
+
+
+def workload_config(workload: str, total_sites: int, world: int, math: str, buffer_sets: int = 0) -> dict:
+    """`config` of the JSON line -- the SAME dict for our arm and for the reference arm (the driver compares them)."""
+    n_max = -(-total_sites // world)
+    sets = buffer_sets_for(n_max, buffer_sets)
+    return {"workload": WORKLOAD_NAME[workload], "total_sites": total_sites, "sites_per_step": total_sites,
+            "n_gpus": world, "partition": "contiguous site ranges, ceil(n/N) rule (reference include.h:181-192)",
+            "math": math, "bytes_per_site": BYTES_PER_SITE,
+            "l2": f"inputs {2 * n_max * 64 * sets >> 20} MiB per GPU in {sets} rotating buffer set(s), far larger than "
+                  "the 126 MB L2: no flush needed between steps"}
 
 
 def load_pkg():
@@ -130,41 +152,41 @@ def cpu_reference_rate(n_sites: int, repeats: int, threads: int, lib: str | None
 
 
 def run_reference_arm(args):
+    """The reference's own CPU plf() over the WHOLE workload per step (same work, same config as our arm), every
+    host thread running the unmodified function on a contiguous site range.  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = min(TOTAL_SITES[args.workload], 16 << 20)
+    total = args.sites or TOTAL_SITES[args.workload]
     import oracle
     ref = oracle.RefOracle() if oracle.RefOracle.available() else None
     kind = "reference" if ref is not None else "port"
     co = None if ref is not None else oracle.COracle()
-    ev, left, right, x1, x2, wgt = host_inputs_tiled(sample)
-    out = np.empty((sample, 16), np.float32)
+    ev, left, right, x1, x2, wgt = host_inputs_tiled(total)
+    out = np.empty((total, 16), np.float32)
 
     def one_step(m):
         if ref is not None:
-            ref.newview(x1[:m], x2[:m], ev, left, right, wgt[:m], nthreads=cores, out=out)
-        else:
-            co.newview(x1[:m], x2[:m], ev, left, right, wgt[:m], nthreads=cores)
+            return ref.newview(x1[:m], x2[:m], ev, left, right, wgt[:m], nthreads=cores, out=out)[1]
+        return co.newview(x1[:m], x2[:m], ev, left, right, wgt[:m], nthreads=cores)[2]
 
     for _ in range(args.warmup):
-        one_step(min(sample, 2 << 20))          # warm-up on a prefix: page-in, thread start-up
+        one_step(min(total, 2 << 20))           # warm-up on a prefix: page-in, thread start-up
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        one_step(sample)
+        inc = one_step(total)
     dt = time.perf_counter() - t0
-    value = sample * args.steps / dt
-    desc = (f"{sample} sites/step of the {TOTAL_SITES[args.workload]}-site workload "
-            f"(host_mem.cpp stimulus, 1Mi-site block tiled), {cores} threads, "
+    assert inc == (total + 3) // 4, "CPU reference produced an unexpected scaler increment"
+    value = total * args.steps / dt
+    desc = (f"the whole {total}-site workload per step (host_mem.cpp stimulus, 1Mi-site block tiled), {cores} threads, "
             f"{'/root/reference/app/src/plf.cpp compiled in place (-O2 -ffp-contract=off)' if kind == 'reference' else 'oracle/plf_oracle.c port'}")
     line = {
         "impl": "reference", "metric": "plf_sites_per_s", "value": value, "unit": "sites/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD_NAME[args.workload], "total_sites": TOTAL_SITES[args.workload],
-                   "sample_sites_per_step": sample},
+        "config": workload_config(args.workload, total, args.gpus, args.math, args.buffer_sets),
         "cpu_baseline": {"value": value, "unit": "sites/s", "cores": cores, "kind": kind, "sample": desc},
         "e2e": {"value": value, "unit": "sites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "hbm_equiv_gbs": value * BYTES_PER_SITE / 1e9,
@@ -211,8 +233,7 @@ def run_b200_arm(args):
     d_ev = torch.from_numpy(ev).to(device)
     d_pl = torch.from_numpy(left).to(device)
     d_pr = torch.from_numpy(right).to(device)
-    # cfg2's 192 MiB working set is only ~1.5x L2: rotate buffer sets so every step reads cold data
-    sets = args.buffer_sets if args.buffer_sets > 0 else (1 if n * 128 >= (1 << 30) else 6)
+    sets = buffer_sets_for(-(-total_sites // world), args.buffer_sets)
     x1 = [torch.empty((n, 16), device=device) for _ in range(sets)]
     x2 = [torch.empty((n, 16), device=device) for _ in range(sets)]
     x3 = [torch.empty((n, 16), device=device) for _ in range(sets)]
@@ -286,9 +307,14 @@ def run_b200_arm(args):
     e2e = run_e2e(pkg, torch, args, local_rank, first, n, total_sites, world, math_mode, barrier,
                   sharding, device, ev, left, right)
 
-    # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------
+    # ---- side workloads: the other BASELINE configs and the section-8f rows, each with its own roofline ----
+    side = None
+    if not args.no_side and args.workload == "cfg3" and (not args.sites or args.side_small):
+        side = run_side(pkg, torch, args, rank, world, local_rank, device, math_mode, barrier, sharding, peak)
+
+    # ---- CPU baseline (rank 0; the other ranks wait at the barrier below) --------------------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         sample = min(total_sites, 16 << 20)
         kind, times = cpu_reference_rate(sample, 3, cores)
@@ -310,12 +336,8 @@ def run_b200_arm(args):
             "metric": "plf_sites_per_s", "value": value, "unit": "sites/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": t_max_ms / K, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD_NAME[args.workload], "total_sites": total_sites,
-                       "sites_per_gpu": n, "partition": "contiguous site ranges, ceil(n/N) rule",
-                       "math": args.math, "kernel": info | {"variant": args.variant},
-                       "l2": f"inputs {2 * n * 64 * sets >> 20} MiB per GPU >> 126 MB L2, "
-                             f"{sets} rotating buffer set(s), no flush needed",
-                       "bytes_per_site": BYTES_PER_SITE},
+            "config": workload_config(args.workload, total_sites, world, args.math, args.buffer_sets),
+            "detail": {"sites_per_gpu": n, "kernel": info | {"variant": args.variant}},
             "hbm_gbs": value * BYTES_PER_SITE / 1e9,
             "hbm_gbs_per_gpu": value * BYTES_PER_SITE / 1e9 / world,
             "frac_of_8TBs_per_gpu": value * BYTES_PER_SITE / 1e9 / world / NOMINAL_HBM_GBS,
@@ -328,7 +350,7 @@ def run_b200_arm(args):
                                           f"{(traffic or {}).get('sites_per_launch')} sites/launch) x {n} sites of this launch; "
                                           + str((traffic or {}).get("note"))) if traffic else None},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_all, "clocks": clocks,
-            "scaler_increment": total_inc,
+            "scaler_increment": total_inc, "side": side,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -416,13 +438,255 @@ def run_e2e(pkg, torch, args, local_rank, first, n, total_sites, world, math_mod
               "pcie_gbs_per_gpu": 193 * cnt0 * e2e_steps / sdt / 1e9,
               "note": "plf_newview_stream over one instance-sized host range per GPU (auto chunks: n/16 clamped to 256 Ki..2 Mi sites, 3 slots)"}
     ctx.close()
+    # Bare-copy yardstick of this box at this N (no kernels): every rank at once moves the same H2D : D2H byte ratio
+    # between pinned host memory and its GPU with plain cudaMemcpyAsync.  The e2e leg cannot be faster than this.
+    p_in, p_out = bufs[0][1], bufs[0][3]                     # instance 0's pinned left / out buffers, reused
+    reps = max(2, int((2 << 30) // max(1, p_in.nbytes)))     # about 2 GiB host->device per rank
+    barrier()
+    psec = pkg.probe_host_link(local_rank, p_in, p_out[: max(1, int(p_in.size * 65 // 128))], reps=reps, pieces=1)
+    psec = sharding.max_over_ranks(psec, device)
+    probe_bytes = reps * (p_in.nbytes + p_out[: max(1, int(p_in.size * 65 // 128))].nbytes)
+    probe_gbs_rank = probe_bytes / psec / 1e9
     for p in frees:
         pkg.host_free(p)
-    return {"value": total_sites * e2e_steps / dt, "unit": "sites/s", "stream": stream,
+    achieved_gbs = (h2d + d2h) * e2e_steps / dt / 1e9
+    link = {"bound": "pcie", "achieved": achieved_gbs * world, "peak": probe_gbs_rank * world, "unit": "GB/s",
+            "frac": achieved_gbs / probe_gbs_rank, "per_gpu_achieved": achieved_gbs, "per_gpu_peak": probe_gbs_rank,
+            "peak_source": f"plf_probe_host_link in this run: {world} rank(s) at once, {reps} rounds of one "
+                           f"{p_in.nbytes >> 20} MiB pinned H2D copy + one {p_in.nbytes * 65 // 128 >> 20} MiB D2H copy "
+                           "(the round trip's 128:65 byte ratio), no kernels, wall clock, max over ranks",
+            "algorithmic_bytes_per_site": 193}
+    return {"value": total_sites * e2e_steps / dt, "unit": "sites/s", "stream": stream, "roofline": link,
             "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
             "instances": inst, "ms_per_step": dt / e2e_steps * 1e3, "host_binding": numa,
             "timing": "host wall clock around plf_write/run/read/wait, barrier + device sync on both sides, max over ranks",
             "pcie_gbs_per_gpu": (h2d + d2h) * e2e_steps / dt / 1e9}
+
+
+# ---------------------------------------------------------------------------------------------
+# side workloads (same run, after the headline): every other BASELINE.json config and the rows SURVEY.md
+# section 8f adds, each timed with CUDA events on its launching stream and given its own roofline
+# ---------------------------------------------------------------------------------------------
+def _roofline(bytes_per_launch, ms, peak, note=None):
+    achieved = bytes_per_launch / (ms * 1e-3) / 1e9
+    r = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+         "algorithmic_bytes": int(bytes_per_launch)}
+    if note:
+        r["note"] = note
+    return r
+
+
+def _stochastic(rng, *shape):
+    """Row-stochastic 4x4 blocks: CLV magnitudes stay bounded up a 1024-taxon tree."""
+    m = rng.random_sample(shape + (4, 4)) + 0.05
+    return (m / m.sum(axis=-1, keepdims=True)).astype(np.float32)
+
+
+def side_cfg2(pkg, torch, device, peak, math_mode, reps=200):
+    """BASELINE configs[1]: one PLF instance, 1 Mi sites, one stream.  K back-to-back launches between TWO events (an
+    event between launches would break the programmatic-dependent-launch chain)."""
+    n = TOTAL_SITES["cfg2"]
+    ev, left, right = stimulus_matrices(SEED)
+    d_ev, d_pl, d_pr = (torch.from_numpy(a).to(device) for a in (ev, left, right))
+    stream = torch.cuda.current_stream().cuda_stream
+    opts = pkg.make_opts(math_mode)
+    out = {}
+    for label, sets in (("cold", 6), ("warm", 1)):
+        x1 = [torch.empty((n, 16), device=device) for _ in range(sets)]
+        x2 = [torch.empty((n, 16), device=device) for _ in range(sets)]
+        x3 = [torch.empty((n, 16), device=device) for _ in range(sets)]
+        sc = [torch.empty(n, dtype=torch.uint8, device=device) for _ in range(sets)]
+        dsum = torch.zeros(1, dtype=torch.int64, device=device)
+        for k in range(sets):
+            pkg.generate_device(x1[k].data_ptr(), x2[k].data_ptr(), 0, n, SEED + k, stream)
+        args = [(x1[k].data_ptr(), x2[k].data_ptr(), x3[k].data_ptr(), sc[k].data_ptr(), d_ev.data_ptr(), d_pl.data_ptr(),
+                 d_pr.data_ptr(), None, n, dsum.data_ptr(), opts, stream) for k in range(sets)]
+        for i in range(2 * sets + 4):
+            pkg.newview_device(*args[i % sets])
+        torch.cuda.synchronize()
+        dsum.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(reps):
+            pkg.newview_device(*args[i % sets])
+        e1.record()
+        issue_us = (time.perf_counter() - t0) / reps * 1e6
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        assert int(dsum.item()) == reps * ((n + 3) // 4), "cfg2: scaler increments do not match the stimulus design"
+        out[label] = {"value": n / (ms * 1e-3), "unit": "sites/s", "us_per_launch": ms * 1e3, "launches": reps,
+                      "buffer_sets": sets, "host_issue_us_per_launch": issue_us,
+                      "roofline": _roofline(BYTES_PER_SITE * n, ms, peak),
+                      "frac_of_8TBs": BYTES_PER_SITE * n / (ms * 1e-3) / 1e9 / NOMINAL_HBM_GBS}
+        del x1, x2, x3, sc
+        torch.cuda.empty_cache()
+    out["workload"] = WORKLOAD_NAME["cfg2"]
+    return out
+
+
+def side_gen(pkg, torch, device, peak, math_mode, n, world, sharding, reps=10):
+    """BASELINE configs[3]: INPUT_SRC=gen analogue -- no CLV is read.  cfg4a writes CLV + scaler (65 B/site), cfg4b
+    folds the outputs into a checksum (no memory traffic: the kernel's pure issue rate)."""
+    x3 = torch.empty((n, 16), device=device)
+    sc = torch.empty(n, dtype=torch.uint8, device=device)
+    dsum = torch.zeros(1, dtype=torch.int64, device=device)
+    chk = torch.zeros(1, dtype=torch.float64, device=device)
+    stream = torch.cuda.current_stream().cuda_stream
+    opts = pkg.make_opts(math_mode)
+    out = {}
+    for label, sink in (("cfg4a_write", pkg.GEN_WRITE), ("cfg4b_discard", pkg.GEN_DISCARD)):
+        a = (x3.data_ptr(), sc.data_ptr(), n, dsum.data_ptr(), chk.data_ptr(), sink, opts, stream)
+        for _ in range(3):
+            pkg.newview_gen_device(*a)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            pkg.newview_gen_device(*a)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = sharding.max_over_ranks(e0.elapsed_time(e1) / reps, device)
+        total = sharding.reduce_scaler_increment(n, device)
+        row = {"value": total / (ms * 1e-3), "unit": "sites/s", "ms_per_launch": ms, "sites_per_gpu": n}
+        if sink == pkg.GEN_WRITE:
+            row["roofline"] = _roofline(65 * n, ms, peak, "writes only: 64 B CLV + 1 scaler byte per site")
+        else:
+            row["roofline"] = None
+            row["note"] = "no memory traffic: arithmetic + vote + reduction only (the sink of s2mm_gen drops the stream)"
+        out[label] = row
+    del x3, sc
+    torch.cuda.empty_cache()
+    return out
+
+
+def side_tree(pkg, torch, device, peak, math_mode, n, first, world, local_rank, sharding, barrier, tips=1024, reps=3):
+    """BASELINE configs[4]: chained newview over a synthetic 1024-taxon tree, 1 Mi sites split over the ranks, per-site
+    scaler counts accumulated up the tree, total all-reduced.  Dense tips (64 B/site) and state-code tips (1 B/site)."""
+    left, right = pkg.balanced_tree(tips)
+    rng = np.random.RandomState(1)
+    ev = _stochastic(rng).reshape(16)
+    pl = _stochastic(rng, tips - 1, 4).reshape(tips - 1, 64)
+    pr = _stochastic(rng, tips - 1, 4).reshape(tips - 1, 64)
+    out = {}
+    for label, codes in (("dense_tips", False), ("code_tips", True)):
+        t = pkg.Tree(left, right, n, device=local_rank, tip_codes=codes)
+        t.set_math(math_mode)
+        if codes:
+            tv = (rng.random_sample((16, 4)) * np.where(np.arange(16)[:, None] % 4 == 0, 1e-10, 1.0)).astype(np.float32)
+            t.write_tip_vector(tv)
+            block = np.random.RandomState(first + 17).randint(0, 16, n + 4096).astype(np.uint8)
+            for tip in range(tips):
+                t.write_tip_codes(tip, block[(tip * 37) % 4096:][:n])
+        else:
+            scratch = torch.empty((n, 16), device=device)
+            for tip in range(tips):      # x1-stream of the generator for even tips, x2-stream for odd ones
+                a, b = (t.tip_ptr(tip), scratch.data_ptr()) if tip % 2 == 0 else (scratch.data_ptr(), t.tip_ptr(tip))
+                pkg.generate_device(a, b, first + tip * 7919, n, 1000 + tip)
+            torch.cuda.synchronize()
+            del scratch
+        t.write_matrices(ev, pl, pr)
+        info = t.info()
+        for _ in range(2):
+            t.run_async()
+        t.wait()
+        times = []
+        for _ in range(reps):
+            barrier()
+            t.run_async()
+            t.wait()
+            times.append(t.last_ms())
+        ms = sharding.max_over_ranks(float(np.median(times)), device)
+        total_scalings = sharding.reduce_scaler_increment(t.total_scalings(), device)
+        total_sites = sharding.reduce_scaler_increment(n, device)
+        lnl = None
+        if not codes:
+            diag = np.exp(-np.linspace(0.0, 1.5, 16)).astype(np.float32)
+            lnl = sharding.reduce_log_likelihood(t.evaluate_root(diag), device)
+        root, cnt = t.read_root(0, min(n, 1024))
+        assert np.isfinite(root).all(), "cfg5: non-finite root CLV"
+        out[label] = {"value": (tips - 1) * total_sites / (ms * 1e-3), "unit": "newview-sites/s", "ms_per_traversal": ms,
+                      "tips": tips, "total_sites": total_sites, "sites_per_gpu": n, "levels": info["levels"],
+                      "device_GiB_per_gpu": info["device_bytes"] / 2 ** 30, "total_scalings": total_scalings,
+                      "root_scaler_count_max": int(cnt.max()), "log_likelihood": lnl,
+                      "roofline": _roofline(info["traversal_bytes"], ms, peak,
+                                            "per GPU; algorithmic bytes = plf_tree_info: 64 B/site per CLV read or written, "
+                                            "1 B/site per code tip read, 4 B/site per count vector read or written")}
+        t.close()
+        torch.cuda.empty_cache()
+    out["workload"] = "BASELINE.json configs[4]: chained PLF over a synthetic 1024-taxon balanced tree, 1Mi sites over N GPUs"
+    return out
+
+
+def side_evaluate(pkg, torch, device, peak, n, world, sharding, reps=10):
+    """Root log-likelihood kernel over the rank's cfg3 shard: 2 CLV reads + 2 count vectors per site."""
+    x1 = torch.empty((n, 16), device=device)
+    x2 = torch.empty((n, 16), device=device)
+    stream = torch.cuda.current_stream().cuda_stream
+    pkg.generate_device(x1.data_ptr(), x2.data_ptr(), 0, n, SEED, stream)
+    c1 = torch.ones(n, dtype=torch.int32, device=device)
+    c2 = torch.zeros(n, dtype=torch.int32, device=device)
+    diag = torch.from_numpy(np.exp(-np.linspace(0.0, 1.5, 16)).astype(np.float32)).to(device)
+    lnl = torch.zeros(reps + 3, dtype=torch.float64, device=device)
+    a = lambda i: (x1.data_ptr(), x2.data_ptr(), c1.data_ptr(), c2.data_ptr(), None, diag.data_ptr(), n,
+                   lnl[i:].data_ptr(), stream)
+    for i in range(3):
+        pkg.evaluate_device(*a(i))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        pkg.evaluate_device(*a(3 + i))
+    e1.record()
+    torch.cuda.synchronize()
+    vals = lnl.cpu().numpy()
+    assert np.isfinite(vals).all() and (vals == vals[0]).all(), "evaluate: the log-likelihood is not reproducible run to run"
+    ms = sharding.max_over_ranks(e0.elapsed_time(e1) / reps, device)
+    total = sharding.reduce_scaler_increment(n, device)
+    del x1, x2, c1, c2
+    torch.cuda.empty_cache()
+    return {"value": total / (ms * 1e-3), "unit": "sites/s", "ms_per_launch": ms, "sites_per_gpu": n,
+            "bitwise_reproducible": True, "log_likelihood_rank0": float(vals[0]),
+            "roofline": _roofline(136 * n, ms, peak, "128 B of CLV + 8 B of scaler counts read per site; fp64 log per site")}
+
+
+def side_protein(pkg, torch, peak, reps=5, n=2 << 20):
+    """STATES=protein: the 20-state newview, strict and FMA, device-resident CLVs."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import protein_bench
+    res = protein_bench.measure(pkg, torch, n, reps, shapes=[(0, 0)], maths=(0, 1), verbose=False)
+    out = {"sites": n, "bytes_per_site": res["bytes_per_site"], "muladd_per_site": res["muladd_per_site"]}
+    for row in res["rows"]:
+        assert row["ok"], "20-state run failed its self-checks"
+        out[row["math"]] = {"value": row["gsites"] * 1e9, "unit": "sites/s", "ms_per_launch": row["ms_mean"],
+                            "tmuladd_per_s": row["tmuladd_per_s"], "kernel": {k: row[k] for k in ("regs", "threads", "smem_bytes")},
+                            "roofline": _roofline(res["bytes_per_site"] * n, row["ms_mean"], peak,
+                                                  "on the HBM / fp32 ridge: 961 B and 4800 multiply-adds per site")}
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_side(pkg, torch, args, rank, world, local_rank, device, math_mode, barrier, sharding, peak):
+    t_start = time.perf_counter()
+    side = {}
+    small = args.side_small
+    first3, n3 = sharding.shard_for_rank((1 << 20) if small else TOTAL_SITES["cfg3"], rank, world)
+    first5, n5 = sharding.shard_for_rank((1 << 14) if small else (1 << 20), rank, world)
+    tips = 64 if small else 1024
+    steps = [("cfg4", lambda: side_gen(pkg, torch, device, peak, math_mode, n3, world, sharding)),
+             ("evaluate", lambda: side_evaluate(pkg, torch, device, peak, n3, world, sharding)),
+             ("cfg5", lambda: side_tree(pkg, torch, device, peak, math_mode, n5, first5, world, local_rank, sharding, barrier,
+                                        tips=tips))]
+    if world == 1:          # single-GPU configurations
+        steps = [("cfg2", lambda: side_cfg2(pkg, torch, device, peak, math_mode, reps=20 if small else 200)),
+                 ("protein", lambda: side_protein(pkg, torch, peak, n=(1 << 17) if small else (2 << 20)))] + steps
+    for name, fn in steps:
+        barrier()
+        t0 = time.perf_counter()
+        side[name] = fn()
+        side[name]["wall_s"] = round(time.perf_counter() - t0, 2)
+    side["wall_s_total"] = round(time.perf_counter() - t_start, 2)
+    side["note"] = ("measured in this run after the headline; CUDA events on the launching stream, max over ranks; "
+                    "roofline.peak = the same measured copy bandwidth as the headline")
+    return side
 
 
 def run_protein_arm(args):
@@ -499,6 +763,8 @@ def main():
     ap.add_argument("--instances", type=int, default=9, help="NUM_ACCELERATORS for the e2e leg")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-side", action="store_true", help="skip the side workloads (cfg2, cfg4, cfg5, protein, evaluate)")
+    ap.add_argument("--side-small", action="store_true", help="side workloads at test sizes (contract test)")
     ap.add_argument("--no-numa-bind", action="store_true", help="N>1: do not pin each rank to its GPU's local CPUs")
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: route everything libraries print on fd 1 (e.g. NCCL's

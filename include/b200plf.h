@@ -329,6 +329,15 @@ int plf_memcpy_d2h(void *dst_host, const void *src_device, size_t bytes, void *s
 int plf_memset_device(void *dst_device, int value, size_t bytes, void *stream);
 int plf_stream_sync(void *stream);
 
+/* Bare host-link probe, the yardstick of the host-buffer path: `reps` rounds of one pinned host->device copy of
+ * h2d_bytes and one device->host copy of d2h_bytes, each cut into `pieces` cudaMemcpyAsync calls, the two directions
+ * on two streams at once, no kernels.  host_in / host_out are pinned host buffers of those sizes (NULL: allocated
+ * and freed inside, untimed); device buffers are internal.  *seconds is the wall time of the timed rounds (one
+ * untimed warm-up round first).  The PLF round trip moves 128 B/site in and 65 B/site out (the reference's own note
+ * on its PCIe limit: README.md:204).                                                                              */
+int plf_probe_host_link(int device, void *host_in, size_t h2d_bytes, void *host_out, size_t d2h_bytes, int reps,
+                        int pieces, double *seconds);
+
 /* Process-wide override of the ring-slot release mechanism (see plf_launch_flags): 1 = fenced everywhere,
  * 0 = data dependency everywhere, -1 = every kernel family's own default (also what PLF_SAFE_RELEASE unset means). */
 int plf_set_release_mode(int mode);

@@ -24,6 +24,7 @@ def test_reference_arm_prints_one_json_line():
     assert d["metric"] == "plf_sites_per_s" and d["unit"] == "sites/s" and d["dtype"] == "f32"
     assert d["value"] > 0 and d["higher_is_better"] is True and d["vs_baseline"] is None
     assert set(d["config"]) >= {"workload"} and "model" not in d["config"]
+    assert d["config"]["sites_per_step"] == d["config"]["total_sites"] == 1 << 20      # same work per step as our arm
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "sites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
@@ -53,7 +54,7 @@ import pytest
 def test_b200_arm_prints_one_complete_json_line():
     """A small run of our arm on the GPU: one JSON line with every key the driver and the judge read."""
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--sites", str(2 << 20), "--steps", "5",
-                        "--warmup", "3", "--e2e-steps", "2"], capture_output=True, text=True, timeout=900)
+                        "--warmup", "3", "--e2e-steps", "2", "--side-small"], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-3000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1, lines
@@ -72,3 +73,13 @@ def test_b200_arm_prints_one_complete_json_line():
     assert d["gpu_launches"] == 5                        # one fused kernel per step, nothing else of ours
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(d["clocks"])
     assert d["scaler_increment"] == (2 << 20) // 4
+    # host-link yardstick beside the end-to-end number
+    er = e["roofline"]
+    assert er["bound"] == "pcie" and er["peak"] > 5 and 0.3 < er["frac"] < 1.2
+    # every other BASELINE config and section-8f row rides in the same line, each with its own roofline
+    side = d["side"]
+    assert {"cfg2", "cfg4", "cfg5", "protein", "evaluate"} <= set(side)
+    for row in (side["cfg2"]["cold"], side["cfg2"]["warm"], side["cfg4"]["cfg4a_write"], side["cfg5"]["dense_tips"],
+                side["cfg5"]["code_tips"], side["protein"]["strict"], side["protein"]["fma"], side["evaluate"]):
+        assert row["value"] > 0 and row["roofline"]["frac"] > 0 and row["roofline"]["algorithmic_bytes"] > 0
+    assert side["cfg4"]["cfg4b_discard"]["value"] > 0 and side["evaluate"]["bitwise_reproducible"] is True

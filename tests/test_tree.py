@@ -195,3 +195,84 @@ def test_dense_tree_rejects_tip_codes(pkg):
             t.write_tip_codes(0, np.zeros(10, np.uint8))
         with pytest.raises(pkg.PlfError):
             t.write_tip_vector(np.zeros(64, np.float32))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE.json configs[4] at its NAMED shape: 1024 taxa.  The site count of the full configuration (1 Mi over
+# 8 GPUs = 131 072 per GPU) is covered twice: every site at n = 4 099 (ragged against all stage sizes), and at
+# 131 072 sites per GPU through oracle-checked slices of device-generated tips.
+# ---------------------------------------------------------------------------------------------------------
+def _stochastic(rng, *shape):
+    m = rng.random_sample(shape + (4, 4)) + 0.05
+    return (m / m.sum(axis=-1, keepdims=True)).astype(np.float32)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", ["balanced", "random"])
+@pytest.mark.parametrize("tip_codes", [False, True])
+def test_cfg5_shape_1024_taxa_every_site(pkg, coracle, shape, tip_codes):
+    n_tips, n = 1024, 4099
+    left, right = pkg.balanced_tree(n_tips) if shape == "balanced" else pkg.random_tree(n_tips, seed=5)
+    rng = np.random.RandomState(1024)
+    ev = rng.random_sample(16).astype(np.float32)
+    pl = _stochastic(rng, n_tips - 1, 4).reshape(n_tips - 1, 64)
+    pr = _stochastic(rng, n_tips - 1, 4).reshape(n_tips - 1, 64)
+    wgt = rng.randint(1, 4, n).astype(np.int32)
+    if tip_codes:
+        codes = rng.randint(0, 16, (n_tips, n)).astype(np.uint8)
+        tip_vector = (rng.random_sample((16, 4)) * 10.0 ** rng.uniform(-6, 0, (16, 1))).astype(np.float32)
+        tips = np.stack([expand_tip_codes(codes[i], tip_vector) for i in range(n_tips)])
+    else:
+        tips = (rng.random_sample((n_tips, n, 16)) * 10.0 ** rng.uniform(-8, 0, (n_tips, n, 1))).astype(np.float32)
+    o_root, o_cnt, o_total = tree_oracle.traverse(coracle, left, right, tips, ev, pl, pr, wgt)
+    assert o_cnt.max() >= 3 and np.isfinite(o_root).all(), "the 1024-taxon stimulus should rescale repeatedly and stay finite"
+    with pkg.Tree(left, right, n, tip_codes=tip_codes) as t:
+        if tip_codes:
+            t.write_tip_vector(tip_vector)
+        for i in range(n_tips):
+            t.write_tip_codes(i, codes[i]) if tip_codes else t.write_tip(i, tips[i])
+        t.write_matrices(ev, pl, pr)
+        t.write_wgt(wgt)
+        for _ in range(2):
+            t.run_async()
+            root, cnt = t.read_root()
+            assert np.array_equal(bits(root), bits(o_root)), first_mismatch(root, o_root)
+            assert np.array_equal(cnt, o_cnt) and t.total_scalings() == o_total
+        info = t.info()
+        assert info["levels"] == (10 if shape == "balanced" else info["levels"]) and info["levels"] >= 10
+
+
+@pytest.mark.gpu
+def test_cfg5_per_gpu_size_slices_match_oracle(pkg, coracle):
+    """1024 taxa x 131 072 sites (one GPU's share of cfg5 on 8 GPUs), tips generated on the device exactly as
+    bench.py's side workload does; three slices (first sites, an unaligned middle run, the last sites) are recomputed
+    by the oracle from the host twin of the generator and compared bit for bit, counts included."""
+    import torch
+    n_tips, n, first = 1024, 131072, 5 * 131072          # rank 5's site range
+    left, right = pkg.balanced_tree(n_tips)
+    rng = np.random.RandomState(1)
+    ev = _stochastic(rng).reshape(16)
+    pl = _stochastic(rng, n_tips - 1, 4).reshape(n_tips - 1, 64)
+    pr = _stochastic(rng, n_tips - 1, 4).reshape(n_tips - 1, 64)
+    slices = [(0, 384), (65519, 419), (n - 257, 257)]
+    with pkg.Tree(left, right, n) as t:
+        scratch = torch.empty((n, 16), device="cuda")
+        for tip in range(n_tips):
+            a, b = (t.tip_ptr(tip), scratch.data_ptr()) if tip % 2 == 0 else (scratch.data_ptr(), t.tip_ptr(tip))
+            pkg.generate_device(a, b, first + tip * 7919, n, 1000 + tip)
+        torch.cuda.synchronize()
+        t.write_matrices(ev, pl, pr)
+        t.run_async()
+        total = t.total_scalings()
+        got = [t.read_root(lo, cnt) for lo, cnt in slices]
+        # the counts of the WHOLE root, for the total
+        _, all_cnt = t.read_root()
+    assert total == int(all_cnt.astype(np.int64).sum()) and all_cnt.max() >= 2
+    for (lo, cnt), (g_root, g_cnt) in zip(slices, got):
+        tips = np.empty((n_tips, cnt, 16), np.float32)
+        for tip in range(n_tips):
+            h1, h2 = pkg.generate_host(first + tip * 7919 + lo, cnt, 1000 + tip)
+            tips[tip] = (h1 if tip % 2 == 0 else h2).reshape(cnt, 16)
+        o_root, o_cnt, _ = tree_oracle.traverse(coracle, left, right, tips, ev, pl, pr, None)
+        assert np.array_equal(bits(g_root), bits(o_root)), (lo, first_mismatch(g_root, o_root))
+        assert np.array_equal(g_cnt, o_cnt), lo
