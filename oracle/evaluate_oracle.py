@@ -1,15 +1,19 @@
 """oracle/evaluate_oracle.py -- root log-likelihood across a branch on the CPU (float64 numpy).
 TEST INFRASTRUCTURE ONLY.
 
-PARITY UNPINNED: this step is not in /root/reference (which stops at newview, app/src/plf.cpp).
-It restates evaluateGTRGAMMA of standard-RAxML (evaluateGenericSpecial.c, the code base the
-reference's plf() derives from, README.md:188-189,207-208) for the reference's CLV layout:
+This step is not in /root/reference (which stops at newview, app/src/plf.cpp), so no reference golden
+vector can exist for it.  It restates evaluateGTRGAMMA of standard-RAxML (evaluateGenericSpecial.c, the
+code base the reference's plf() derives from, README.md:188-189,207-208) for the reference's CLV layout:
 
     term_i = log(0.25 * |sum_{j,k} x1[i,j,k] * x2[i,j,k] * diag[j,k]|) + (cnt1_i + cnt2_i) * log(2^-32)
     lnL    = sum_i wgt_i * term_i
 
-There is no golden vector for it in the reference; the GPU kernel is checked against this
-restatement only (tolerance 1e-9 relative: fp64 on both sides, different summation order)."""
+PARITY: pinned against an INDEPENDENT model instead of a reference vector -- oracle/felsenstein_fp64.py
+(textbook state-space Felsenstein pruning with explicit GTR+Gamma4 transition matrices in float64, itself
+checked against 50-digit mpmath).  tests/test_felsenstein.py chains the pinned newview oracle up a tree,
+applies this function across the root branch and requires the textbook log-likelihood to 1e-6 relative
+(measured 3e-8), including trees that rescale up to 13 times per site; the same test drives the CUDA path.
+The GPU kernel is additionally compared with this restatement directly (1e-9 relative: fp64 on both sides)."""
 from __future__ import annotations
 
 import numpy as np

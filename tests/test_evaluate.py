@@ -1,6 +1,6 @@
-"""Root log-likelihood across a branch -- parity UNPINNED: the reference has no
-such step; the CUDA kernel is checked against oracle/evaluate_oracle.py (RAxML's evaluateGTRGAMMA
-restated), fp64 on both sides, tolerance 1e-9 relative."""
+"""Root log-likelihood across a branch.  The reference has no such step; the CUDA kernel is
+checked here against oracle/evaluate_oracle.py (RAxML's evaluateGTRGAMMA restated), fp64 on both sides, tolerance
+1e-9 relative, and that restatement is pinned to an independent textbook model in tests/test_felsenstein.py."""
 from __future__ import annotations
 
 import numpy as np
