@@ -33,7 +33,7 @@ INPUT_MEM, INPUT_GEN = 0, 1
 MATH_STRICT, MATH_FMA = 0, 1
 GEN_WRITE, GEN_DISCARD = 0, 1
 MARK_BEGIN, MARK_T1, MARK_T2, MARK_END = 0, 1, 2, 3
-LAUNCH_NO_PDL, LAUNCH_FENCED_RELEASE, LAUNCH_DEP_RELEASE = 1, 2, 4
+LAUNCH_NO_PDL, LAUNCH_FENCED_RELEASE, LAUNCH_DEP_RELEASE, LAUNCH_SINGLE_CTA = 1, 2, 4, 8
 
 # Algorithmic HBM bytes per site: read 64 (x1) + 64 (x2), write 64 (x3) + 1 scaler byte.
 BYTES_PER_SITE = 193
@@ -128,6 +128,18 @@ PROTOTYPES = {
     "plf_kernel_info": (_i, [_i, _i] + [ctypes.POINTER(_i)] * 4),
     "plf_launch_count": (ctypes.c_ulonglong, []),
     "plf_set_release_mode": (_i, [_i]),
+    "plf_range_push": (_i, [ctypes.c_char_p]),
+    "plf_range_pop": (_i, []),
+    "plf_multi_create": (_i, [ctypes.POINTER(_vp), ctypes.POINTER(_i), _i, _u, _i, _i]),
+    "plf_multi_destroy": (_i, [_vp]),
+    "plf_multi_last_error": (ctypes.c_char_p, [_vp]),
+    "plf_multi_size": (_i, [_vp]),
+    "plf_multi_ctx": (_vp, [_vp, _i]),
+    "plf_multi_partition": (_i, [_sz, _i, _i, ctypes.POINTER(_sz), ctypes.POINTER(_sz)]),
+    "plf_multi_newview": (_i, [_vp] * 9 + [_sz, ctypes.POINTER(ctypes.c_longlong)]),
+    "plf_multi_reduce": (_i, [_vp, ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_double),
+                              ctypes.POINTER(ctypes.c_longlong), ctypes.POINTER(ctypes.c_double)]),
+    "plf_multi_info": (_i, [_vp, ctypes.POINTER(_i), ctypes.POINTER(_i), ctypes.POINTER(ctypes.c_ulonglong)]),
     "plf_probe_host_link": (_i, [_i, _vp, _sz, _vp, _sz, _i, _i, ctypes.POINTER(ctypes.c_double)]),
 }
 
@@ -298,19 +310,23 @@ class Context:
     objects and run handles (host_mem.cpp:108-157)."""
 
     def __init__(self, device: int = 0, n_instances: int = 1, layout: int = LAYOUT_COMB,
-                 input_src: int = INPUT_MEM):
+                 input_src: int = INPUT_MEM, _borrowed: int | None = None):
         self.lib = load()
-        self._ctx = _vp()
-        _check(self.lib.plf_ctx_create(ctypes.byref(self._ctx), device, n_instances, layout, input_src))
+        self._owned = _borrowed is None
+        if _borrowed is None:
+            self._ctx = _vp()
+            _check(self.lib.plf_ctx_create(ctypes.byref(self._ctx), device, n_instances, layout, input_src))
+        else:
+            self._ctx = _vp(_borrowed)          # a context that belongs to a Multi
         self.device = device
         self.n_instances = n_instances
         self.layout = layout
         self.input_src = input_src
 
     def close(self):
-        if self._ctx:
+        if self._ctx and self._owned:
             self.lib.plf_ctx_destroy(self._ctx)
-            self._ctx = _vp()
+        self._ctx = _vp()
 
     def __enter__(self):
         return self
@@ -458,6 +474,80 @@ class Context:
                   self.elapsed_ms(k, MARK_T2, MARK_END)) for k in range(k_inst)]
             return out, sc, total, t
         return out, sc, total
+
+
+class Multi:
+    """Several GPUs of one box from one process (plf_multi_*): the reference's ceil(n/parts) site split over the GPUs,
+    one Context per GPU, and the final NCCL all-reduce of the scaler increments / log-likelihoods."""
+
+    def __init__(self, devices, n_instances: int = 1, layout: int = LAYOUT_COMB, input_src: int = INPUT_MEM):
+        self.lib = load()
+        self.devices = [int(d) for d in devices]
+        arr = (ctypes.c_int * len(self.devices))(*self.devices)
+        self._m = _vp()
+        rc = self.lib.plf_multi_create(ctypes.byref(self._m), arr, len(self.devices), n_instances, layout, input_src)
+        if rc != 0:
+            raise PlfError(rc, self.lib.plf_multi_last_error(None).decode())
+        self.contexts = [Context(d, n_instances, layout, input_src, _borrowed=self.lib.plf_multi_ctx(self._m, r))
+                         for r, d in enumerate(self.devices)]
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise PlfError(rc, self.lib.plf_multi_last_error(self._m).decode())
+
+    def close(self):
+        if self._m:
+            for c in self.contexts:
+                c.close()
+            self.lib.plf_multi_destroy(self._m)
+            self._m = _vp()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def partition(self, n_sites: int, rank: int):
+        first, cnt = _sz(0), _sz(0)
+        self._ck(self.lib.plf_multi_partition(n_sites, len(self.devices), rank, ctypes.byref(first), ctypes.byref(cnt)))
+        return first.value, cnt.value
+
+    def newview(self, ev, p_left, p_right, x1, x2, wgt=None):
+        """Host arrays in, host arrays out: (x3[n,16], scaler[n], NCCL-reduced scaler increment)."""
+        ev = np.ascontiguousarray(ev, np.float32)
+        pl = np.ascontiguousarray(p_left, np.float32)
+        pr = np.ascontiguousarray(p_right, np.float32)
+        x1 = np.ascontiguousarray(x1, np.float32).reshape(-1, 16)
+        x2 = np.ascontiguousarray(x2, np.float32).reshape(-1, 16)
+        n = x1.shape[0]
+        x3 = np.empty((n, 16), np.float32)
+        sc = np.empty(n, np.uint8)
+        if wgt is not None:
+            wgt = np.ascontiguousarray(wgt, np.int32)
+        inc = ctypes.c_longlong(0)
+        self._ck(self.lib.plf_multi_newview(self._m, _ptr(ev), _ptr(pl), _ptr(pr), _ptr(x1), _ptr(x2), _ptr(x3), _ptr(sc),
+                                            _ptr(wgt), n, ctypes.byref(inc)))
+        return x3, sc, inc.value
+
+    def reduce(self, increments=None, lnl=None):
+        g = len(self.devices)
+        ia = (ctypes.c_longlong * g)(*[int(v) for v in increments]) if increments is not None else None
+        la = (ctypes.c_double * g)(*[float(v) for v in lnl]) if lnl is not None else None
+        it, lt = ctypes.c_longlong(0), ctypes.c_double(0.0)
+        self._ck(self.lib.plf_multi_reduce(self._m, ia, la, ctypes.byref(it), ctypes.byref(lt)))
+        return it.value, lt.value
+
+    def info(self):
+        n, v, r = _i(0), _i(0), ctypes.c_ulonglong(0)
+        self._ck(self.lib.plf_multi_info(self._m, ctypes.byref(n), ctypes.byref(v), ctypes.byref(r)))
+        return {"n_devices": n.value, "nccl_version": v.value, "reductions": r.value}
 
 
 def make_opts(math_mode: int = MATH_STRICT, variant: int = 0, threads: int = 0,

@@ -10,6 +10,8 @@
 #include "plf_kernels.cuh"
 #include "plf_registry.h"
 
+#include <nvtx3/nvToolsExt.h>
+
 #include <atomic>
 #include <map>
 #include <cstdarg>
@@ -107,14 +109,9 @@ int fail(plf_ctx *ctx, int code, const char *fmt, ...)
 // B200 (profiles/r01_sweep.md, "static vs dynamic").
 constexpr int kDefaultVariant = 1432;
 constexpr int kDefaultThreads = 512;
-// Small launches (fewer than kSmallLaunchSites sites) default to a shape of which TWO CTAs fit on an SM (8 consumer
-// warps + 1, 96 registers, 3 stages of 256 sites = 96 KB), so that independent instances (NUM_ACCELERATORS streams,
-// host_mem.cpp:287-325) run side by side instead of queueing behind full-SM CTAs, and with programmatic dependent
-// launch the ramp of a launch overlaps the tail of its predecessor in the stream.  0 disables the rule.
-constexpr size_t kSmallLaunchSites = (size_t)8 << 20;
-constexpr int kSmallVariant = 0;
-constexpr int kSmallThreads = 256;
-
+// One shape for every launch size: at 1 Mi sites per launch (BASELINE configs[1]) the two-CTA-per-SM shapes (8 consumer
+// warps, 96 registers, 96 KB rings: variants 2332, 2334, 2632 with 256 threads) measured within 1 % of this one, serial
+// or spread over nine instance streams (profiles/r02_small_launch.md), so there is no size-dependent rule.
 using plf::KernelSel;
 using plf::NewviewFn;
 
@@ -197,14 +194,8 @@ int resolve_launch(plf_ctx *ctx, const plf_launch_opts *opts, size_t n, KernelSe
     int math = opts ? opts->math_mode : PLF_MATH_STRICT;
     int variant = opts ? opts->variant : 0;
     int thr = opts ? opts->threads_per_block : 0;
-    if (variant == 0 && thr == 0) {
-        const bool small = kSmallVariant != 0 && n < kSmallLaunchSites;
-        variant = small ? kSmallVariant : kDefaultVariant;
-        thr = small ? kSmallThreads : kDefaultThreads;
-    } else {
-        if (variant == 0) variant = kDefaultVariant;
-        if (thr == 0) thr = kDefaultThreads;
-    }
+    if (variant == 0) variant = kDefaultVariant;
+    if (thr == 0) thr = kDefaultThreads;
     int bps = opts ? opts->blocks_per_sm : 0;
     if (math != PLF_MATH_STRICT && math != PLF_MATH_FMA)
         return fail(ctx, PLF_ERR_INVALID, "unknown math mode %d", math);
@@ -221,7 +212,7 @@ int resolve_launch(plf_ctx *ctx, const plf_launch_opts *opts, size_t n, KernelSe
     const size_t blocks_needed = (n + per_iter - 1) / per_iter;
     size_t g = (size_t)sms * (size_t)bps;
     if (g > blocks_needed) g = blocks_needed;
-    if (g == 0) g = 1;
+    if (g == 0 || (opts && (opts->flags & PLF_LAUNCH_SINGLE_CTA))) g = 1;
     *sel = k;
     *grid = (int)g;
     return PLF_OK;
@@ -1167,8 +1158,9 @@ int plf_newview_states_device(int states, const float *x1, const float *x2, floa
         return launch_newview(nullptr, x1, x2, x3, scaler, sc->mats, sc->mats + 16, sc->mats + 80, wgt, n, scaler_sum, opts, st);
     }
     if (opts && opts->ev_per_category) return fail(nullptr, PLF_ERR_INVALID, "ev_per_category is a DNA gen-mode option");
+    const int aa_flags = release_flag(opts, true) | ((opts && (opts->flags & PLF_LAUNCH_SINGLE_CTA)) ? plf::kAaSingleCta : 0);
     int rc = plf::launch_newview_aa(x1, x2, x3, scaler, ev, p_left, p_right, wgt, n, scaler_sum, math,
-                                    opts ? opts->variant : 0, opts ? opts->threads_per_block : 0, st);
+                                    opts ? opts->variant : 0, opts ? opts->threads_per_block : 0, aa_flags, st);
     if (rc == PLF_ERR_INVALID)
         return fail(nullptr, rc, "no 20-state kernel for variant %d / threads %d", opts ? opts->variant : 0,
                     opts ? opts->threads_per_block : 0);
@@ -1247,6 +1239,21 @@ int plf_memset_device(void *dst_device, int value, size_t bytes, void *stream)
 int plf_stream_sync(void *stream)
 {
     PLF_CUDA(nullptr, cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    return PLF_OK;
+}
+
+// NVTX ranges for the hosts (the reference wraps its run loop in xrt::profile::user_range("roundtrip_exec_time"),
+// host_mem.cpp:273,282,395).  NVTX v3 is header-only: without a profiler attached the calls cost a few nanoseconds.
+int plf_range_push(const char *name)
+{
+    if (!name) return fail(nullptr, PLF_ERR_INVALID, "NULL range name");
+    nvtxRangePushA(name);
+    return PLF_OK;
+}
+
+int plf_range_pop(void)
+{
+    nvtxRangePop();
     return PLF_OK;
 }
 

@@ -361,7 +361,7 @@ int aa_kernel_info(int math, int variant, int threads, int *regs, int *block_thr
 // ev / pl / pr are HOST arrays (see include/b200plf.h): the kernel receives them by value, P transposed to [l][k].
 int launch_newview_aa(const float *x1, const float *x2, float *x3, unsigned char *scaler, const float *ev,
                       const float *pl, const float *pr, const int *wgt, size_t n, unsigned long long *scaler_sum,
-                      int math, int variant, int threads, cudaStream_t stream)
+                      int math, int variant, int threads, int flags, cudaStream_t stream)
 {
     const AaSel k = aa_select(math, variant, threads);
     if (!k.fn) return PLF_ERR_INVALID;
@@ -383,8 +383,8 @@ int launch_newview_aa(const float *x1, const float *x2, float *x3, unsigned char
     const size_t tiles = (n + 8 * k.t - 1) / (8 * k.t);
     size_t grid = (tiles + k.warps - 1) / k.warps;
     if (grid > (size_t)sms) grid = sms;
-    k.fn<<<(int)grid, k.warps * 32, smem, stream>>>(m, x1, x2, x3, scaler, wgt, n, scaler_sum,
-                                                    fenced_release(true) ? kFlagFencedRelease : 0);
+    if (flags & kAaSingleCta) grid = 1;
+    k.fn<<<(int)grid, k.warps * 32, smem, stream>>>(m, x1, x2, x3, scaler, wgt, n, scaler_sum, flags & kFlagFencedRelease);
     count_launches(1);
     return cudaGetLastError() == cudaSuccess ? PLF_OK : PLF_ERR_CUDA;
 }

@@ -46,7 +46,8 @@ int launch_evaluate(const float *x1, const float *x2, const int *cnt1, const int
 // 20-state (protein) newview and the S-state stimulus generator (plf_protein.cu); return a plf_status
 int launch_newview_aa(const float *x1, const float *x2, float *x3, unsigned char *scaler, const float *ev,
                       const float *pl, const float *pr, const int *wgt, size_t n, unsigned long long *scaler_sum,
-                      int math, int variant, int threads, cudaStream_t stream);
+                      int math, int variant, int threads, int flags, cudaStream_t stream);
+constexpr int kAaSingleCta = 1 << 16;     // launch flag of launch_newview_aa: one block (stress-test hook); low bits = kernel flags
 int aa_kernel_info(int math, int variant, int threads, int *regs, int *block_threads, size_t *smem, int *tile_sites);
 int launch_generate_states(int states, float *x1, float *x2, size_t first_site, size_t n, uint64_t seed, cudaStream_t stream);
 void generate_states_host(int states, float *x1, float *x2, size_t first_site, size_t n, uint64_t seed);

@@ -11,7 +11,8 @@
 //   * bad arguments are fatal (the reference prints and continues with an uninitialised field);
 //   * the stimulus generator is seeded (PLF_SEED, default 42) so runs are reproducible;
 //   * sizes are 64-bit; the layout comes from the configuration name and unknown names are errors;
-//   * a comma-separated device list spreads the instances round-robin over several GPUs.
+//   * a comma-separated device list spreads the instances round-robin over several GPUs (plf_multi: one context
+//     per GPU, and the kernel-fused scaler increments of the GPUs are summed with one NCCL all-reduce per call).
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -169,13 +170,27 @@ int main(int argc, char *argv[])
     std::cout << bar << std::endl << std::right;
 
     // ---- Init: contexts (acap_info) and device buffers (xrt::bo) --------------------------------
+    plf_multi *multi = nullptr;
+    if (plf_multi_create(&multi, devices.data(), static_cast<int>(devices.size()), cfg.num_accelerators, cfg.layout, PLF_INPUT_MEM) != PLF_OK)
+        die(std::string("plf_multi_create: ") + plf_multi_last_error(nullptr));
     std::vector<plf_ctx *> ctxs;
-    for (int d : devices) {
-        plf_ctx *c = nullptr;
-        check(plf_ctx_create(&c, d, cfg.num_accelerators, cfg.layout, PLF_INPUT_MEM), nullptr, "plf_ctx_create");
+    for (size_t r = 0; r < devices.size(); ++r) {
+        plf_ctx *c = plf_multi_ctx(multi, static_cast<int>(r));
         if (const char *m = std::getenv("PLF_MATH")) check(plf_ctx_set_math(c, std::strcmp(m, "fma") == 0 ? PLF_MATH_FMA : PLF_MATH_STRICT), c, "plf_ctx_set_math");
         ctxs.push_back(c);
     }
+    {
+        int nccl_version = 0;
+        plf_multi_info(multi, nullptr, &nccl_version, nullptr);
+        if (devices.size() > 1) std::cout << "scaler increments of the " << devices.size() << " GPUs are reduced with NCCL " << nccl_version << std::endl;
+    }
+    // per call: sum of the kernel-fused increments of each GPU's instances, then one all-reduce over the GPUs
+    auto reduce_fused = [&](const std::vector<long long> &per_gpu) {
+        long long total = 0;
+        if (plf_multi_reduce(multi, per_gpu.data(), nullptr, &total, nullptr) != PLF_OK)
+            die(std::string("plf_multi_reduce: ") + plf_multi_last_error(multi));
+        return total;
+    };
     std::vector<InstanceSlot> slot(tb.parallel_instances);
     for (unsigned k = 0; k < tb.parallel_instances; ++k) {
         slot[k] = {ctxs[k % ctxs.size()], static_cast<unsigned>(k / ctxs.size())};
@@ -285,8 +300,10 @@ int main(int argc, char *argv[])
 
 #if !defined(NO_INTERMEDIATE_RESULTS) || NO_INTERMEDIATE_RESULTS == 0
     std::vector<TimingData> execution_ms(tb.parallel_instances, TimingData(tb.plf_calls));
+    plf_range_push("roundtrip_exec_time");            // the reference's xrt::profile::user_range (host_mem.cpp:273,282,395)
     for (size_t i = 0; i < tb.plf_calls; ++i) {
         const double call_begin = t.elapsed_ms();
+        std::vector<long long> fused_per_gpu(ctxs.size(), 0);
         for (unsigned k = 0; k < tb.parallel_instances; ++k) enqueue_instance(k, i, true);
         for (unsigned k = 0; k < tb.parallel_instances; ++k) {                 // sync all instances
             plf_ctx *c = slot[k].ctx;
@@ -302,15 +319,19 @@ int main(int argc, char *argv[])
             d.end[i] = d.t2[i] + mh;
             long long fused = 0;
             check(plf_scaler_increment(c, slot[k].local, &fused), c, "plf_scaler_increment");
-            scalerIncrementFused[i] += fused;
+            fused_per_gpu[k % ctxs.size()] += fused;
         }
+        scalerIncrementFused[i] = reduce_fused(fused_per_gpu);
         // host-side scaler reduction, as the reference does it (host_mem.cpp:384-388)
         for (size_t j = 0; j < tb.alignment_sites; ++j) scalerIncrement[i] += static_cast<long long>(scalerVector[i][j]) * wgt[j];
     }
+    plf_range_pop();
 #else
     TimingData execution_ms(tb.plf_calls);
+    plf_range_push("roundtrip_exec_time");
     for (size_t i = 0; i < tb.plf_calls; ++i) {
         execution_ms.begin[i] = t.elapsed_ms();
+        std::vector<long long> fused_per_gpu(ctxs.size(), 0);
         for (unsigned k = 0; k < tb.parallel_instances; ++k) pack(k);             // packing is part of the round trip
         execution_ms.t1[i] = t.elapsed_ms();
         for (unsigned k = 0; k < tb.parallel_instances; ++k) enqueue_instance(k, i, false);
@@ -318,12 +339,14 @@ int main(int argc, char *argv[])
             check(plf_wait(slot[k].ctx, slot[k].local), slot[k].ctx, "plf_wait");
             long long fused = 0;
             check(plf_scaler_increment(slot[k].ctx, slot[k].local, &fused), slot[k].ctx, "plf_scaler_increment");
-            scalerIncrementFused[i] += fused;
+            fused_per_gpu[k % ctxs.size()] += fused;
         }
+        scalerIncrementFused[i] = reduce_fused(fused_per_gpu);
         execution_ms.t2[i] = t.elapsed_ms();
         for (size_t j = 0; j < tb.alignment_sites; ++j) scalerIncrement[i] += static_cast<long long>(scalerVector[i][j]) * wgt[j];
         execution_ms.end[i] = t.elapsed_ms();
     }
+    plf_range_pop();
 #endif
 
     // PLF_DUMP_DIR=<dir>: the whole-run packed inputs and the outputs of call 0 as PLFB files
@@ -414,6 +437,6 @@ int main(int argc, char *argv[])
         plf_host_free(dataLeft[k]);
         plf_host_free(dataRight[k]);
     }
-    for (plf_ctx *c : ctxs) plf_ctx_destroy(c);
+    plf_multi_destroy(multi);
     return exit_code;
 }

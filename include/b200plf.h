@@ -179,7 +179,9 @@ typedef struct plf_launch_opts {
 typedef enum plf_launch_flags {
     PLF_LAUNCH_NO_PDL = 1,          /* do not launch with programmatic stream serialization            */
     PLF_LAUNCH_FENCED_RELEASE = 2,
-    PLF_LAUNCH_DEP_RELEASE = 4
+    PLF_LAUNCH_DEP_RELEASE = 4,
+    PLF_LAUNCH_SINGLE_CTA = 8       /* test hook: the whole launch on ONE block (its ring refills from L2 at full
+                                     * speed -- the worst case for the slot-release race; tests/test_stress.py) */
 } plf_launch_flags;
 
 /* Newview of n sites.  ALL pointers are device pointers on `device`'s current context:
@@ -317,6 +319,34 @@ int plf_states_kernel_info(int states, int math_mode, int variant, int threads_p
                            int *regs_per_thread, int *block_threads, size_t *smem_bytes,
                            int *tile_sites);
 
+/* ---- several GPUs of one box from one host process -----------------------------------------------
+ * The reference scales over independent accelerator instances by contiguous site ranges: ceil(n / parts) sites each,
+ * the last part takes the remainder (app/src/include.h:181-192), and sums the per-instance scaler increments on the
+ * host (app/src/host_mem.cpp:384-388).  plf_multi applies the same rule to the GPUs of a box: one plf_ctx per GPU
+ * (the whole instance API applies to plf_multi_ctx(m, rank)), no data-path exchange between GPUs, and ONE collective:
+ * the final sum of the per-GPU scaler increments (int64) and log-likelihoods (fp64) with ncclAllReduce over
+ * NVLink/NVSwitch.  NCCL is resolved with dlopen("libnccl.so.2") at creation; a one-GPU plf_multi does not need it. */
+typedef struct plf_multi plf_multi;
+int plf_multi_create(plf_multi **multi, const int *devices, int n_devices, unsigned n_instances, int layout, int input_src);
+int plf_multi_destroy(plf_multi *multi);
+const char *plf_multi_last_error(const plf_multi *multi);
+int plf_multi_size(const plf_multi *multi);
+plf_ctx *plf_multi_ctx(plf_multi *multi, int rank);
+/* The reference's split rule for part `part` of `n_parts` (include.h:181-192): first site and site count. */
+int plf_multi_partition(size_t n_sites, int n_parts, int part, size_t *first, size_t *count);
+/* One newview over HOST arrays (the arguments of plf(), plf.h:1-5), the sites partitioned over the GPUs, every GPU
+ * running the streamed path (plf_newview_stream) on its range from its own host thread.  *increment (may be NULL) is the
+ * NCCL-reduced total of the per-GPU scaler increments.  Blocks until x3 / scaler are complete.                      */
+int plf_multi_newview(plf_multi *multi, const float *ev, const float *p_left, const float *p_right, const float *x1,
+                      const float *x2, float *x3, char *scaler, const int *wgt, size_t n_sites, long long *increment);
+/* The optional final reduction for callers that drive the per-GPU contexts themselves: increments[rank] / lnl[rank]
+ * (either may be NULL) are summed over the ranks with one grouped ncclAllReduce per type; every rank's result is read
+ * back and must agree.                                                                                              */
+int plf_multi_reduce(plf_multi *multi, const long long *increments, const double *lnl, long long *increment_total,
+                     double *lnl_total);
+/* Number of GPUs, NCCL version in use (0 for one GPU), number of NCCL reductions issued so far. */
+int plf_multi_info(const plf_multi *multi, int *n_devices, int *nccl_version, unsigned long long *reductions);
+
 /* ---- device memory for callers that own their buffers ------------------------------------------
  * The instance API keeps device memory inside the context (the xrt::bo role).  The *_device entry points
  * (plf_newview_device, plf_newview_states_device, plf_evaluate_device) work on caller-owned device memory;
@@ -328,6 +358,12 @@ int plf_memcpy_h2d(void *dst_device, const void *src_host, size_t bytes, void *s
 int plf_memcpy_d2h(void *dst_host, const void *src_device, size_t bytes, void *stream);
 int plf_memset_device(void *dst_device, int value, size_t bytes, void *stream);
 int plf_stream_sync(void *stream);
+
+/* Named profiler ranges (NVTX) for host code without CUDA headers: the reference brackets its run loop with
+ * xrt::profile::user_range("roundtrip_exec_time") (host_mem.cpp:273,282,395); the hosts here use the same name, so an
+ * nsys / ncu timeline shows the same region.                                                                      */
+int plf_range_push(const char *name);
+int plf_range_pop(void);
 
 /* Bare host-link probe, the yardstick of the host-buffer path: `reps` rounds of one pinned host->device copy of
  * h2d_bytes and one device->host copy of d2h_bytes, each cut into `pieces` cudaMemcpyAsync calls, the two directions
