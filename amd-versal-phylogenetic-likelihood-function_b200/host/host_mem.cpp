@@ -412,7 +412,8 @@ int main(int argc, char *argv[])
     const std::string csv_name = "plf_" + cfg.aie_name + "_" + cfg.pl_name + "_plfs" + std::to_string(tb.plf_calls) + "_alignments" +
                                  std::to_string(tb.alignment_sites) + "_usedgraphs" + std::to_string(tb.parallel_instances) + ".csv";
 #if !defined(NO_INTERMEDIATE_RESULTS) || NO_INTERMEDIATE_RESULTS == 0
-    print_timing_data(execution_ms[0], reference_ms, static_cast<double>(tb.data_size()), total_sites, tb.plf_calls);
+    print_timing_data(execution_ms[0], reference_ms, static_cast<double>(tb.data_size()), total_sites, tb.plf_calls, "B200",
+                      static_cast<double>(tb.alignments_per_instance(0)) * tb.plf_calls);
     if (csv) write_to_csv(csv_name, execution_ms);
 #else
     {

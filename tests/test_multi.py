@@ -77,7 +77,8 @@ def test_multi_two_gpus_shards_and_nccl_totals(pkg, coracle, n):
         incs, lnls = [], []
         for r, ctx in enumerate(m.contexts):
             lo, cnt = m.partition(n, r)
-            g3, gsc, ginc = ctx.newview(ev, left, right, x1[lo:lo + cnt], x2[lo:lo + cnt], wgt[lo:lo + cnt])
+            g3, gsc, ginc = ctx.newview(ev, left, right, x1[lo:lo + cnt], x2[lo:lo + cnt], wgt[lo:lo + cnt],
+                                        instances=3 if cnt >= 9 else 1)
             assert np.array_equal(bits(g3), bits(o3[lo:lo + cnt])), (r, first_mismatch(g3, o3[lo:lo + cnt]))
             assert np.array_equal(gsc, osc[lo:lo + cnt])
             incs.append(ginc)
