@@ -33,6 +33,7 @@ INPUT_MEM, INPUT_GEN = 0, 1
 MATH_STRICT, MATH_FMA = 0, 1
 GEN_WRITE, GEN_DISCARD = 0, 1
 MARK_BEGIN, MARK_T1, MARK_T2, MARK_END = 0, 1, 2, 3
+STATES_DNA, STATES_PROTEIN = 4, 20
 LAUNCH_NO_PDL, LAUNCH_FENCED_RELEASE, LAUNCH_DEP_RELEASE, LAUNCH_SINGLE_CTA = 1, 2, 4, 8
 
 # Algorithmic HBM bytes per site: read 64 (x1) + 64 (x2), write 64 (x3) + 1 scaler byte.
@@ -62,6 +63,8 @@ PROTOTYPES = {
     "plf_device_info": (_i, [_i, ctypes.c_char_p, _sz, ctypes.c_char_p, _sz]),
     "plf_device_from_string": (_i, [ctypes.c_char_p, ctypes.POINTER(_i)]),
     "plf_ctx_create": (_i, [ctypes.POINTER(_vp), _i, _u, _i, _i]),
+    "plf_ctx_create_states": (_i, [ctypes.POINTER(_vp), _i, _u, _i, _i, _i]),
+    "plf_ctx_states": (_i, [_vp]),
     "plf_ctx_destroy": (_i, [_vp]),
     "plf_last_error": (ctypes.c_char_p, [_vp]),
     "plf_ctx_set_math": (_i, [_vp, _i]),
@@ -95,6 +98,7 @@ PROTOTYPES = {
     "plf_generate_host": (_i, [_vp, _vp, _sz, _sz, ctypes.c_uint64]),
     "plf_tree_create": (_i, [ctypes.POINTER(_vp), _i, _u, _vp, _vp, _sz]),
     "plf_tree_create_ex": (_i, [ctypes.POINTER(_vp), _i, _u, _vp, _vp, _sz, _i]),
+    "plf_tree_create_states": (_i, [ctypes.POINTER(_vp), _i, _u, _vp, _vp, _sz, _i, _i]),
     "plf_tree_write_tip_codes": (_i, [_vp, _u, _vp, _sz, _sz]),
     "plf_tree_write_tip_vector": (_i, [_vp, _vp]),
     "plf_tree_destroy": (_i, [_vp]),
@@ -114,6 +118,7 @@ PROTOTYPES = {
     "plf_tree_last_ms": (_i, [_vp, ctypes.POINTER(ctypes.c_float)]),
     "plf_tree_evaluate_root": (_i, [_vp, _vp, ctypes.POINTER(ctypes.c_double)]),
     "plf_evaluate_device": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "plf_evaluate_states_device": (_i, [_i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "plf_newview_states_device": (_i, [_i] + [_vp] * 8 + [_sz, _vp, ctypes.POINTER(LaunchOpts), _vp]),
     "plf_generate_states_device": (_i, [_i, _vp, _vp, _sz, _sz, ctypes.c_uint64, _vp]),
     "plf_generate_states_host": (_i, [_i, _vp, _vp, _sz, _sz, ctypes.c_uint64]),
@@ -131,6 +136,7 @@ PROTOTYPES = {
     "plf_range_push": (_i, [ctypes.c_char_p]),
     "plf_range_pop": (_i, []),
     "plf_multi_create": (_i, [ctypes.POINTER(_vp), ctypes.POINTER(_i), _i, _u, _i, _i]),
+    "plf_multi_create_states": (_i, [ctypes.POINTER(_vp), ctypes.POINTER(_i), _i, _u, _i, _i, _i]),
     "plf_multi_destroy": (_i, [_vp]),
     "plf_multi_last_error": (ctypes.c_char_p, [_vp]),
     "plf_multi_size": (_i, [_vp]),
@@ -252,11 +258,16 @@ class TestbenchInfo:
         """First site of an instance: k * alignments_per_instance(0) (host_mem.cpp:229,290)."""
         return instance * self.alignments_per_instance()
 
+    @property
+    def states(self) -> int:
+        return self.elements_per_alignment // 4
+
     def header_left(self) -> int:
-        return HEADER_COMB
+        """[EV S^2 | P 4S^2] in front of the CLV (80 floats for DNA, 2000 for protein)."""
+        return 5 * self.states * self.states
 
     def header_right(self) -> int:
-        return HEADER_COMB if self.layout == LAYOUT_COMB else HEADER_SEP
+        return self.header_left() if self.layout == LAYOUT_COMB else 4 * self.states * self.states
 
     def instance_active_elements_left(self, instance: int) -> int:
         return self.alignments_per_instance(instance) * self.elements_per_alignment + self.header_left()
@@ -289,15 +300,15 @@ def partition_sites(n: int, parts: int):
 
 
 def pack_left(ev, p_left, x1):
-    """[EV16 | P_left64 | CLV] (host_mem.cpp:231-233)."""
-    return np.concatenate([np.asarray(ev, np.float32).reshape(16),
-                           np.asarray(p_left, np.float32).reshape(64),
+    """[EV S^2 | P_left 4S^2 | CLV] (host_mem.cpp:231-233; S = 4: [EV16 | P64 | CLV]); S from the size of EV."""
+    return np.concatenate([np.asarray(ev, np.float32).reshape(-1),
+                           np.asarray(p_left, np.float32).reshape(-1),
                            np.asarray(x1, np.float32).reshape(-1)])
 
 
 def pack_right(ev, p_right, x2, layout: int = LAYOUT_COMB):
     """Comb: [EV16 | P_right64 | CLV]; Sep: [P_right64 | CLV] (host_mem.cpp:234-241)."""
-    parts = [np.asarray(p_right, np.float32).reshape(64), np.asarray(x2, np.float32).reshape(-1)]
+    parts = [np.asarray(p_right, np.float32).reshape(-1), np.asarray(x2, np.float32).reshape(-1)]
     if layout == LAYOUT_COMB:
         parts.insert(0, np.asarray(ev, np.float32).reshape(16))
     return np.concatenate(parts)
@@ -310,12 +321,13 @@ class Context:
     objects and run handles (host_mem.cpp:108-157)."""
 
     def __init__(self, device: int = 0, n_instances: int = 1, layout: int = LAYOUT_COMB,
-                 input_src: int = INPUT_MEM, _borrowed: int | None = None):
+                 input_src: int = INPUT_MEM, _borrowed: int | None = None, states: int = STATES_DNA):
         self.lib = load()
         self._owned = _borrowed is None
+        self.states = states
         if _borrowed is None:
             self._ctx = _vp()
-            _check(self.lib.plf_ctx_create(ctypes.byref(self._ctx), device, n_instances, layout, input_src))
+            _check(self.lib.plf_ctx_create_states(ctypes.byref(self._ctx), device, n_instances, layout, input_src, states))
         else:
             self._ctx = _vp(_borrowed)          # a context that belongs to a Multi
         self.device = device
@@ -421,7 +433,7 @@ class Context:
         ev = np.ascontiguousarray(ev, np.float32)
         pl = np.ascontiguousarray(p_left, np.float32)
         pr = np.ascontiguousarray(p_right, np.float32)
-        n = n_sites if n_sites is not None else x1.size // 16
+        n = n_sites if n_sites is not None else x1.size // (4 * self.states)
         inc = ctypes.c_longlong(0)
         self._ck(self.lib.plf_newview_stream(self._ctx, _ptr(ev), _ptr(pl), _ptr(pr), _ptr(x1), _ptr(x2), _ptr(x3),
                                              _ptr(scaler), _ptr(wgt), n, chunk_sites, ctypes.byref(inc)))
@@ -434,15 +446,16 @@ class Context:
         (x3[n,16] f32, scaler[n] u8, scaler_increment)."""
         if self.input_src != INPUT_MEM:
             raise PlfError(-4, "Context.newview needs INPUT_SRC=mem")
-        x1 = np.ascontiguousarray(x1, np.float32).reshape(-1, 16)
-        x2 = np.ascontiguousarray(x2, np.float32).reshape(-1, 16)
+        sf = 4 * self.states
+        x1 = np.ascontiguousarray(x1, np.float32).reshape(-1, sf)
+        x2 = np.ascontiguousarray(x2, np.float32).reshape(-1, sf)
         n = x1.shape[0]
         k_inst = self.n_instances if instances is None else instances
-        tb = TestbenchInfo(n, k_inst, layout=self.layout)
+        tb = TestbenchInfo(n, k_inst, layout=self.layout, elements_per_alignment=sf)
         if n and not tb.valid():
             raise PlfError(-1, f"{n} sites cannot be split over {k_inst} instances "
                                "(last instance would be empty)")
-        out = np.empty((n, 16), np.float32)
+        out = np.empty((n, sf), np.float32)
         sc = np.empty(n, np.uint8)
         if wgt is not None:
             wgt = np.ascontiguousarray(wgt, np.int32)
@@ -480,15 +493,18 @@ class Multi:
     """Several GPUs of one box from one process (plf_multi_*): the reference's ceil(n/parts) site split over the GPUs,
     one Context per GPU, and the final NCCL all-reduce of the scaler increments / log-likelihoods."""
 
-    def __init__(self, devices, n_instances: int = 1, layout: int = LAYOUT_COMB, input_src: int = INPUT_MEM):
+    def __init__(self, devices, n_instances: int = 1, layout: int = LAYOUT_COMB, input_src: int = INPUT_MEM,
+                 states: int = STATES_DNA):
         self.lib = load()
         self.devices = [int(d) for d in devices]
+        self.states = states
         arr = (ctypes.c_int * len(self.devices))(*self.devices)
         self._m = _vp()
-        rc = self.lib.plf_multi_create(ctypes.byref(self._m), arr, len(self.devices), n_instances, layout, input_src)
+        rc = self.lib.plf_multi_create_states(ctypes.byref(self._m), arr, len(self.devices), n_instances, layout, input_src,
+                                              states)
         if rc != 0:
             raise PlfError(rc, self.lib.plf_multi_last_error(None).decode())
-        self.contexts = [Context(d, n_instances, layout, input_src, _borrowed=self.lib.plf_multi_ctx(self._m, r))
+        self.contexts = [Context(d, n_instances, layout, input_src, _borrowed=self.lib.plf_multi_ctx(self._m, r), states=states)
                          for r, d in enumerate(self.devices)]
 
     def _ck(self, rc):
@@ -524,10 +540,11 @@ class Multi:
         ev = np.ascontiguousarray(ev, np.float32)
         pl = np.ascontiguousarray(p_left, np.float32)
         pr = np.ascontiguousarray(p_right, np.float32)
-        x1 = np.ascontiguousarray(x1, np.float32).reshape(-1, 16)
-        x2 = np.ascontiguousarray(x2, np.float32).reshape(-1, 16)
+        sf = 4 * self.states
+        x1 = np.ascontiguousarray(x1, np.float32).reshape(-1, sf)
+        x2 = np.ascontiguousarray(x2, np.float32).reshape(-1, sf)
         n = x1.shape[0]
-        x3 = np.empty((n, 16), np.float32)
+        x3 = np.empty((n, sf), np.float32)
         sc = np.empty(n, np.uint8)
         if wgt is not None:
             wgt = np.ascontiguousarray(wgt, np.int32)
@@ -645,7 +662,6 @@ def load_plfb(path: str):
 
 
 # ---- general state count: the reference's STATES knob (4 = DNA, 20 = protein; README.md:36,67,202) ----
-STATES_DNA, STATES_PROTEIN = 4, 20
 
 
 def newview_states_device(states: int, x1, x2, x3, scaler, ev, p_left, p_right, wgt, n: int, scaler_sum,
@@ -734,17 +750,18 @@ class Tree:
     """Post-order traversal of a rooted binary tree on one GPU: every inner node is one fused
     newview of its two children; all nodes of one level run in one launch."""
 
-    def __init__(self, left, right, n_sites: int, device: int = 0, tip_codes: bool = False):
+    def __init__(self, left, right, n_sites: int, device: int = 0, tip_codes: bool = False, states: int = STATES_DNA):
         self.lib = load()
         self.tip_codes = tip_codes
+        self.states = states
         self.left = np.ascontiguousarray(left, np.int32)
         self.right = np.ascontiguousarray(right, np.int32)
         self.n_inner = self.left.size
         self.n_tips = self.n_inner + 1
         self.n_sites = n_sites
         self._t = _vp()
-        rc = self.lib.plf_tree_create_ex(ctypes.byref(self._t), device, self.n_tips, _ptr(self.left),
-                                         _ptr(self.right), n_sites, 1 if tip_codes else 0)
+        rc = self.lib.plf_tree_create_states(ctypes.byref(self._t), device, self.n_tips, _ptr(self.left),
+                                             _ptr(self.right), n_sites, 1 if tip_codes else 0, states)
         if rc != 0:
             raise PlfError(rc, self.lib.plf_tree_last_error(None).decode())
 
@@ -795,9 +812,10 @@ class Tree:
         self._ck(self.lib.plf_tree_write_tip_vector(self._t, _ptr(tv)))
 
     def write_matrices(self, ev, p_left, p_right):
-        ev = np.ascontiguousarray(ev, np.float32).reshape(16)
-        pl = np.ascontiguousarray(p_left, np.float32).reshape(self.n_inner, 64)
-        pr = np.ascontiguousarray(p_right, np.float32).reshape(self.n_inner, 64)
+        S = self.states
+        ev = np.ascontiguousarray(ev, np.float32).reshape(S * S)
+        pl = np.ascontiguousarray(p_left, np.float32).reshape(self.n_inner, 4 * S * S)
+        pr = np.ascontiguousarray(p_right, np.float32).reshape(self.n_inner, 4 * S * S)
         self._ck(self.lib.plf_tree_write_matrices(self._t, _ptr(ev), _ptr(pl), _ptr(pr)))
 
     def write_wgt(self, wgt):
@@ -816,7 +834,7 @@ class Tree:
 
     def read_root(self, first_site: int = 0, n: int | None = None):
         n = self.n_sites - first_site if n is None else n
-        clv = np.empty((n, 16), np.float32)
+        clv = np.empty((n, 4 * self.states), np.float32)
         cnt = np.empty(n, np.int32)
         self._ck(self.lib.plf_tree_read_root(self._t, _ptr(clv), _ptr(cnt), first_site, n))
         return clv, cnt
@@ -840,10 +858,16 @@ class Tree:
 
     def evaluate_root(self, diag) -> float:
         """Log-likelihood of this rank's sites across the root branch (after run_async)."""
-        diag = np.ascontiguousarray(diag, np.float32).reshape(16)
+        diag = np.ascontiguousarray(diag, np.float32).reshape(4 * self.states)
         v = ctypes.c_double(0)
         self._ck(self.lib.plf_tree_evaluate_root(self._t, _ptr(diag), ctypes.byref(v)))
         return v.value
+
+
+def evaluate_states_device(states: int, x1, x2, cnt1, cnt2, wgt, diag, n: int, lnl, stream: int = 0):
+    """lnl (device double) += log-likelihood across a branch for S = 4 or 20 states; all pointers are device ints."""
+    _check(load().plf_evaluate_states_device(states, _ptr(x1), _ptr(x2), _ptr(cnt1), _ptr(cnt2), _ptr(wgt), _ptr(diag), n,
+                                             _ptr(lnl), _ptr(stream)))
 
 
 def evaluate_device(x1, x2, cnt1, cnt2, wgt, diag, n: int, lnl, stream: int = 0):

@@ -55,6 +55,7 @@ struct Instance {
 
 struct plf_ctx {
     int device = 0;
+    int states = 4;                         // STATES knob: 4 (DNA) or 20 (protein)
     int layout = PLF_LAYOUT_COMB;
     int input_src = PLF_INPUT_MEM;
     int math = PLF_MATH_STRICT;
@@ -415,12 +416,33 @@ int gen_pattern_device(plf_ctx *ctx, float **out)
     return PLF_OK;
 }
 
+// 20-state newview on device-resident operands (matrices included): the protein kernel of plf_protein.cu.
+// opts->variant / threads_per_block of a context are DNA tuning knobs and do not apply; math and release flags do.
+int launch_states(plf_ctx *ctx, const float *x1, const float *x2, float *x3, unsigned char *scaler, const float *ev,
+                  const float *pl, const float *pr, const int *wgt, size_t n, unsigned long long *sum,
+                  const plf_launch_opts *opts, cudaStream_t stream)
+{
+    const int math = opts ? opts->math_mode : PLF_MATH_STRICT;
+    int rc = plf::launch_newview_aa(x1, x2, x3, scaler, ev, pl, pr, wgt, n, sum, math, 0, 0, release_flag(opts, true), stream);
+    if (rc != PLF_OK) return fail(ctx, rc, "20-state newview launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return PLF_OK;
+}
+
 struct Mats144 {
     float v[144];
 };
 __global__ void plf_store_mats(const __grid_constant__ Mats144 m, float *__restrict__ dst)
 {
     if (threadIdx.x < 144) dst[threadIdx.x] = m.v[threadIdx.x];
+}
+
+struct Mats3600 {
+    float v[3600];
+};
+__global__ void plf_store_mats_aa(const __grid_constant__ Mats3600 m, float *__restrict__ dst)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 3600) dst[i] = m.v[i];
 }
 
 int check_inst(plf_ctx *ctx, unsigned inst, bool need_alloc, Instance **out)
@@ -436,9 +458,15 @@ int check_inst(plf_ctx *ctx, unsigned inst, bool need_alloc, Instance **out)
     return PLF_OK;
 }
 
+// Sizes in floats for the context's state count S: one site 4S, EV S^2, one child's P 4S^2; the packed buffers are
+// [EV | P | CLV] (left, and right in the Comb layout) or [P | CLV] (right, Sep) -- host_mem.cpp:231-241 with 4 -> S.
+size_t site_floats(const plf_ctx *ctx) { return 4u * (size_t)ctx->states; }
+size_t ev_floats(const plf_ctx *ctx) { return (size_t)ctx->states * ctx->states; }
+size_t p_floats(const plf_ctx *ctx) { return 4u * (size_t)ctx->states * ctx->states; }
+size_t left_header(const plf_ctx *ctx) { return ev_floats(ctx) + p_floats(ctx); }
 size_t right_header(const plf_ctx *ctx)
 {
-    return ctx->layout == PLF_LAYOUT_COMB ? PLF_HEADER_COMB : PLF_HEADER_SEP;
+    return ctx->layout == PLF_LAYOUT_COMB ? left_header(ctx) : p_floats(ctx);
 }
 
 void free_instance(Instance &I)
@@ -546,8 +574,19 @@ int plf_device_from_string(const char *s, int *device)
 
 int plf_ctx_create(plf_ctx **out, int device, unsigned n_instances, int layout, int input_src)
 {
+    return plf_ctx_create_states(out, device, n_instances, layout, input_src, 4);
+}
+
+int plf_ctx_states(const plf_ctx *ctx) { return ctx ? ctx->states : 0; }
+
+int plf_ctx_create_states(plf_ctx **out, int device, unsigned n_instances, int layout, int input_src, int states)
+{
     if (!out) return fail(nullptr, PLF_ERR_INVALID, "NULL ctx out-pointer");
     *out = nullptr;
+    if (states != 4 && states != 20)
+        return fail(nullptr, PLF_ERR_INVALID, "STATES=%d is not supported (4 = DNA, 20 = protein)", states);
+    if (states != 4 && input_src == PLF_INPUT_GEN)
+        return fail(nullptr, PLF_ERR_INVALID, "INPUT_SRC=gen is defined for STATES=DNA only (the gen movers emit a 16-float site pattern)");
     if (n_instances == 0 || n_instances > 1024)
         return fail(nullptr, PLF_ERR_INVALID, "n_instances must be in 1..1024 (got %u)", n_instances);
     if (layout != PLF_LAYOUT_COMB && layout != PLF_LAYOUT_SEP)
@@ -564,6 +603,7 @@ int plf_ctx_create(plf_ctx **out, int device, unsigned n_instances, int layout, 
     plf_ctx *ctx = new (std::nothrow) plf_ctx;
     if (!ctx) return fail(nullptr, PLF_ERR_NOMEM, "out of host memory");
     ctx->device = device;
+    ctx->states = states;
     ctx->layout = layout;
     ctx->input_src = input_src;
     cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
@@ -674,16 +714,16 @@ int plf_instance_alloc(plf_ctx *ctx, unsigned inst, size_t max_sites)
     int rc = check_inst(ctx, inst, false, &I);
     if (rc != PLF_OK) return rc;
     if (max_sites == 0) return fail(ctx, PLF_ERR_INVALID, "max_sites must be > 0");
-    if (max_sites > (SIZE_MAX / 64) - 2) return fail(ctx, PLF_ERR_INVALID, "max_sites too large");
+    if (max_sites > (SIZE_MAX / (site_floats(ctx) * 4)) - 64) return fail(ctx, PLF_ERR_INVALID, "max_sites too large");
     PLF_CUDA(ctx, cudaSetDevice(ctx->device));
     if (I->allocated) {
         PLF_CUDA(ctx, cudaStreamSynchronize(I->stream));
         free_instance(*I);
     }
-    const size_t clv = max_sites * PLF_SITE_FLOATS * sizeof(float);
+    const size_t clv = max_sites * site_floats(ctx) * sizeof(float);
     cudaError_t e = cudaSuccess;
     if (ctx->input_src == PLF_INPUT_MEM) {
-        e = cudaMalloc(&I->d_left, PLF_HEADER_COMB * sizeof(float) + clv);
+        e = cudaMalloc(&I->d_left, left_header(ctx) * sizeof(float) + clv);
         if (e == cudaSuccess) e = cudaMalloc(&I->d_right, right_header(ctx) * sizeof(float) + clv);
     }
     if (e == cudaSuccess) e = cudaMalloc(&I->d_out, clv);
@@ -721,8 +761,8 @@ static int write_packed(plf_ctx *ctx, unsigned inst, bool left, const float *src
         return fail(ctx, PLF_ERR_STATE, "INPUT_SRC=gen instances have no input buffers");
     if (bytes == 0) return PLF_OK;
     if (!src) return fail(ctx, PLF_ERR_INVALID, "NULL host buffer");
-    const size_t header = left ? PLF_HEADER_COMB : right_header(ctx);
-    const size_t cap = (header + I->max_sites * PLF_SITE_FLOATS) * sizeof(float);
+    const size_t header = left ? left_header(ctx) : right_header(ctx);
+    const size_t cap = (header + I->max_sites * site_floats(ctx)) * sizeof(float);
     if (offset > cap || bytes > cap - offset)
         return fail(ctx, PLF_ERR_INVALID, "write of %zu bytes at offset %zu exceeds the %s buffer (%zu bytes)",
                     bytes, offset, left ? "left" : "right", cap);
@@ -784,12 +824,16 @@ int plf_run_async(plf_ctx *ctx, unsigned inst, size_t sites)
     opts.flags = 0;
     if (ctx->input_src == PLF_INPUT_MEM) {
         const float *ev = I->d_left;                                   // mem[0]
-        const float *pl = I->d_left + PLF_EV_FLOATS;                   // mem[1..4]
-        const float *x1 = I->d_left + PLF_HEADER_COMB;                 // mem[5+i]
-        const float *pr = ctx->layout == PLF_LAYOUT_COMB ? I->d_right + PLF_EV_FLOATS : I->d_right;
+        const float *pl = I->d_left + ev_floats(ctx);                  // mem[1..4]
+        const float *x1 = I->d_left + left_header(ctx);                // mem[5+i]
+        const float *pr = ctx->layout == PLF_LAYOUT_COMB ? I->d_right + ev_floats(ctx) : I->d_right;
         const float *x2 = I->d_right + right_header(ctx);
-        rc = launch_newview(ctx, x1, x2, I->d_out, I->d_scaler, ev, pl, pr,
-                            I->use_wgt ? I->d_wgt : nullptr, sites, d_sum, &opts, I->stream);
+        if (ctx->states == 4)
+            rc = launch_newview(ctx, x1, x2, I->d_out, I->d_scaler, ev, pl, pr,
+                                I->use_wgt ? I->d_wgt : nullptr, sites, d_sum, &opts, I->stream);
+        else
+            rc = launch_states(ctx, x1, x2, I->d_out, I->d_scaler, ev, pl, pr, I->use_wgt ? I->d_wgt : nullptr, sites, d_sum,
+                               &opts, I->stream);
     } else {
         PLF_CUDA(ctx, cudaMemsetAsync(I->d_check, 0, sizeof(double), I->stream));
         rc = launch_gen(ctx, I->d_out, I->d_scaler, ctx->d_gen, sites, d_sum, I->d_check,
@@ -818,7 +862,7 @@ int plf_read_out(plf_ctx *ctx, unsigned inst, float *dst, size_t bytes, size_t o
     if (rc != PLF_OK) return rc;
     if (bytes == 0) return PLF_OK;
     if (!dst) return fail(ctx, PLF_ERR_INVALID, "NULL host buffer");
-    const size_t cap = I->max_sites * PLF_SITE_FLOATS * sizeof(float);
+    const size_t cap = I->max_sites * site_floats(ctx) * sizeof(float);
     if (offset > cap || bytes > cap - offset)
         return fail(ctx, PLF_ERR_INVALID, "read of %zu bytes at offset %zu exceeds the out buffer (%zu bytes)",
                     bytes, offset, cap);
@@ -1029,15 +1073,17 @@ int plf_newview_stream(plf_ctx *ctx, const float *ev, const float *p_left, const
         // auto: about 16 chunks per call, between 256 Ki sites (16 MiB per CLV copy: still far above the per-copy
         // overhead) and 2 Mi sites (128 MiB).  The pipeline drains for one chunk's D2H at the end of a call, so a
         // 7 Mi-site call cut into four 2 Mi chunks ran at 2/3 of the PCIe rate; sixteen chunks lose 6 %.
+        const size_t scale = site_floats(ctx) / 16;                   // the limits are byte sizes: 20-state sites are 5x larger
         chunk_sites = (n_sites + 15) / 16;
-        if (chunk_sites < ((size_t)256 << 10)) chunk_sites = (size_t)256 << 10;
-        if (chunk_sites > ((size_t)2 << 20)) chunk_sites = (size_t)2 << 20;
+        if (chunk_sites < ((size_t)256 << 10) / scale) chunk_sites = ((size_t)256 << 10) / scale;
+        if (chunk_sites > ((size_t)2 << 20) / scale) chunk_sites = ((size_t)2 << 20) / scale;
     }
     if (chunk_sites > n_sites && n_sites > 0) chunk_sites = n_sites;
     chunk_sites = (chunk_sites + 255) & ~(size_t)255;
     constexpr int K = plf_ctx::kStreamSlots;
+    const size_t sf = site_floats(ctx), evf = ev_floats(ctx), pf = p_floats(ctx);
     if (!ctx->sd_mats) {
-        PLF_CUDA(ctx, cudaMalloc(&ctx->sd_mats, 144 * sizeof(float)));
+        PLF_CUDA(ctx, cudaMalloc(&ctx->sd_mats, (evf + 2 * pf) * sizeof(float)));
         PLF_CUDA(ctx, cudaMalloc(&ctx->sd_sum, sizeof(unsigned long long)));
         PLF_CUDA(ctx, cudaMallocHost(&ctx->sh_sum, sizeof(unsigned long long)));
         for (int k = 0; k < K; ++k) PLF_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->s_stream[k], cudaStreamNonBlocking));
@@ -1055,7 +1101,7 @@ int plf_newview_stream(plf_ctx *ctx, const float *ev, const float *p_left, const
             ctx->sd_wgt[k] = nullptr;
         }
         ctx->stream_chunk = 0;
-        const size_t clv = chunk_sites * PLF_SITE_FLOATS * sizeof(float);
+        const size_t clv = chunk_sites * sf * sizeof(float);
         for (int k = 0; k < K; ++k) {
             PLF_CUDA(ctx, cudaMalloc(&ctx->sd_x1[k], clv));
             PLF_CUDA(ctx, cudaMalloc(&ctx->sd_x2[k], clv));
@@ -1066,11 +1112,11 @@ int plf_newview_stream(plf_ctx *ctx, const float *ev, const float *p_left, const
         ctx->stream_chunk = chunk_sites;
     }
     cudaStream_t s0 = ctx->s_stream[0];
-    float mats[144];
-    memcpy(mats, ev, 16 * sizeof(float));
-    memcpy(mats + 16, p_left, 64 * sizeof(float));
-    memcpy(mats + 80, p_right, 64 * sizeof(float));
-    PLF_CUDA(ctx, cudaMemcpyAsync(ctx->sd_mats, mats, sizeof mats, cudaMemcpyHostToDevice, s0));
+    std::vector<float> mats(evf + 2 * pf);
+    memcpy(mats.data(), ev, evf * sizeof(float));
+    memcpy(mats.data() + evf, p_left, pf * sizeof(float));
+    memcpy(mats.data() + evf + pf, p_right, pf * sizeof(float));
+    PLF_CUDA(ctx, cudaMemcpyAsync(ctx->sd_mats, mats.data(), mats.size() * sizeof(float), cudaMemcpyHostToDevice, s0));
     PLF_CUDA(ctx, cudaMemsetAsync(ctx->sd_sum, 0, sizeof(unsigned long long), s0));
     PLF_CUDA(ctx, cudaStreamSynchronize(s0));                        // `mats` is a stack temporary
     plf_launch_opts opts;
@@ -1097,15 +1143,19 @@ int plf_newview_stream(plf_ctx *ctx, const float *ev, const float *p_left, const
         const int b = (int)(k % K);
         cudaStream_t st = ctx->s_stream[b];
         const size_t cnt = n_sites - lo < chunk_sites ? n_sites - lo : chunk_sites;
-        const size_t bytes = cnt * PLF_SITE_FLOATS * sizeof(float);
-        PLF_CUDA_DRAIN(cudaMemcpyAsync(ctx->sd_x1[b], x1 + lo * 16, bytes, cudaMemcpyHostToDevice, st));
-        PLF_CUDA_DRAIN(cudaMemcpyAsync(ctx->sd_x2[b], x2 + lo * 16, bytes, cudaMemcpyHostToDevice, st));
+        const size_t bytes = cnt * sf * sizeof(float);
+        PLF_CUDA_DRAIN(cudaMemcpyAsync(ctx->sd_x1[b], x1 + lo * sf, bytes, cudaMemcpyHostToDevice, st));
+        PLF_CUDA_DRAIN(cudaMemcpyAsync(ctx->sd_x2[b], x2 + lo * sf, bytes, cudaMemcpyHostToDevice, st));
         if (wgt) PLF_CUDA_DRAIN(cudaMemcpyAsync(ctx->sd_wgt[b], wgt + lo, cnt * sizeof(int), cudaMemcpyHostToDevice, st));
-        int rc = launch_newview(ctx, ctx->sd_x1[b], ctx->sd_x2[b], ctx->sd_x3[b], ctx->sd_sc[b], ctx->sd_mats,
-                                ctx->sd_mats + 16, ctx->sd_mats + 80, wgt ? ctx->sd_wgt[b] : nullptr, cnt, ctx->sd_sum,
-                                &opts, st);
+        int rc = ctx->states == 4
+                     ? launch_newview(ctx, ctx->sd_x1[b], ctx->sd_x2[b], ctx->sd_x3[b], ctx->sd_sc[b], ctx->sd_mats,
+                                      ctx->sd_mats + evf, ctx->sd_mats + evf + pf, wgt ? ctx->sd_wgt[b] : nullptr, cnt,
+                                      ctx->sd_sum, &opts, st)
+                     : launch_states(ctx, ctx->sd_x1[b], ctx->sd_x2[b], ctx->sd_x3[b], ctx->sd_sc[b], ctx->sd_mats,
+                                     ctx->sd_mats + evf, ctx->sd_mats + evf + pf, wgt ? ctx->sd_wgt[b] : nullptr, cnt,
+                                     ctx->sd_sum, &opts, st);
         if (rc != PLF_OK) return drain(rc);
-        PLF_CUDA_DRAIN(cudaMemcpyAsync(x3 + lo * 16, ctx->sd_x3[b], bytes, cudaMemcpyDeviceToHost, st));
+        PLF_CUDA_DRAIN(cudaMemcpyAsync(x3 + lo * sf, ctx->sd_x3[b], bytes, cudaMemcpyDeviceToHost, st));
         if (scaler) PLF_CUDA_DRAIN(cudaMemcpyAsync(scaler + lo, ctx->sd_sc[b], cnt, cudaMemcpyDeviceToHost, st));
     }
 #undef PLF_CUDA_DRAIN
@@ -1118,11 +1168,19 @@ int plf_newview_stream(plf_ctx *ctx, const float *ev, const float *p_left, const
 int plf_evaluate_device(const float *x1, const float *x2, const int *cnt1, const int *cnt2, const int *wgt,
                         const float *diag, size_t n, double *lnl, void *stream)
 {
+    return plf_evaluate_states_device(4, x1, x2, cnt1, cnt2, wgt, diag, n, lnl, stream);
+}
+
+int plf_evaluate_states_device(int states, const float *x1, const float *x2, const int *cnt1, const int *cnt2, const int *wgt,
+                               const float *diag, size_t n, double *lnl, void *stream)
+{
+    if (states != 4 && states != 20)
+        return fail(nullptr, PLF_ERR_INVALID, "STATES=%d is not supported (4 = DNA, 20 = protein)", states);
     if (n == 0) return PLF_OK;
     if (!x1 || !x2 || !diag || !lnl) return fail(nullptr, PLF_ERR_INVALID, "evaluate: NULL device pointer");
     if (((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)diag) & 15u)
         return fail(nullptr, PLF_ERR_INVALID, "evaluate: CLV / diag pointers must be 16-byte aligned");
-    int rc = plf::launch_evaluate(x1, x2, cnt1, cnt2, wgt, diag, n, lnl, static_cast<cudaStream_t>(stream));
+    int rc = plf::launch_evaluate(states, x1, x2, cnt1, cnt2, wgt, diag, n, lnl, static_cast<cudaStream_t>(stream));
     if (rc != PLF_OK) return fail(nullptr, rc, "evaluate kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     return PLF_OK;
 }
@@ -1159,8 +1217,21 @@ int plf_newview_states_device(int states, const float *x1, const float *x2, floa
     }
     if (opts && opts->ev_per_category) return fail(nullptr, PLF_ERR_INVALID, "ev_per_category is a DNA gen-mode option");
     const int aa_flags = release_flag(opts, true) | ((opts && (opts->flags & PLF_LAUNCH_SINGLE_CTA)) ? plf::kAaSingleCta : 0);
-    int rc = plf::launch_newview_aa(x1, x2, x3, scaler, ev, p_left, p_right, wgt, n, scaler_sum, math,
-                                    opts ? opts->variant : 0, opts ? opts->threads_per_block : 0, aa_flags, st);
+    // HOST matrices: by value into the stream's staging record (as for S = 4), then the kernel reads device memory
+    plf::StreamScratch *sc = nullptr;
+    int rc = plf::stream_scratch(st, &sc);
+    if (rc != PLF_OK) return fail(nullptr, rc, "per-stream scratch allocation failed");
+    {
+        Mats3600 m;
+        memcpy(m.v, ev, 400 * sizeof(float));
+        memcpy(m.v + 400, p_left, 1600 * sizeof(float));
+        memcpy(m.v + 2000, p_right, 1600 * sizeof(float));
+        plf_store_mats_aa<<<4, 1024, 0, st>>>(m, sc->mats);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        PLF_CUDA(nullptr, cudaGetLastError());
+    }
+    rc = plf::launch_newview_aa(x1, x2, x3, scaler, sc->mats, sc->mats + 400, sc->mats + 2000, wgt, n, scaler_sum, math,
+                                opts ? opts->variant : 0, opts ? opts->threads_per_block : 0, aa_flags, st);
     if (rc == PLF_ERR_INVALID)
         return fail(nullptr, rc, "no 20-state kernel for variant %d / threads %d", opts ? opts->variant : 0,
                     opts ? opts->threads_per_block : 0);

@@ -6,6 +6,7 @@
 //   lnL = sum_i wgt[i] * ( log(0.25 * | sum_{j,k} x1[i,j,k] * x2[i,j,k] * diag[j,k] |)
 //                          + (cnt1[i] + cnt2[i]) * log(2^-32) )
 //
+// for S = 4 (DNA) or S = 20 (protein) states per category k, four categories j.
 // x1, x2 are the CLVs at the two ends of the branch (eigen-space, as newview leaves them), diag[j,k]
 // = exp(lambda_k * rate_j * t) for the branch, cnt1/cnt2 the accumulated per-site scaler counts.
 // One thread per (site, category) as in the newview kernels: a 128-bit load per child, four fp64
@@ -23,46 +24,55 @@
 namespace plf {
 
 constexpr int kEvalThreads = 256;
-constexpr int kEvalUnroll = 4;
 
-__global__ void __launch_bounds__(kEvalThreads, 3)
+// S states per category (4: DNA, one 128-bit load per child and element; 20: protein, five), U independent
+// (site, category) elements per thread and iteration.  diag is [category][state], 4*S floats.
+template <int S, int U>
+__global__ void __launch_bounds__(kEvalThreads, S == 4 ? 3 : 2)
 plf_evaluate_kernel(const float4 *__restrict__ x1, const float4 *__restrict__ x2,
                     const int *__restrict__ cnt1, const int *__restrict__ cnt2,
                     const int *__restrict__ wgt, const float *__restrict__ diag, size_t n,
                     double *__restrict__ lnl, StreamScratch *__restrict__ scratch)
 {
+    constexpr int Q = S / 4;                    // 128-bit words per (site, category)
     const int lane = threadIdx.x & 31;
     const int cat = lane & 3;
-    const float4 dg = __ldg(reinterpret_cast<const float4 *>(diag) + cat);
-    const double d0 = dg.x, d1 = dg.y, d2 = dg.z, d3 = dg.w;
+    float4 dg[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) dg[q] = __ldg(reinterpret_cast<const float4 *>(diag) + cat * Q + q);
     const double log_min = -32.0 * 0.69314718055994530942;        // log(2^-32)
-    const size_t n_vec = n * 4;
+    const size_t n_vec = n * 4;                 // (site, category) elements
     const size_t n_pad = (n_vec + 31) & ~(size_t)31;   // whole warps: the 4 lanes of a site stay together
     const size_t stride = (size_t)gridDim.x * kEvalThreads;
     double acc = 0.0;
-    // kEvalUnroll independent (site, category) elements per thread and iteration: all 2*kEvalUnroll 128-bit loads are
-    // issued before the first use, so a thread keeps 128 B in flight instead of 32 (the kernel is latency-bound
-    // otherwise: 5.3 TB/s with one element per iteration).
-    for (size_t v0 = (size_t)blockIdx.x * kEvalThreads + threadIdx.x; v0 < n_pad; v0 += kEvalUnroll * stride) {
-        float4 a[kEvalUnroll], b[kEvalUnroll];
-        bool live[kEvalUnroll];
+    // All 2*U*Q 128-bit loads of an iteration are issued before the first use, so a DNA thread keeps 128 B in flight
+    // instead of 32 (the kernel is latency-bound otherwise: 5.3 TB/s with one element per iteration).
+    for (size_t v0 = (size_t)blockIdx.x * kEvalThreads + threadIdx.x; v0 < n_pad; v0 += U * stride) {
+        float4 a[U][Q], b[U][Q];
+        bool live[U];
 #pragma unroll
-        for (int u = 0; u < kEvalUnroll; ++u) {
+        for (int u = 0; u < U; ++u) {
             const size_t v = v0 + u * stride;
             live[u] = v < n_vec;
             if (live[u]) {
-                a[u] = ld_stream(x1 + v);
-                b[u] = ld_stream(x2 + v);
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    a[u][q] = ld_stream(x1 + v * Q + q);
+                    b[u][q] = ld_stream(x2 + v * Q + q);
+                }
             }
         }
 #pragma unroll
-        for (int u = 0; u < kEvalUnroll; ++u) {
+        for (int u = 0; u < U; ++u) {
             const size_t v = v0 + u * stride;
             if (v >= n_pad) break;                      // warp-uniform: n_pad and the strides are multiples of 32
             double t = 0.0;
-            if (live[u])
-                t = (double)a[u].x * (double)b[u].x * d0 + (double)a[u].y * (double)b[u].y * d1 +
-                    (double)a[u].z * (double)b[u].z * d2 + (double)a[u].w * (double)b[u].w * d3;
+            if (live[u]) {
+#pragma unroll
+                for (int q = 0; q < Q; ++q)
+                    t += (double)a[u][q].x * (double)b[u][q].x * (double)dg[q].x + (double)a[u][q].y * (double)b[u][q].y * (double)dg[q].y +
+                         (double)a[u][q].z * (double)b[u][q].z * (double)dg[q].z + (double)a[u][q].w * (double)b[u][q].w * (double)dg[q].w;
+            }
             t += __shfl_xor_sync(0xffffffffu, t, 1);
             t += __shfl_xor_sync(0xffffffffu, t, 2);
             if (live[u] && cat == 0) {
@@ -109,24 +119,34 @@ plf_evaluate_kernel(const float4 *__restrict__ x1, const float4 *__restrict__ x2
     }
 }
 
-int launch_evaluate(const float *x1, const float *x2, const int *cnt1, const int *cnt2, const int *wgt,
+template <int S, int U>
+static int launch_evaluate_t(const float *x1, const float *x2, const int *cnt1, const int *cnt2, const int *wgt,
+                             const float *diag, size_t n, double *lnl, cudaStream_t stream, int sms)
+{
+    constexpr int bps = S == 4 ? 3 : 2;
+    size_t grid = (n * 4 + kEvalThreads * U - 1) / (kEvalThreads * U);
+    if (grid > (size_t)sms * bps) grid = (size_t)sms * bps;
+    if (grid > (size_t)kEvalMaxBlocks) grid = kEvalMaxBlocks;
+    if (grid == 0) return PLF_OK;
+    StreamScratch *scratch = nullptr;
+    if (int rc = stream_scratch(stream, &scratch)) return rc;
+    plf_evaluate_kernel<S, U><<<(int)grid, kEvalThreads, 0, stream>>>(reinterpret_cast<const float4 *>(x1),
+                                                                      reinterpret_cast<const float4 *>(x2), cnt1, cnt2, wgt,
+                                                                      diag, n, lnl, scratch);
+    count_launches(1);
+    return cudaGetLastError() == cudaSuccess ? PLF_OK : PLF_ERR_CUDA;
+}
+
+int launch_evaluate(int states, const float *x1, const float *x2, const int *cnt1, const int *cnt2, const int *wgt,
                     const float *diag, size_t n, double *lnl, cudaStream_t stream)
 {
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess ||
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
         return PLF_ERR_CUDA;
-    size_t grid = (n * 4 + kEvalThreads * kEvalUnroll - 1) / (kEvalThreads * kEvalUnroll);
-    if (grid > (size_t)sms * 3) grid = (size_t)sms * 3;
-    if (grid > (size_t)kEvalMaxBlocks) grid = kEvalMaxBlocks;
-    if (grid == 0) return PLF_OK;
-    StreamScratch *scratch = nullptr;
-    if (int rc = stream_scratch(stream, &scratch)) return rc;
-    plf_evaluate_kernel<<<(int)grid, kEvalThreads, 0, stream>>>(reinterpret_cast<const float4 *>(x1),
-                                                                reinterpret_cast<const float4 *>(x2), cnt1, cnt2,
-                                                                wgt, diag, n, lnl, scratch);
-    count_launches(1);
-    return cudaGetLastError() == cudaSuccess ? PLF_OK : PLF_ERR_CUDA;
+    if (states == 4) return launch_evaluate_t<4, 4>(x1, x2, cnt1, cnt2, wgt, diag, n, lnl, stream, sms);
+    if (states == 20) return launch_evaluate_t<20, 1>(x1, x2, cnt1, cnt2, wgt, diag, n, lnl, stream, sms);
+    return PLF_ERR_INVALID;
 }
 
 }  // namespace plf

@@ -146,6 +146,12 @@ int plf_multi_partition(size_t n_sites, int n_parts, int part, size_t *first, si
 
 int plf_multi_create(plf_multi **out, const int *devices, int n_devices, unsigned n_instances, int layout, int input_src)
 {
+    return plf_multi_create_states(out, devices, n_devices, n_instances, layout, input_src, 4);
+}
+
+int plf_multi_create_states(plf_multi **out, const int *devices, int n_devices, unsigned n_instances, int layout, int input_src,
+                            int states)
+{
     if (!out) return mfail(nullptr, PLF_ERR_INVALID, "NULL out-pointer");
     *out = nullptr;
     if (!devices || n_devices < 1 || n_devices > 64) return mfail(nullptr, PLF_ERR_INVALID, "need 1..64 devices");
@@ -163,7 +169,7 @@ int plf_multi_create(plf_multi **out, const int *devices, int n_devices, unsigne
     };
     for (int r = 0; r < n_devices; ++r) {
         plf_ctx *c = nullptr;
-        int rc = plf_ctx_create(&c, devices[r], n_instances, layout, input_src);
+        int rc = plf_ctx_create_states(&c, devices[r], n_instances, layout, input_src, states);
         if (rc != PLF_OK) return bail(mfail(nullptr, rc, "rank %d (device %d): %s", r, devices[r], plf_last_error(nullptr)));
         m->ctx.push_back(c);
         cudaStream_t s = nullptr;
@@ -278,7 +284,8 @@ int plf_multi_newview(plf_multi *m, const float *ev, const float *p_left, const 
         size_t first = 0, cnt = 0;
         plf_multi_partition(n_sites, g, r, &first, &cnt);
         if (cnt == 0) return;
-        rc[r] = plf_newview_stream(m->ctx[r], ev, p_left, p_right, x1 + first * 16, x2 + first * 16, x3 + first * 16,
+        const size_t sf = 4u * (size_t)plf_ctx_states(m->ctx[r]);
+        rc[r] = plf_newview_stream(m->ctx[r], ev, p_left, p_right, x1 + first * sf, x2 + first * sf, x3 + first * sf,
                                    scaler ? scaler + first : nullptr, wgt ? wgt + first : nullptr, cnt, 0, &inc[r]);
         if (rc[r] != PLF_OK) err[r] = plf_last_error(m->ctx[r]);
     };

@@ -148,12 +148,9 @@ __device__ __forceinline__ void aa_backtransform(const float *__restrict__ ev_s,
     }
 }
 
-// The three matrices as they travel to the device: a kernel argument (14.4 KB by value, constant bank 0).
-struct alignas(16) AaMats {
-    float pl[4][kAaMat];      // [category][l][k]  (transposed on the host)
-    float pr[4][kAaMat];
-    float ev[kAaMat];         // [k][l]
-};
+// The three matrices are DEVICE arrays in the reference's layouts (EV [k][l], P [category][k][l]): the head of an
+// instance's packed buffers, a tree's per-node matrices, or the stream's staging record for host-matrix callers.  Every
+// block copies them into shared memory once (P transposed to [l][k] on the way): 14.4 KB per block, L2-resident.
 
 __host__ __device__ constexpr size_t aa_bar_offset() { return (size_t)(8 * kAaMatPitch + kAaMat) * sizeof(float); }           // 14528
 __host__ __device__ constexpr size_t aa_tile_offset(int warps) { return (aa_bar_offset() + (size_t)warps * 2 * sizeof(uint64_t) + 127) & ~(size_t)127; }
@@ -164,9 +161,11 @@ __host__ __device__ constexpr size_t aa_smem_bytes(int t, int warps)
 
 template <class M, int T, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1)
-plf_newview_aa(const __grid_constant__ AaMats mats, const float *__restrict__ x1, const float *__restrict__ x2,
+plf_newview_aa(const float *__restrict__ ev, const float *__restrict__ pl, const float *__restrict__ pr,
+               const float *__restrict__ x1, const float *__restrict__ x2,
                float *__restrict__ x3, unsigned char *__restrict__ scaler, const int *__restrict__ wgt, size_t n,
-               unsigned long long *__restrict__ scaler_sum, int flags)
+               unsigned long long *__restrict__ scaler_sum, int flags, const int *__restrict__ cnt1,
+               const int *__restrict__ cnt2, int *__restrict__ cnt3)
 {
     constexpr int TILE = 8 * T;                                   // sites per warp round
     constexpr int TILE_FLOATS = TILE * kAaSite;
@@ -181,13 +180,13 @@ plf_newview_aa(const __grid_constant__ AaMats mats, const float *__restrict__ x1
     float *my_x2 = my_x1 + TILE_FLOATS;
     uint64_t *bar1 = bars + 2 * warp, *bar2 = bar1 + 1;
 
-    // prologue: matrices from the argument into shared memory (P arrives transposed to [l][k]), barriers
+    // prologue: matrices from global into shared memory, P transposed to [l][k]; barriers
     for (int idx = threadIdx.x; idx < 4 * kAaMat; idx += WARPS * 32) {
-        const int j = idx / kAaMat, rem = idx - j * kAaMat;
-        s_pl[j * kAaMatPitch + rem] = mats.pl[j][rem];
-        s_pr[j * kAaMatPitch + rem] = mats.pr[j][rem];
+        const int j = idx / kAaMat, rem = idx - j * kAaMat, k = rem / kAaStates, l = rem - k * kAaStates;
+        s_pl[j * kAaMatPitch + l * kAaStates + k] = __ldg(pl + idx);
+        s_pr[j * kAaMatPitch + l * kAaStates + k] = __ldg(pr + idx);
     }
-    for (int idx = threadIdx.x; idx < kAaMat; idx += WARPS * 32) s_ev[idx] = mats.ev[idx];
+    for (int idx = threadIdx.x; idx < kAaMat; idx += WARPS * 32) s_ev[idx] = __ldg(ev + idx);
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2 * WARPS; ++i) mbar_init(bars + i, 1);
         mbar_fence_init();
@@ -269,6 +268,7 @@ plf_newview_aa(const __grid_constant__ AaMats mats, const float *__restrict__ x1
             const size_t site = s0 + lane;
             if (site < n) {
                 if (scaler) scaler[site] = scaled ? 1 : 0;
+                if (cnt3) cnt3[site] = (cnt1 ? __ldg(cnt1 + site) : 0) + (cnt2 ? __ldg(cnt2 + site) : 0) + (scaled ? 1 : 0);
                 if (scaled) my_sum += wgt ? (unsigned long long)(long long)wgt[site] : 1ull;
             }
         }
@@ -314,8 +314,8 @@ plf_generate_states_kernel(float4 *__restrict__ x1, float4 *__restrict__ x2, uin
 
 namespace {
 
-using AaFn = void (*)(const AaMats, const float *, const float *, float *, unsigned char *, const int *, size_t,
-                      unsigned long long *, int);
+using AaFn = void (*)(const float *, const float *, const float *, const float *, const float *, float *, unsigned char *,
+                      const int *, size_t, unsigned long long *, int, const int *, const int *, int *);
 struct AaSel {
     AaFn fn = nullptr;
     int t = 0, warps = 0;
@@ -358,10 +358,12 @@ int aa_kernel_info(int math, int variant, int threads, int *regs, int *block_thr
     return PLF_OK;
 }
 
-// ev / pl / pr are HOST arrays (see include/b200plf.h): the kernel receives them by value, P transposed to [l][k].
+// ev / pl / pr are DEVICE arrays in the reference's layouts; cnt1 / cnt2 / cnt3 are optional per-site scaler counts of
+// the children and of the result (chained newview over a tree), NULL otherwise.
 int launch_newview_aa(const float *x1, const float *x2, float *x3, unsigned char *scaler, const float *ev,
                       const float *pl, const float *pr, const int *wgt, size_t n, unsigned long long *scaler_sum,
-                      int math, int variant, int threads, int flags, cudaStream_t stream)
+                      int math, int variant, int threads, int flags, cudaStream_t stream, const int *cnt1, const int *cnt2,
+                      int *cnt3)
 {
     const AaSel k = aa_select(math, variant, threads);
     if (!k.fn) return PLF_ERR_INVALID;
@@ -370,21 +372,14 @@ int launch_newview_aa(const float *x1, const float *x2, float *x3, unsigned char
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
         return PLF_ERR_CUDA;
     if (n == 0) return PLF_OK;
-    AaMats m;
-    for (int j = 0; j < 4; ++j)
-        for (int kk = 0; kk < kAaStates; ++kk)
-            for (int l = 0; l < kAaStates; ++l) {
-                m.pl[j][l * kAaStates + kk] = pl[(j * kAaStates + kk) * kAaStates + l];
-                m.pr[j][l * kAaStates + kk] = pr[(j * kAaStates + kk) * kAaStates + l];
-            }
-    for (int i = 0; i < kAaMat; ++i) m.ev[i] = ev[i];
     const size_t smem = aa_smem_bytes(k.t, k.warps);
     if (cudaFuncSetAttribute(k.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return PLF_ERR_CUDA;
     const size_t tiles = (n + 8 * k.t - 1) / (8 * k.t);
     size_t grid = (tiles + k.warps - 1) / k.warps;
     if (grid > (size_t)sms) grid = sms;
     if (flags & kAaSingleCta) grid = 1;
-    k.fn<<<(int)grid, k.warps * 32, smem, stream>>>(m, x1, x2, x3, scaler, wgt, n, scaler_sum, flags & kFlagFencedRelease);
+    k.fn<<<(int)grid, k.warps * 32, smem, stream>>>(ev, pl, pr, x1, x2, x3, scaler, wgt, n, scaler_sum, flags & kFlagFencedRelease,
+                                                    cnt1, cnt2, cnt3);
     count_launches(1);
     return cudaGetLastError() == cudaSuccess ? PLF_OK : PLF_ERR_CUDA;
 }

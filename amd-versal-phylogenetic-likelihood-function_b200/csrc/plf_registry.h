@@ -40,13 +40,14 @@ KernelSel select_tma_dyn_strict(int u, int d, int b, int threads);
 KernelSel select_tma_dyn_fma(int u, int d, int b, int threads);
 
 // root log-likelihood kernel (plf_evaluate.cu); returns a plf_status
-int launch_evaluate(const float *x1, const float *x2, const int *cnt1, const int *cnt2, const int *wgt,
+int launch_evaluate(int states, const float *x1, const float *x2, const int *cnt1, const int *cnt2, const int *wgt,
                     const float *diag, size_t n, double *lnl, cudaStream_t stream);
 
 // 20-state (protein) newview and the S-state stimulus generator (plf_protein.cu); return a plf_status
 int launch_newview_aa(const float *x1, const float *x2, float *x3, unsigned char *scaler, const float *ev,
                       const float *pl, const float *pr, const int *wgt, size_t n, unsigned long long *scaler_sum,
-                      int math, int variant, int threads, int flags, cudaStream_t stream);
+                      int math, int variant, int threads, int flags, cudaStream_t stream, const int *cnt1 = nullptr,
+                      const int *cnt2 = nullptr, int *cnt3 = nullptr);
 constexpr int kAaSingleCta = 1 << 16;     // launch flag of launch_newview_aa: one block (stress-test hook); low bits = kernel flags
 int aa_kernel_info(int math, int variant, int threads, int *regs, int *block_threads, size_t *smem, int *tile_sites);
 int launch_generate_states(int states, float *x1, float *x2, size_t first_site, size_t n, uint64_t seed, cudaStream_t stream);
@@ -62,7 +63,7 @@ struct StreamScratch {
     unsigned long long work[2];           // work-counter pair of the dynamically scheduled kernels (self-cleaning)
     unsigned long long ticket;            // block ticket of the log-likelihood reduction (self-cleaning)
     unsigned long long pad;
-    float mats[144];                      // EV[16] | P_left[64] | P_right[64] staged from host arrays
+    float mats[3600];                     // EV | P_left | P_right staged from HOST arrays (S = 4: 16|64|64, S = 20: 400|1600|1600)
     double partials[kEvalMaxBlocks];      // per-block partial sums, reduced in block order by the last block
 };
 int stream_scratch(cudaStream_t stream, StreamScratch **out);     // returns a plf_status

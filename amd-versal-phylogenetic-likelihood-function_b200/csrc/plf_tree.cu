@@ -24,6 +24,7 @@
 
 struct plf_tree {
     int device = 0;
+    int states = 4;                            // STATES knob: 4 (DNA, level-batched kernel) or 20 (protein, one launch per node)
     unsigned n_tips = 0, n_inner = 0;
     size_t n_sites = 0;
     int math = PLF_MATH_STRICT;
@@ -39,7 +40,7 @@ struct plf_tree {
     unsigned char *d_codes = nullptr;          // codes: [n_tips][code_stride]
     float *d_pool = nullptr;                   // [n_slots][n_sites*16]
     int *d_counts = nullptr;                   // [n_slots][n_sites]
-    float *d_mats = nullptr;                   // EV[16] | P_left[n_inner][64] | P_right[n_inner][64] | tipvec[16][4]
+    float *d_mats = nullptr;                   // EV[S^2] | P_left[n_inner][4S^2] | P_right[n_inner][4S^2] | tipvec[16][4] (DNA)
     int *d_wgt = nullptr;
     bool use_wgt = false;
     plf::BatchOp *d_ops = nullptr;             // all ops, level after level
@@ -119,13 +120,19 @@ BatchSel pick_batch(int math, int u)
                                 : batch_sel<plf::MathStrictScalar, plf::MathStrict>(u);
 }
 
+size_t site_floats(const plf_tree *t) { return 4u * (size_t)t->states; }
+size_t ev_floats(const plf_tree *t) { return (size_t)t->states * t->states; }
+size_t p_floats(const plf_tree *t) { return 4u * (size_t)t->states * t->states; }
+float *node_pl(plf_tree *t, unsigned k) { return t->d_mats + ev_floats(t) + p_floats(t) * (size_t)k; }
+float *node_pr(plf_tree *t, unsigned k) { return t->d_mats + ev_floats(t) + p_floats(t) * ((size_t)t->n_inner + k); }
+
 // tip code vectors are padded to a multiple of 16 bytes (bulk-copy granularity)
 size_t code_stride(const plf_tree *t) { return (t->n_sites + 15) & ~(size_t)15; }
 
 // dense CLV of a node; NULL for a compressed tip
 float *node_clv(plf_tree *t, int node)
 {
-    const size_t stride = t->n_sites * PLF_SITE_FLOATS;
+    const size_t stride = t->n_sites * site_floats(t);
     if (node < (int)t->n_tips) return t->tip_format ? nullptr : t->d_tips + (size_t)node * stride;
     return t->d_pool + (size_t)t->slot[node - t->n_tips] * stride;
 }
@@ -135,7 +142,7 @@ const unsigned char *node_codes(plf_tree *t, int node)
     return (t->tip_format && node < (int)t->n_tips) ? t->d_codes + (size_t)node * code_stride(t) : nullptr;
 }
 
-float *tipvec_ptr(plf_tree *t) { return t->d_mats + 16 + 128 * (size_t)t->n_inner; }
+float *tipvec_ptr(plf_tree *t) { return t->d_mats + ev_floats(t) + 2 * p_floats(t) * (size_t)t->n_inner; }
 
 // count vectors are padded to a multiple of 4 ints so that every stage of them is a legal
 // (16-byte aligned, 16-byte granular) bulk copy
@@ -186,9 +193,51 @@ int launch_level(plf_tree *t, const BatchSel &k, size_t level, cudaStream_t s)
     return PLF_OK;
 }
 
+// 20 states: one launch of the protein kernel per inner node, level after level (nodes of a level are independent, and
+// the captured stream keeps the level order).  A node moves 964 B/site, so from ~30 k sites per GPU a launch is long
+// enough to hide its own launch cost inside the graph.
+int build_graph_states(plf_tree *t)
+{
+    if (t->exec) {
+        cudaGraphExecDestroy(t->exec);
+        t->exec = nullptr;
+    }
+    cudaGraph_t graph = nullptr;
+    TREE_CUDA(t, cudaStreamBeginCapture(t->stream, cudaStreamCaptureModeThreadLocal));
+    cudaError_t e = cudaMemsetAsync(t->d_sum, 0, sizeof(unsigned long long), t->stream);
+    int rc = PLF_OK;
+    const int flags = plf::fenced_release(true) ? plf::kFlagFencedRelease : 0;
+    for (size_t l = 0; l < t->levels.size() && e == cudaSuccess && rc == PLF_OK; ++l)
+        for (int k : t->levels[l]) {
+            rc = plf::launch_newview_aa(node_clv(t, t->left[k]), node_clv(t, t->right[k]), node_clv(t, (int)t->n_tips + k), nullptr,
+                                        t->d_mats, node_pl(t, (unsigned)k), node_pr(t, (unsigned)k), t->use_wgt ? t->d_wgt : nullptr,
+                                        t->n_sites, t->d_sum, t->math, 0, 0, flags, t->stream, node_counts(t, t->left[k]),
+                                        node_counts(t, t->right[k]), node_counts(t, (int)t->n_tips + k));
+            if (rc != PLF_OK) break;
+        }
+    if (e == cudaSuccess && rc == PLF_OK)
+        e = cudaMemcpyAsync(t->h_sum, t->d_sum, sizeof(unsigned long long), cudaMemcpyDeviceToHost, t->stream);
+    cudaError_t e2 = cudaStreamEndCapture(t->stream, &graph);
+    if (rc != PLF_OK || e != cudaSuccess || e2 != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        return tfail(t, rc != PLF_OK ? rc : PLF_ERR_CUDA, "graph capture of the 20-state traversal failed: %s",
+                     cudaGetErrorString(e != cudaSuccess ? e : e2));
+    }
+    e = cudaGraphInstantiate(&t->exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return tfail(t, PLF_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    t->exec_math = t->math;
+    t->exec_u = t->tune_u;
+    t->exec_chunk = t->tune_chunk;
+    t->exec_wgt = t->use_wgt;
+    t->exec_fenced = plf::fenced_release(false) ? 1 : 0;
+    return PLF_OK;
+}
+
 // (Re)capture the traversal: counter reset + one launch per level + read-back of the counter.
 int build_graph(plf_tree *t)
 {
+    if (t->states != 4) return build_graph_states(t);
     int u = t->tune_u;
     if (u == 0) {
         // 352-site stages (4 rows per warp) unless even the widest level would leave most SMs with < 4 stages
@@ -246,11 +295,20 @@ int plf_tree_create(plf_tree **out, int device, unsigned n_tips, const int *left
 int plf_tree_create_ex(plf_tree **out, int device, unsigned n_tips, const int *left, const int *right, size_t n_sites,
                        int tip_format)
 {
+    return plf_tree_create_states(out, device, n_tips, left, right, n_sites, tip_format, 4);
+}
+
+int plf_tree_create_states(plf_tree **out, int device, unsigned n_tips, const int *left, const int *right, size_t n_sites,
+                           int tip_format, int states)
+{
     if (!out) return tfail(nullptr, PLF_ERR_INVALID, "NULL tree out-pointer");
     *out = nullptr;
+    if (states != 4 && states != 20) return tfail(nullptr, PLF_ERR_INVALID, "STATES=%d is not supported (4 = DNA, 20 = protein)", states);
+    if (states != 4 && tip_format != PLF_TIPS_DENSE)
+        return tfail(nullptr, PLF_ERR_INVALID, "state-code tips are implemented for STATES=DNA only");
     if (n_tips < 2 || !left || !right || n_sites == 0)
         return tfail(nullptr, PLF_ERR_INVALID, "need n_tips >= 2, child arrays and n_sites > 0");
-    if (n_sites > (SIZE_MAX / 128)) return tfail(nullptr, PLF_ERR_INVALID, "n_sites too large");
+    if (n_sites > (SIZE_MAX / 1024)) return tfail(nullptr, PLF_ERR_INVALID, "n_sites too large");
     if (tip_format != PLF_TIPS_DENSE && tip_format != PLF_TIPS_CODES)
         return tfail(nullptr, PLF_ERR_INVALID, "unknown tip format %d", tip_format);
     const unsigned n_inner = n_tips - 1;
@@ -278,6 +336,7 @@ int plf_tree_create_ex(plf_tree **out, int device, unsigned n_tips, const int *l
     t->n_tips = n_tips;
     t->n_inner = n_inner;
     t->n_sites = n_sites;
+    t->states = states;
     t->tip_format = tip_format;
     if (const char *e = getenv("PLF_TREE_STATIC")) t->dynamic = !(e[0] == '1');
     t->left.assign(left, left + n_inner);
@@ -313,7 +372,7 @@ int plf_tree_create_ex(plf_tree **out, int device, unsigned n_tips, const int *l
     }
     t->n_slots = next_slot;
 
-    const size_t clv_bytes = n_sites * PLF_SITE_FLOATS * sizeof(float);
+    const size_t clv_bytes = n_sites * site_floats(t) * sizeof(float);
     cudaError_t e = cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&t->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&t->ev1);
@@ -323,7 +382,7 @@ int plf_tree_create_ex(plf_tree **out, int device, unsigned n_tips, const int *l
     if (e == cudaSuccess) e = cudaMalloc(&t->d_pool, clv_bytes * t->n_slots);
     if (e == cudaSuccess) e = cudaMalloc(&t->d_counts, count_stride(t) * sizeof(int) * t->n_slots);
     if (e == cudaSuccess) e = cudaMemset(t->d_counts, 0, count_stride(t) * sizeof(int) * t->n_slots);
-    if (e == cudaSuccess) e = cudaMalloc(&t->d_mats, (16 + 128 * (size_t)n_inner + 64) * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&t->d_mats, (ev_floats(t) + 2 * p_floats(t) * (size_t)n_inner + 64) * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&t->d_ops, sizeof(plf::BatchOp) * n_inner);
     if (e == cudaSuccess) e = cudaMalloc(&t->d_sum, sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc(&t->d_work, 2 * sizeof(unsigned long long));
@@ -357,8 +416,8 @@ int plf_tree_create_ex(plf_tree **out, int device, unsigned n_tips, const int *l
             o.tip2 = node_codes(t, t->right[k]);
             o.tipvec = tip_format == PLF_TIPS_CODES ? tipvec_ptr(t) : nullptr;
             o.ev = t->d_mats;
-            o.pl = t->d_mats + 16 + 64 * (size_t)k;
-            o.pr = t->d_mats + 16 + 64 * (size_t)n_inner + 64 * (size_t)k;
+            o.pl = node_pl(t, (unsigned)k);
+            o.pr = node_pr(t, (unsigned)k);
             ops.push_back(o);
         }
     }
@@ -428,7 +487,7 @@ int plf_tree_write_tip(plf_tree *t, unsigned tip, const float *clv, size_t bytes
     if (!t) return tfail(nullptr, PLF_ERR_INVALID, "NULL tree");
     if (tip >= t->n_tips) return tfail(t, PLF_ERR_INVALID, "tip %u out of range (%u tips)", tip, t->n_tips);
     if (t->tip_format != PLF_TIPS_DENSE) return tfail(t, PLF_ERR_STATE, "tree stores tips as state codes: use plf_tree_write_tip_codes");
-    const size_t cap = t->n_sites * PLF_SITE_FLOATS * sizeof(float);
+    const size_t cap = t->n_sites * site_floats(t) * sizeof(float);
     if (offset > cap || bytes > cap - offset) return tfail(t, PLF_ERR_INVALID, "write exceeds the tip CLV (%zu bytes)", cap);
     if (bytes == 0) return PLF_OK;
     if (!clv) return tfail(t, PLF_ERR_INVALID, "NULL host buffer");
@@ -466,10 +525,10 @@ int plf_tree_write_matrices(plf_tree *t, const float *ev, const float *p_left, c
 {
     if (!t || !ev || !p_left || !p_right) return tfail(t, PLF_ERR_INVALID, "NULL argument");
     TREE_CUDA(t, cudaSetDevice(t->device));
-    const size_t pb = 64 * (size_t)t->n_inner * sizeof(float);
-    TREE_CUDA(t, cudaMemcpyAsync(t->d_mats, ev, 16 * sizeof(float), cudaMemcpyHostToDevice, t->stream));
-    TREE_CUDA(t, cudaMemcpyAsync(t->d_mats + 16, p_left, pb, cudaMemcpyHostToDevice, t->stream));
-    TREE_CUDA(t, cudaMemcpyAsync(t->d_mats + 16 + 64 * (size_t)t->n_inner, p_right, pb, cudaMemcpyHostToDevice, t->stream));
+    const size_t pb = p_floats(t) * (size_t)t->n_inner * sizeof(float);
+    TREE_CUDA(t, cudaMemcpyAsync(t->d_mats, ev, ev_floats(t) * sizeof(float), cudaMemcpyHostToDevice, t->stream));
+    TREE_CUDA(t, cudaMemcpyAsync(node_pl(t, 0), p_left, pb, cudaMemcpyHostToDevice, t->stream));
+    TREE_CUDA(t, cudaMemcpyAsync(node_pr(t, 0), p_right, pb, cudaMemcpyHostToDevice, t->stream));
     TREE_CUDA(t, cudaStreamSynchronize(t->stream));     // host arrays may be pageable temporaries
     return PLF_OK;
 }
@@ -501,7 +560,7 @@ int plf_tree_run_async(plf_tree *t)
     TREE_CUDA(t, cudaEventRecord(t->ev0, t->stream));
     TREE_CUDA(t, cudaGraphLaunch(t->exec, t->stream));
     TREE_CUDA(t, cudaEventRecord(t->ev1, t->stream));
-    plf::count_launches(t->levels.size());
+    plf::count_launches(t->states == 4 ? t->levels.size() : (size_t)t->n_inner);
     t->ran = true;
     return PLF_OK;
 }
@@ -522,7 +581,7 @@ int plf_tree_read_root(plf_tree *t, float *clv, int *scaler_counts, size_t first
     TREE_CUDA(t, cudaSetDevice(t->device));
     const int root = (int)(t->n_tips + t->n_inner - 1);
     if (clv && n)
-        TREE_CUDA(t, cudaMemcpyAsync(clv, node_clv(t, root) + first_site * PLF_SITE_FLOATS, n * PLF_SITE_FLOATS * sizeof(float),
+        TREE_CUDA(t, cudaMemcpyAsync(clv, node_clv(t, root) + first_site * site_floats(t), n * site_floats(t) * sizeof(float),
                                      cudaMemcpyDeviceToHost, t->stream));
     if (scaler_counts && n)
         TREE_CUDA(t, cudaMemcpyAsync(scaler_counts, node_counts(t, root) + first_site, n * sizeof(int),
@@ -547,8 +606,8 @@ int plf_tree_info(plf_tree *t, unsigned *levels, unsigned *clv_slots, size_t *de
     if (levels) *levels = (unsigned)t->levels.size();
     if (clv_slots) *clv_slots = t->n_slots;
     if (device_bytes)
-        *device_bytes = (t->tip_format ? code_stride(t) * (size_t)t->n_tips : t->n_sites * 64 * (size_t)t->n_tips) +
-                        t->n_sites * 64 * (size_t)t->n_slots + count_stride(t) * 4 * (size_t)t->n_slots;
+        *device_bytes = (t->tip_format ? code_stride(t) * (size_t)t->n_tips : t->n_sites * site_floats(t) * 4 * (size_t)t->n_tips) +
+                        t->n_sites * site_floats(t) * 4 * (size_t)t->n_slots + count_stride(t) * 4 * (size_t)t->n_slots;
     if (traversal_bytes) {
         // per node: 64 B/site written, 64 B/site read per dense child (1 B/site per compressed tip),
         // + 4 B per count vector read (inner children) or written
@@ -556,8 +615,9 @@ int plf_tree_info(plf_tree *t, unsigned *levels, unsigned *clv_slots, size_t *de
         for (unsigned k = 0; k < t->n_inner; ++k)
             inner_children += (t->left[k] >= (int)t->n_tips) + (t->right[k] >= (int)t->n_tips);
         const size_t tip_children = 2 * (size_t)t->n_inner - inner_children;
-        const size_t tip_read = t->tip_format ? 1 : 64;
-        *traversal_bytes = t->n_sites * (64 * (size_t)t->n_inner + 64 * inner_children + tip_read * tip_children +
+        const size_t clv_site = site_floats(t) * 4;
+        const size_t tip_read = t->tip_format ? 1 : clv_site;
+        *traversal_bytes = t->n_sites * (clv_site * (size_t)t->n_inner + clv_site * inner_children + tip_read * tip_children +
                                          4 * ((size_t)t->n_inner + inner_children));
     }
     return PLF_OK;
@@ -568,14 +628,14 @@ int plf_tree_evaluate_root(plf_tree *t, const float *diag, double *lnl)
     if (!t || !diag || !lnl) return tfail(t, PLF_ERR_INVALID, "NULL argument");
     if (!t->ran) return tfail(t, PLF_ERR_STATE, "tree has not been run");
     TREE_CUDA(t, cudaSetDevice(t->device));
-    if (!t->d_lnl) TREE_CUDA(t, cudaMalloc(&t->d_lnl, 2 * sizeof(double) + 16 * sizeof(float)));
+    if (!t->d_lnl) TREE_CUDA(t, cudaMalloc(&t->d_lnl, 2 * sizeof(double) + 80 * sizeof(float)));
     float *d_diag = reinterpret_cast<float *>(t->d_lnl + 2);          // 16-byte aligned behind the accumulator
     TREE_CUDA(t, cudaMemsetAsync(t->d_lnl, 0, sizeof(double), t->stream));
-    TREE_CUDA(t, cudaMemcpyAsync(d_diag, diag, 16 * sizeof(float), cudaMemcpyHostToDevice, t->stream));
+    TREE_CUDA(t, cudaMemcpyAsync(d_diag, diag, site_floats(t) * sizeof(float), cudaMemcpyHostToDevice, t->stream));
     const int a = t->left[t->n_inner - 1], b = t->right[t->n_inner - 1];
     if (!node_clv(t, a) || !node_clv(t, b))
         return tfail(t, PLF_ERR_STATE, "a child of the root is a compressed tip: evaluate needs two dense CLVs");
-    int rc = plf::launch_evaluate(node_clv(t, a), node_clv(t, b), node_counts(t, a), node_counts(t, b),
+    int rc = plf::launch_evaluate(t->states, node_clv(t, a), node_clv(t, b), node_counts(t, a), node_counts(t, b),
                                   t->use_wgt ? t->d_wgt : nullptr, d_diag, t->n_sites, t->d_lnl, t->stream);
     if (rc != PLF_OK) return tfail(t, rc, "evaluate kernel launch failed");
     TREE_CUDA(t, cudaMemcpyAsync(lnl, t->d_lnl, sizeof(double), cudaMemcpyDeviceToHost, t->stream));

@@ -112,7 +112,6 @@ int main(int argc, char *argv[])
     } catch (const std::exception &e) {
         die(e.what());
     }
-    if (cfg.n_states != 4) die("STATES=" + cfg.states + " runs through host_states.exe (this host is the DNA drop-in)");
     if (cfg.input_src != PLF_INPUT_MEM) die("configuration '" + cfg.name + "' is INPUT_SRC=gen: use host_gen.exe");
     const std::vector<int> devices = parse_devices(argv[2]);
 
@@ -122,6 +121,7 @@ int main(int argc, char *argv[])
     tb.parallel_instances = static_cast<unsigned>(parse_count(argv[5], "parallel instances"));
     tb.window_size = cfg.window_size;
     tb.layout = cfg.layout;
+    tb.set_states(cfg.n_states);                      // STATES knob: DNA (4) or AA (20), from the configuration name
     if (tb.alignment_sites == 0 || tb.plf_calls == 0 || tb.parallel_instances == 0)
         die("alignments, plf calls and instances must all be > 0");
     if (tb.parallel_instances > cfg.num_accelerators * devices.size())
@@ -148,6 +148,7 @@ int main(int argc, char *argv[])
     kv("alignment sites:", std::to_string(tb.alignment_sites));
     kv("plf calls:", std::to_string(tb.plf_calls));
     kv("parallel plfs:", std::to_string(tb.parallel_instances));
+    kv("STATES:", cfg.states + " (" + std::to_string(tb.states) + " states x 4 rate categories, " + std::to_string(tb.elements_per_alignment) + " floats per site)");
     kv("PLIO layout:", cfg.layout == PLF_LAYOUT_COMB ? "Comb  [EV|P|CLV] / [EV|P|CLV]" : "Sep  [EV|P|CLV] / [P|CLV]");
     kv("AIE window size:", std::to_string(tb.window_size) + " (ignored: no windows on the GPU)");
     std::cout << bar << std::endl;
@@ -171,7 +172,8 @@ int main(int argc, char *argv[])
 
     // ---- Init: contexts (acap_info) and device buffers (xrt::bo) --------------------------------
     plf_multi *multi = nullptr;
-    if (plf_multi_create(&multi, devices.data(), static_cast<int>(devices.size()), cfg.num_accelerators, cfg.layout, PLF_INPUT_MEM) != PLF_OK)
+    if (plf_multi_create_states(&multi, devices.data(), static_cast<int>(devices.size()), cfg.num_accelerators, cfg.layout, PLF_INPUT_MEM,
+                                static_cast<int>(tb.states)) != PLF_OK)
         die(std::string("plf_multi_create: ") + plf_multi_last_error(nullptr));
     std::vector<plf_ctx *> ctxs;
     for (size_t r = 0; r < devices.size(); ++r) {
@@ -208,16 +210,19 @@ int main(int argc, char *argv[])
     const char *seed_env = std::getenv("PLF_SEED");
     std::mt19937 gen(seed_env ? static_cast<uint32_t>(std::strtoul(seed_env, nullptr, 10)) : 42u);
     std::uniform_real_distribution<> dis(0.0, 1.0);
-    float ev[16], branchleft[64], branchright[64];
-    for (float &v : ev) v = static_cast<float>(dis(gen));
-    for (int j = 0; j < 64; ++j) {
+    const size_t SF = tb.elements_per_alignment, EVF = tb.ev_elements(), PF = tb.branch_elements();     // 16 / 16 / 64 for DNA
+    std::vector<float> ev_v(EVF), bl_v(PF), br_v(PF);
+    float *ev = ev_v.data(), *branchleft = bl_v.data(), *branchright = br_v.data();
+    for (size_t j = 0; j < EVF; ++j) ev[j] = static_cast<float>(dis(gen));
+    for (size_t j = 0; j < PF; ++j) {
         branchleft[j] = static_cast<float>(dis(gen));
         branchright[j] = static_cast<float>(dis(gen));
     }
     std::vector<float> alignmentsleft(tb.elements_per_plf()), alignmentsright(tb.elements_per_plf());
-    const float tiny_scale = static_cast<float>(std::pow(1.0e-12, 1));
+    // 1e-12 as in the reference for DNA; 1e-14 for AA, whose 20-term sums are 25x larger
+    const float tiny_scale = tb.states == 4 ? static_cast<float>(std::pow(1.0e-12, 1)) : 1.0e-14f;
     for (size_t j = 0; j < tb.elements_per_plf(); ++j) {
-        const float scale = (j % 64 < 16) ? tiny_scale : 1.0f;    // every 4th site underflows
+        const float scale = ((j / SF) % 4 == 0) ? tiny_scale : 1.0f;    // every 4th site underflows (j % 64 < 16 for DNA)
         alignmentsleft[j] = static_cast<float>(dis(gen) * scale);
         alignmentsright[j] = static_cast<float>(dis(gen));
     }
@@ -233,6 +238,7 @@ int main(int argc, char *argv[])
                 die("PLF_LOAD_DIR: the files hold " + std::to_string(hl.sites) + " sites, the run asks for " +
                     std::to_string(tb.alignment_sites));
             const float *l = reinterpret_cast<const float *>(lb.data()), *r = reinterpret_cast<const float *>(rb.data());
+            if (tb.states != 4) die("PLF_LOAD_DIR: PLFB files hold DNA buffers");
             std::copy(l, l + 16, ev);
             std::copy(l + 16, l + 80, branchleft);
             std::copy(l + 80, l + 80 + tb.elements_per_plf(), alignmentsleft.begin());
@@ -258,18 +264,18 @@ int main(int argc, char *argv[])
     std::cout << "Prepare data for transfer ... " << std::endl;
     std::vector<float *> dataLeft(tb.parallel_instances), dataRight(tb.parallel_instances);
     auto pack = [&](unsigned k) {
-        const size_t off = tb.instance_first_site(k) * 16, cnt = tb.alignments_per_instance(k) * 16;
+        const size_t off = tb.instance_first_site(k) * SF, cnt = tb.alignments_per_instance(k) * SF;
         float *l = dataLeft[k], *r = dataRight[k];
-        std::copy(ev, ev + 16, l);
-        std::copy(branchleft, branchleft + 64, l + 16);
-        std::copy(alignmentsleft.begin() + off, alignmentsleft.begin() + off + cnt, l + 80);
+        std::copy(ev, ev + EVF, l);                                                     // [EV | P_left | CLV]
+        std::copy(branchleft, branchleft + PF, l + EVF);
+        std::copy(alignmentsleft.begin() + off, alignmentsleft.begin() + off + cnt, l + EVF + PF);
         if (tb.layout == PLF_LAYOUT_COMB) {
-            std::copy(ev, ev + 16, r);
-            std::copy(branchright, branchright + 64, r + 16);
-            std::copy(alignmentsright.begin() + off, alignmentsright.begin() + off + cnt, r + 80);
+            std::copy(ev, ev + EVF, r);
+            std::copy(branchright, branchright + PF, r + EVF);
+            std::copy(alignmentsright.begin() + off, alignmentsright.begin() + off + cnt, r + EVF + PF);
         } else {
-            std::copy(branchright, branchright + 64, r);
-            std::copy(alignmentsright.begin() + off, alignmentsright.begin() + off + cnt, r + 64);
+            std::copy(branchright, branchright + PF, r);
+            std::copy(alignmentsright.begin() + off, alignmentsright.begin() + off + cnt, r + PF);
         }
     };
     for (unsigned k = 0; k < tb.parallel_instances; ++k) {
@@ -293,7 +299,7 @@ int main(int argc, char *argv[])
         if (marks) check(plf_mark(c, li, PLF_MARK_T1), c, "plf_mark");
         check(plf_run_async(c, li, cnt), c, "plf_run_async");
         if (marks) check(plf_mark(c, li, PLF_MARK_T2), c, "plf_mark");
-        check(plf_read_out(c, li, result[call] + first * 16, cnt * 16 * sizeof(float), 0), c, "plf_read_out");
+        check(plf_read_out(c, li, result[call] + first * SF, cnt * SF * sizeof(float), 0), c, "plf_read_out");
         check(plf_read_scaler(c, li, scalerVector[call] + first, cnt, 0), c, "plf_read_scaler");
         if (marks) check(plf_mark(c, li, PLF_MARK_END), c, "plf_mark");
     };
@@ -351,6 +357,7 @@ int main(int argc, char *argv[])
 
     // PLF_DUMP_DIR=<dir>: the whole-run packed inputs and the outputs of call 0 as PLFB files
     if (const char *dir = std::getenv("PLF_DUMP_DIR")) {
+        if (tb.states != 4) die("PLF_DUMP_DIR: PLFB files hold DNA buffers");
         try {
             const size_t n = tb.alignment_sites, roff = tb.layout == PLF_LAYOUT_COMB ? 16 : 0;
             std::vector<float> lb(80 + 16 * n), rb(roff + 64 + 16 * n);
@@ -382,13 +389,17 @@ int main(int argc, char *argv[])
     for (size_t i = 0; i < tb.plf_calls && errors < 20; ++i) {
         long long inc_cpu = 0;
         reference_ms.t1[i] = t.elapsed_ms();
-        golden_plf(alignmentsleft.data(), alignmentsright.data(), cpuResult.data(), ev, tb.alignment_sites, branchleft,
-                   branchright, wgt.data(), inc_cpu);
+        if (tb.states == 4)
+            golden_plf(alignmentsleft.data(), alignmentsright.data(), cpuResult.data(), ev, tb.alignment_sites, branchleft,
+                       branchright, wgt.data(), inc_cpu);
+        else
+            golden_plf_states(tb.states, alignmentsleft.data(), alignmentsright.data(), cpuResult.data(), ev, tb.alignment_sites,
+                              branchleft, branchright, wgt.data(), inc_cpu);
         reference_ms.t2[i] = t.elapsed_ms();
         for (size_t j = 0; j < tb.elements_per_plf(); ++j) {
             if (cpuResult[j] != result[i][j]) {
-                std::cout << "ERROR: alignment data wrong for call " << i << " at alignment " << (j >> 4) << ", probability "
-                          << (j % 16) << ", cpu!=b200: " << cpuResult[j] << "!=" << result[i][j] << std::endl;
+                std::cout << "ERROR: alignment data wrong for call " << i << " at alignment " << (j / SF) << ", probability "
+                          << (j % SF) << ", cpu!=b200: " << cpuResult[j] << "!=" << result[i][j] << std::endl;
                 if (++errors >= 20) break;
             }
         }
@@ -413,7 +424,7 @@ int main(int argc, char *argv[])
                                  std::to_string(tb.alignment_sites) + "_usedgraphs" + std::to_string(tb.parallel_instances) + ".csv";
 #if !defined(NO_INTERMEDIATE_RESULTS) || NO_INTERMEDIATE_RESULTS == 0
     print_timing_data(execution_ms[0], reference_ms, static_cast<double>(tb.data_size()), total_sites, tb.plf_calls, "B200",
-                      static_cast<double>(tb.alignments_per_instance(0)) * tb.plf_calls);
+                      static_cast<double>(tb.alignments_per_instance(0)) * tb.plf_calls, 3.0 * SF * 4 + 1);
     if (csv) write_to_csv(csv_name, execution_ms);
 #else
     {

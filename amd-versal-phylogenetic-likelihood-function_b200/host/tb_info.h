@@ -22,7 +22,7 @@ struct AcceleratorConfig {
     std::string name;
     std::string aie_name, pl_name;
     unsigned num_accelerators = 9;    // NUM_ACCELERATORS
-    std::string states = "DNA";       // STATES: "DNA" (4 states) or "AA" (20 states, host_states.exe only)
+    std::string states = "DNA";       // STATES: "DNA" (4 states) or "AA" (20 states)
     unsigned n_states = 4;
     bool window = true;               // AIE_TYPE
     size_t window_size = 8192;        // WINDOW_SIZE (bytes per lane window; informational on GPU)
@@ -97,8 +97,17 @@ struct TestbenchInfo {
     unsigned parallel_instances = 1;
     size_t window_size = 8192;
     int layout = PLF_LAYOUT_COMB;
-    static constexpr size_t elements_per_alignment = PLF_SITE_FLOATS;
+    unsigned states = 4;              // STATES: 4 (DNA) or 20 (AA); every size below scales with it
+    size_t elements_per_alignment = PLF_SITE_FLOATS;     // 4 rate categories x states
     static constexpr size_t word_size = sizeof(float);
+
+    void set_states(unsigned s)
+    {
+        states = s;
+        elements_per_alignment = 4u * static_cast<size_t>(s);
+    }
+    size_t ev_elements() const { return static_cast<size_t>(states) * states; }
+    size_t branch_elements() const { return 4u * static_cast<size_t>(states) * states; }
 
     size_t alignments_per_instance() const
     {
@@ -118,8 +127,8 @@ struct TestbenchInfo {
         return alignment_sites > 0 && parallel_instances > 0 &&
                alignments_padding() < alignments_per_instance();
     }
-    size_t header_left() const { return PLF_HEADER_COMB; }
-    size_t header_right() const { return layout == PLF_LAYOUT_COMB ? PLF_HEADER_COMB : PLF_HEADER_SEP; }
+    size_t header_left() const { return ev_elements() + branch_elements(); }          // [EV | P]: 80 floats for DNA
+    size_t header_right() const { return layout == PLF_LAYOUT_COMB ? header_left() : branch_elements(); }
     size_t instance_elements_left() const { return alignments_per_instance() * elements_per_alignment + header_left(); }
     size_t instance_elements_right() const { return alignments_per_instance() * elements_per_alignment + header_right(); }
     size_t instance_elements_out() const { return alignments_per_instance() * elements_per_alignment; }

@@ -78,7 +78,8 @@ inline void print_row(const std::string &label, double ms, double bytes, double 
 // kernel_sites: sites x calls the TIMED instance's kernel processed (the table rows follow the reference and divide the
 // whole run's sites by instance 0's time; the HBM lines must not: with several instances that overstates the traffic).
 inline void print_timing_data(const TimingData &d, const TimingData &r, double data_size, double total_sites,
-                              size_t calls, const char *device_label = "B200", double kernel_sites = -1.0)
+                              size_t calls, const char *device_label = "B200", double kernel_sites = -1.0,
+                              double bytes_per_site = kBytesPerSite)
 {
     if (kernel_sites < 0.0) kernel_sites = total_sites;
     const std::string bar(101, '=');
@@ -97,11 +98,11 @@ inline void print_timing_data(const TimingData &d, const TimingData &r, double d
     print_row("Total execution time:", d.total(), data_size, total_sites);
     std::cout << bar << std::endl;
     if (d.msm() > 0.0) {
-        const double gbs = kBytesPerSite * kernel_sites / (d.msm() / 1e3) / 1e9;
-        const double best = kBytesPerSite * (kernel_sites / calls) / (d.min_msm() / 1e3) / 1e9;
-        std::cout << "| HBM traffic (193 B/site), all calls:   | " << std::setw(10) << gbs << " GB/s = " << std::setw(6)
+        const double gbs = bytes_per_site * kernel_sites / (d.msm() / 1e3) / 1e9;
+        const double best = bytes_per_site * (kernel_sites / calls) / (d.min_msm() / 1e3) / 1e9;
+        std::cout << "| HBM traffic (" << bytes_per_site << " B/site), all calls:   | " << std::setw(10) << gbs << " GB/s = " << std::setw(6)
                   << 100.0 * gbs / kHbmRooflineGBs << " % of 8 TB/s" << std::endl;
-        std::cout << "| HBM traffic (193 B/site), fastest call:| " << std::setw(10) << best << " GB/s = " << std::setw(6)
+        std::cout << "| HBM traffic (" << bytes_per_site << " B/site), fastest call:| " << std::setw(10) << best << " GB/s = " << std::setw(6)
                   << 100.0 * best / kHbmRooflineGBs << " % of 8 TB/s" << std::endl;
         std::cout << bar << std::endl;
     }

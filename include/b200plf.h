@@ -83,6 +83,14 @@ int plf_device_from_string(const char *bdf_or_ordinal, int *device);
  * n_instances is NUM_ACCELERATORS (Makefile:29): independent PLF instances, each with its own
  * CUDA stream.  Fails (PLF_ERR_CUDA) instead of throwing.                                     */
 int plf_ctx_create(plf_ctx **ctx, int device, unsigned n_instances, int layout, int input_src);
+/* The same with the STATES knob (Makefile:31; README.md:36,202): states = 4 (DNA, what plf_ctx_create gives) or 20
+ * (protein).  With S states every size of the instance API scales: one site is 4*S floats, EV S*S, one child's branch
+ * matrices 4*S*S, so the packed buffers are [EV S^2 | P 4S^2 | CLV n*4S] (left; right in the Comb layout) and
+ * [P 4S^2 | CLV] (right, Sep) -- host_mem.cpp:231-241 with 4 replaced by S.  plf_instance_alloc, plf_write_left/right,
+ * plf_run_async, plf_read_out/scaler, plf_scaler_increment and plf_newview_stream all follow the context's state count;
+ * the matrices are read from the head of the device buffers, not passed per launch.  INPUT_SRC=gen exists for DNA only. */
+int plf_ctx_create_states(plf_ctx **ctx, int device, unsigned n_instances, int layout, int input_src, int states);
+int plf_ctx_states(const plf_ctx *ctx);
 int plf_ctx_destroy(plf_ctx *ctx);
 /* Last error message of this ctx (or of ctx-less calls when ctx == NULL).  Never NULL. */
 const char *plf_last_error(const plf_ctx *ctx);
@@ -241,6 +249,11 @@ int plf_tree_create(plf_tree **tree, int device, unsigned n_tips, const int *lef
 typedef enum plf_tip_format { PLF_TIPS_DENSE = 0, PLF_TIPS_CODES = 1 } plf_tip_format;
 int plf_tree_create_ex(plf_tree **tree, int device, unsigned n_tips, const int *left, const int *right,
                        size_t n_sites, int tip_format);
+/* STATES knob for trees: states = 4 (what plf_tree_create_ex gives) or 20.  A 20-state tree keeps dense tips (80 floats
+ * per site), takes EV[400] and P_left / P_right [(n_tips-1)][1600], diag float[80] for plf_tree_evaluate_root, and runs
+ * one launch of the 20-state kernel per inner node (captured in the same CUDA graph), carrying the scaler counts.   */
+int plf_tree_create_states(plf_tree **tree, int device, unsigned n_tips, const int *left, const int *right,
+                           size_t n_sites, int tip_format, int states);
 /* CODES trees: n state codes of a tip starting at first_site; the 16 x 4 table tip_vector[code][state]. */
 int plf_tree_write_tip_codes(plf_tree *tree, unsigned tip, const unsigned char *codes, size_t n,
                              size_t first_site);
@@ -284,6 +297,10 @@ int plf_tree_last_ms(plf_tree *tree, float *ms);
  * (device double; the caller zeroes it).  fp64 products, log and accumulation.                  */
 int plf_evaluate_device(const float *x1, const float *x2, const int *cnt1, const int *cnt2,
                         const int *wgt, const float *diag, size_t n, double *lnl, void *stream);
+/* The same for S = 4 or 20 states: x1, x2 are n*4*S floats, diag is float[4*S] = [category][state].  The sum is
+ * reproducible bit for bit from run to run (fixed-order two-stage reduction, one addition to *lnl per launch).      */
+int plf_evaluate_states_device(int states, const float *x1, const float *x2, const int *cnt1, const int *cnt2,
+                               const int *wgt, const float *diag, size_t n, double *lnl, void *stream);
 /* The same across the ROOT branch of a traversed tree: between the two children of the last inner
  * node, with their accumulated scaler counts and the tree's weights.  diag is a HOST float[16].
  * Must follow a completed plf_tree_run_async (the children's buffers are still intact then).  */
@@ -298,9 +315,10 @@ int plf_tree_evaluate_root(plf_tree *tree, const float *diag, double *lnl);
  *   ev       : HOST float[S*S]      [k][l]
  *   p_left/p_right : HOST float[4*S*S] [category][k][l]
  *   scaler   : DEVICE uint8[n] or NULL; wgt DEVICE int32[n] or NULL; scaler_sum DEVICE counter or NULL
- * The matrices are HOST arrays (they are host arrays in the reference's host too, host_mem.cpp:183-197): the
- * 20-state kernel receives them as a kernel argument and reads them through the constant bank; they are
- * consumed before the call returns.  A site rescales when all 4*S entries are below 2^-32.  S = 4 runs the DNA
+ * The matrices are HOST arrays (they are host arrays in the reference's host too, host_mem.cpp:183-197): they travel
+ * by value into a per-stream staging record on the device and the kernel reads them from there; they are consumed
+ * before the call returns, and the call can be captured into a CUDA graph.  (The instance API of a 20-state context,
+ * plf_ctx_create_states, keeps the matrices in its device buffers and uploads nothing per launch.)  A site rescales when all 4*S entries are below 2^-32.  S = 4 runs the DNA
  * kernel of plf_newview_device.  For S = 20, opts->variant is the number of sites per lane of the register tile
  * (1, 2 or 4; threads_per_block 512 / 256,384 / 128,256); 0 = the fastest measured shape for the math mode.   */
 int plf_newview_states_device(int states, const float *x1, const float *x2, float *x3,
@@ -328,6 +346,8 @@ int plf_states_kernel_info(int states, int math_mode, int variant, int threads_p
  * NVLink/NVSwitch.  NCCL is resolved with dlopen("libnccl.so.2") at creation; a one-GPU plf_multi does not need it. */
 typedef struct plf_multi plf_multi;
 int plf_multi_create(plf_multi **multi, const int *devices, int n_devices, unsigned n_instances, int layout, int input_src);
+int plf_multi_create_states(plf_multi **multi, const int *devices, int n_devices, unsigned n_instances, int layout,
+                            int input_src, int states);
 int plf_multi_destroy(plf_multi *multi);
 const char *plf_multi_last_error(const plf_multi *multi);
 int plf_multi_size(const plf_multi *multi);

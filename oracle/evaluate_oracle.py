@@ -22,9 +22,10 @@ LOG_MIN = -32.0 * np.log(2.0)
 
 
 def evaluate(x1, x2, diag, cnt1=None, cnt2=None, wgt=None) -> float:
-    x1 = np.asarray(x1, np.float64).reshape(-1, 16)
-    x2 = np.asarray(x2, np.float64).reshape(-1, 16)
-    d = np.asarray(diag, np.float32).astype(np.float64).reshape(1, 16)
+    """diag has 4*S entries ([category][state]); S = 4 for the reference's DNA layout, 20 for protein."""
+    d = np.asarray(diag, np.float32).astype(np.float64).reshape(1, -1)
+    x1 = np.asarray(x1, np.float64).reshape(-1, d.shape[1])
+    x2 = np.asarray(x2, np.float64).reshape(-1, d.shape[1])
     with np.errstate(divide="ignore", invalid="ignore"):
         term = np.log(0.25 * np.abs((x1 * x2 * d).sum(axis=1)))
     c = np.zeros(x1.shape[0])

@@ -8,14 +8,18 @@ from __future__ import annotations
 import numpy as np
 
 
-def traverse(coracle, left, right, tips, ev, p_left, p_right, wgt=None):
-    """tips: [n_tips, n, 16].  Returns (root CLV [n,16], per-site counts [n], total scalings)."""
+def traverse(coracle, left, right, tips, ev, p_left, p_right, wgt=None, states: int = 4):
+    """tips: [n_tips, n, 4*states].  Returns (root CLV [n, 4*states], per-site counts [n], total scalings).
+    states = 4 goes through the pinned DNA restatement, any other count through the general-S loop nest."""
     n_tips = tips.shape[0]
     clv = {i: tips[i] for i in range(n_tips)}
     cnt = {i: np.zeros(tips.shape[1], np.int32) for i in range(n_tips)}
     total = 0
     for k, (a, b) in enumerate(zip(left, right)):
-        x3, sc, inc = coracle.newview(clv[int(a)], clv[int(b)], ev, p_left[k], p_right[k], wgt)
+        if states == 4:
+            x3, sc, inc = coracle.newview(clv[int(a)], clv[int(b)], ev, p_left[k], p_right[k], wgt)
+        else:
+            x3, sc, inc = coracle.newview_states(states, clv[int(a)], clv[int(b)], ev, p_left[k], p_right[k], wgt)
         node = n_tips + k
         clv[node] = x3
         cnt[node] = cnt[int(a)] + cnt[int(b)] + sc.astype(np.int32)

@@ -247,9 +247,21 @@ def test_host_states_argument_errors(hosts):
     assert r.returncode == 2 and "DNA or AA" in r.stderr
     r = run(HOST_STATES, "plf_128x9AAwindow8192Comb_genAAwindowComb", 0, 100, 1)
     assert r.returncode == 2 and "INPUT_SRC=mem" in r.stderr
-    for exe in (hosts[0], hosts[1], HOST_STREAM):                         # the DNA drop-ins refuse an AA configuration
+    for exe in (hosts[1], HOST_STREAM):                         # the gen / stream test benches are DNA only and say so
         r = run(exe, CFG_AA, 0, 100, 1, 1)
         assert r.returncode == 2 and ("host_states" in r.stderr or "Usage" in r.stderr)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg,sites,calls,instances", [
+    (CFG_AA, 100, 1, 1), (CFG_AA, 200003, 2, 9), ("plf_128x4AAwindow8192Sep_memAAwindowSep", 50001, 1, 3)])
+def test_host_mem_runs_the_AA_configuration(hosts, cfg, sites, calls, instances):
+    """STATES=AA through the main drop-in host: the same five arguments, the instance API of a 20-state context
+    (packed [EV400|P1600|CLV] buffers), exact verification against the host's S-state golden."""
+    r = run(hosts[0], cfg, 0, sites, calls, instances)
+    assert r.returncode == 0, r.stdout[-2500:] + r.stderr[-2000:]
+    assert "Test result: Passed" in r.stdout and f"scalerIncrement (call 0): {(sites + 3) // 4}" in r.stdout
+    assert "AA (20 states x 4 rate categories, 80 floats per site)" in r.stdout and "961 B/site" in r.stdout
 
 
 @pytest.mark.gpu
