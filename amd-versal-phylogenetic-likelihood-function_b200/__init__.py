@@ -307,10 +307,10 @@ def pack_left(ev, p_left, x1):
 
 
 def pack_right(ev, p_right, x2, layout: int = LAYOUT_COMB):
-    """Comb: [EV16 | P_right64 | CLV]; Sep: [P_right64 | CLV] (host_mem.cpp:234-241)."""
+    """Comb: [EV | P_right | CLV]; Sep: [P_right | CLV] (host_mem.cpp:234-241; 16 | 64 floats for DNA, 400 | 1600 for AA)."""
     parts = [np.asarray(p_right, np.float32).reshape(-1), np.asarray(x2, np.float32).reshape(-1)]
     if layout == LAYOUT_COMB:
-        parts.insert(0, np.asarray(ev, np.float32).reshape(16))
+        parts.insert(0, np.asarray(ev, np.float32).reshape(-1))
     return np.concatenate(parts)
 
 

@@ -28,7 +28,7 @@ constexpr int kEvalThreads = 256;
 // S states per category (4: DNA, one 128-bit load per child and element; 20: protein, five), U independent
 // (site, category) elements per thread and iteration.  diag is [category][state], 4*S floats.
 template <int S, int U>
-__global__ void __launch_bounds__(kEvalThreads, S == 4 ? 3 : 2)
+__global__ void __launch_bounds__(kEvalThreads, S == 4 ? (U == 1 ? 6 : 4) : 2)
 plf_evaluate_kernel(const float4 *__restrict__ x1, const float4 *__restrict__ x2,
                     const int *__restrict__ cnt1, const int *__restrict__ cnt2,
                     const int *__restrict__ wgt, const float *__restrict__ diag, size_t n,
@@ -45,8 +45,9 @@ plf_evaluate_kernel(const float4 *__restrict__ x1, const float4 *__restrict__ x2
     const size_t n_pad = (n_vec + 31) & ~(size_t)31;   // whole warps: the 4 lanes of a site stay together
     const size_t stride = (size_t)gridDim.x * kEvalThreads;
     double acc = 0.0;
-    // All 2*U*Q 128-bit loads of an iteration are issued before the first use, so a DNA thread keeps 128 B in flight
-    // instead of 32 (the kernel is latency-bound otherwise: 5.3 TB/s with one element per iteration).
+    // All 2*U*Q 128-bit loads of an iteration are issued before the first use.  Measured on B200 (DNA, 64 Mi sites):
+    // U = 1 with 6-8 blocks per SM 5.3 TB/s, U = 4 with 3 blocks per SM 3.6 TB/s -- the kernel is bound by the fp64
+    // chain (conversions, products, log) rather than by loads in flight, so occupancy beats unrolling.
     for (size_t v0 = (size_t)blockIdx.x * kEvalThreads + threadIdx.x; v0 < n_pad; v0 += U * stride) {
         float4 a[U][Q], b[U][Q];
         bool live[U];
@@ -123,7 +124,7 @@ template <int S, int U>
 static int launch_evaluate_t(const float *x1, const float *x2, const int *cnt1, const int *cnt2, const int *wgt,
                              const float *diag, size_t n, double *lnl, cudaStream_t stream, int sms)
 {
-    constexpr int bps = S == 4 ? 3 : 2;
+    constexpr int bps = S == 4 ? (U == 1 ? 6 : 4) : 2;
     size_t grid = (n * 4 + kEvalThreads * U - 1) / (kEvalThreads * U);
     if (grid > (size_t)sms * bps) grid = (size_t)sms * bps;
     if (grid > (size_t)kEvalMaxBlocks) grid = kEvalMaxBlocks;
@@ -144,7 +145,7 @@ int launch_evaluate(int states, const float *x1, const float *x2, const int *cnt
     if (cudaGetDevice(&dev) != cudaSuccess ||
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
         return PLF_ERR_CUDA;
-    if (states == 4) return launch_evaluate_t<4, 4>(x1, x2, cnt1, cnt2, wgt, diag, n, lnl, stream, sms);
+    if (states == 4) return launch_evaluate_t<4, 1>(x1, x2, cnt1, cnt2, wgt, diag, n, lnl, stream, sms);
     if (states == 20) return launch_evaluate_t<20, 1>(x1, x2, cnt1, cnt2, wgt, diag, n, lnl, stream, sms);
     return PLF_ERR_INVALID;
 }
