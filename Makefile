@@ -52,7 +52,7 @@ lib:
 CSRC := $(PKG)/csrc
 OBJDIR := $(PKG)/build
 KHDRS := $(CSRC)/plf_kernels.cuh $(CSRC)/plf_registry.h include/b200plf.h
-OBJS := $(OBJDIR)/plf_capi.o $(OBJDIR)/plf_tree.o $(OBJDIR)/plf_evaluate.o $(OBJDIR)/plf_protein.o $(OBJDIR)/plf_multi.o $(OBJDIR)/sel_ldg_strict.o $(OBJDIR)/sel_ldg_fma.o \
+OBJS := $(OBJDIR)/plf_capi.o $(OBJDIR)/plf_tree.o $(OBJDIR)/plf_evaluate.o $(OBJDIR)/plf_protein.o $(OBJDIR)/plf_protein_tc.o $(OBJDIR)/plf_multi.o $(OBJDIR)/sel_ldg_strict.o $(OBJDIR)/sel_ldg_fma.o \
         $(OBJDIR)/sel_tma_strict.o $(OBJDIR)/sel_tma_fma.o $(OBJDIR)/sel_dyn_strict.o $(OBJDIR)/sel_dyn_fma.o
 
 $(OBJDIR)/plf_capi.o: $(CSRC)/plf_capi.cu $(KHDRS)
@@ -67,6 +67,9 @@ $(OBJDIR)/plf_evaluate.o: $(CSRC)/plf_evaluate.cu $(KHDRS)
 	$(NVCC) $(NVFLAGS) -c -o $@ $<
 
 $(OBJDIR)/plf_protein.o: $(CSRC)/plf_protein.cu $(KHDRS)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -c -o $@ $<
+$(OBJDIR)/plf_protein_tc.o: $(CSRC)/plf_protein_tc.cu $(KHDRS)
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) -c -o $@ $<
 # NCCL: header only at build time (types and prototypes); the symbols are resolved with dlopen at run time

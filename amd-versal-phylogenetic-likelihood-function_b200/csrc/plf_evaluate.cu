@@ -28,7 +28,7 @@ constexpr int kEvalThreads = 256;
 // S states per category (4: DNA, one 128-bit load per child and element; 20: protein, five), U independent
 // (site, category) elements per thread and iteration.  diag is [category][state], 4*S floats.
 template <int S, int U>
-__global__ void __launch_bounds__(kEvalThreads, S == 4 ? (U == 1 ? 6 : 4) : 2)
+__global__ void __launch_bounds__(kEvalThreads, S == 4 ? (U == 1 ? 6 : 3) : 2)
 plf_evaluate_kernel(const float4 *__restrict__ x1, const float4 *__restrict__ x2,
                     const int *__restrict__ cnt1, const int *__restrict__ cnt2,
                     const int *__restrict__ wgt, const float *__restrict__ diag, size_t n,
@@ -45,9 +45,8 @@ plf_evaluate_kernel(const float4 *__restrict__ x1, const float4 *__restrict__ x2
     const size_t n_pad = (n_vec + 31) & ~(size_t)31;   // whole warps: the 4 lanes of a site stay together
     const size_t stride = (size_t)gridDim.x * kEvalThreads;
     double acc = 0.0;
-    // All 2*U*Q 128-bit loads of an iteration are issued before the first use.  Measured on B200 (DNA, 64 Mi sites):
-    // U = 1 with 6-8 blocks per SM 5.3 TB/s, U = 4 with 3 blocks per SM 3.6 TB/s -- the kernel is bound by the fp64
-    // chain (conversions, products, log) rather than by loads in flight, so occupancy beats unrolling.
+    // All 2*U*Q 128-bit loads of an iteration are issued before the first use (ncu on the one-element version:
+    // long_scoreboard 12 warps per issue, DRAM 56 %: too few bytes in flight).
     for (size_t v0 = (size_t)blockIdx.x * kEvalThreads + threadIdx.x; v0 < n_pad; v0 += U * stride) {
         float4 a[U][Q], b[U][Q];
         bool live[U];
@@ -63,10 +62,15 @@ plf_evaluate_kernel(const float4 *__restrict__ x1, const float4 *__restrict__ x2
                 }
             }
         }
+        // Per element: the four category lanes of a site add up their partial sums (two shuffles).  With U == 4 the
+        // logarithm of element u is then taken by the lane whose category is u: one log per LANE for four elements,
+        // instead of one per warp instruction with 8 of 32 lanes active (the log is two thirds of the instructions).
+        double mine = 0.0;
+        size_t my_site = 0;
+        bool my_live = false;
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const size_t v = v0 + u * stride;
-            if (v >= n_pad) break;                      // warp-uniform: n_pad and the strides are multiples of 32
             double t = 0.0;
             if (live[u]) {
 #pragma unroll
@@ -76,15 +80,27 @@ plf_evaluate_kernel(const float4 *__restrict__ x1, const float4 *__restrict__ x2
             }
             t += __shfl_xor_sync(0xffffffffu, t, 1);
             t += __shfl_xor_sync(0xffffffffu, t, 2);
-            if (live[u] && cat == 0) {
-                const size_t s = v >> 2;
-                double term = log(0.25 * fabs(t));
-                int c = 0;
-                if (cnt1) c += __ldg(cnt1 + s);
-                if (cnt2) c += __ldg(cnt2 + s);
-                term += (double)c * log_min;
-                acc += (wgt ? (double)__ldg(wgt + s) : 1.0) * term;
+            if (cat == (U == 4 ? u : 0)) {
+                mine = t;
+                my_site = v >> 2;
+                my_live = live[u];
             }
+            if (U != 4 && my_live && cat == 0) {          // one element per iteration: lane 0 of the site finishes it here
+                double term = log(0.25 * fabs(mine));
+                int c = 0;
+                if (cnt1) c += __ldg(cnt1 + my_site);
+                if (cnt2) c += __ldg(cnt2 + my_site);
+                term += (double)c * log_min;
+                acc += (wgt ? (double)__ldg(wgt + my_site) : 1.0) * term;
+            }
+        }
+        if (U == 4 && my_live) {
+            double term = log(0.25 * fabs(mine));
+            int c = 0;
+            if (cnt1) c += __ldg(cnt1 + my_site);
+            if (cnt2) c += __ldg(cnt2 + my_site);
+            term += (double)c * log_min;
+            acc += (wgt ? (double)__ldg(wgt + my_site) : 1.0) * term;
         }
     }
     __shared__ double warp_acc[kEvalThreads / 32];
@@ -124,7 +140,7 @@ template <int S, int U>
 static int launch_evaluate_t(const float *x1, const float *x2, const int *cnt1, const int *cnt2, const int *wgt,
                              const float *diag, size_t n, double *lnl, cudaStream_t stream, int sms)
 {
-    constexpr int bps = S == 4 ? (U == 1 ? 6 : 4) : 2;
+    constexpr int bps = S == 4 ? (U == 1 ? 6 : 3) : 2;
     size_t grid = (n * 4 + kEvalThreads * U - 1) / (kEvalThreads * U);
     if (grid > (size_t)sms * bps) grid = (size_t)sms * bps;
     if (grid > (size_t)kEvalMaxBlocks) grid = kEvalMaxBlocks;
@@ -145,7 +161,7 @@ int launch_evaluate(int states, const float *x1, const float *x2, const int *cnt
     if (cudaGetDevice(&dev) != cudaSuccess ||
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
         return PLF_ERR_CUDA;
-    if (states == 4) return launch_evaluate_t<4, 1>(x1, x2, cnt1, cnt2, wgt, diag, n, lnl, stream, sms);
+    if (states == 4) return launch_evaluate_t<4, 4>(x1, x2, cnt1, cnt2, wgt, diag, n, lnl, stream, sms);
     if (states == 20) return launch_evaluate_t<20, 1>(x1, x2, cnt1, cnt2, wgt, diag, n, lnl, stream, sms);
     return PLF_ERR_INVALID;
 }

@@ -347,6 +347,9 @@ AaSel aa_select(int math, int variant, int threads)
 
 int aa_kernel_info(int math, int variant, int threads, int *regs, int *block_threads, size_t *smem, int *tile_sites)
 {
+    if (variant == kAaVariantTensorCore)
+        return math == PLF_MATH_FMA && (threads == 0 || threads == 320) ? aa_tc_kernel_info(regs, block_threads, smem, tile_sites)
+                                                                        : PLF_ERR_INVALID;
     const AaSel k = aa_select(math, variant, threads);
     if (!k.fn) return PLF_ERR_INVALID;
     cudaFuncAttributes attr;
@@ -365,6 +368,11 @@ int launch_newview_aa(const float *x1, const float *x2, float *x3, unsigned char
                       int math, int variant, int threads, int flags, cudaStream_t stream, const int *cnt1, const int *cnt2,
                       int *cnt3)
 {
+    // variant 9: the tensor-core kernel.  3xTF32 is fp32-class but not the reference's rounding sequence: FMA mode only.
+    if (variant == kAaVariantTensorCore) {
+        if (math != PLF_MATH_FMA || (threads != 0 && threads != 320)) return PLF_ERR_INVALID;
+        return launch_newview_aa_tc(x1, x2, x3, scaler, ev, pl, pr, wgt, n, scaler_sum, flags, stream, cnt1, cnt2, cnt3);
+    }
     const AaSel k = aa_select(math, variant, threads);
     if (!k.fn) return PLF_ERR_INVALID;
     int dev = 0, sms = 0;

@@ -1,0 +1,437 @@
+// csrc/plf_protein_tc.cu -- 20-state newview on the 5th-generation tensor cores (tcgen05 + TMEM), tolerance mode.
+//
+// The 20-state path (the reference's STATES knob) is the one place in scope with a real
+// contraction: per rate category and child, [sites x 20] . [20 x 20], and once more for the EV back-transform
+// (app/src/plf.cpp:29-50 with 4 -> 20 states).  The CUDA-core kernel of plf_protein.cu is bound by shared-memory
+// operand bandwidth and the fp32 pipe (4.97 G sites/s = 0.73 of the HBM copy peak).  Here the three products run as
+//
+//        3xTF32:   A.B  ~=  A_hi.B_hi + A_lo.B_hi + A_hi.B_lo,     x_hi = rna_tf32(x), x_lo = rna_tf32(x - x_hi)
+//
+// on tcgen05.mma (kind::tf32, M = 128 sites, N = 32 >= 20, K = 24 >= 20 in three K = 8 steps), fp32 accumulation in
+// TMEM.  Each operand keeps 22 significant bits, the dropped lo.lo term is 2^-22 relative: fp32-class accuracy, but
+// NOT the reference's rounding sequence -- bit-exactness is impossible on tensor cores, so this kernel exists for
+// PLF_MATH_FMA only (<= 1e-5 relative, the tests state it); PLF_MATH_STRICT keeps the FMUL2/FADD kernel.
+//
+// Shape (one CTA per SM, 320 threads):
+//   warps 0-3 / 4-7   two WORKER GROUPS of 128 threads; thread t of a group owns site row t of the group's current
+//                     128-site tile = TMEM lane t.  A group is a self-contained sequential pipeline (convert -> MMA ->
+//                     product -> MMA -> read back); the two groups work on alternating tiles, so one group's CUDA-core
+//                     phases overlap the other's tensor-core phases.
+//   warps 8 / 9       one PRODUCER lane per group: TMA tensor copies (cp.async.bulk.tensor.2d, SASS UTMALDG) of
+//                     {20 floats x 128 sites} boxes -- one (category, child) operand, 10 KB, row pitch 80 B, which makes
+//                     the row-per-lane LDS.128 reads conflict-free -- into a 6-box ring per group (120 KB in flight per
+//                     SM).  Rows past the end of the site range are zero-filled by the TMA unit.
+//   A operands        never touch shared memory again: a worker splits its row into hi/lo in registers and writes both
+//                     to TMEM (tcgen05.st); the MMAs take A from TMEM and B (the constant matrices, pre-split, K-major
+//                     no-swizzle canonical layout, 54 KB) from shared memory.
+//   per category      a = x1.P_l^T, b = x2.P_r^T (18 MMAs) -> tcgen05.ld -> p = a*b in registers, split, tcgen05.st ->
+//                     x3 = p.EV (9 MMAs) -> tcgen05.ld into registers; after the fourth category the thread holds its
+//                     site's 80 results: threshold test, x 2^32, 256-bit stores, scaler byte, scaler count.
+// TMEM: 512 columns = 2 groups x (3 accumulators x 32 + 6 A-operand regions x 24).
+#include "../../include/b200plf.h"
+#include "plf_kernels.cuh"
+#include "plf_registry.h"
+
+#include <cuda.h>
+
+namespace plf {
+
+namespace tc {
+
+constexpr int kS = 20;                       // states
+constexpr int kSite = 80;                    // floats per site
+constexpr int kTile = 128;                   // sites per tile = MMA M = TMEM lanes
+constexpr int kBoxBytes = kS * kTile * 4;    // one (category, child) box: 10 240 B
+constexpr int kRing = 6;                     // boxes per group ring
+constexpr int kN = 32;                       // MMA N (>= 20, multiple of 16 for M = 128)
+constexpr int kK = 24;                       // padded K (three K = 8 steps)
+constexpr int kBMat = (kK / 4) * kN * 16;    // one B matrix in canonical K-major layout: 6 chunks x 32 rows x 16 B = 3072 B
+constexpr int kNumB = 9;                     // P_left[4], P_right[4], EV
+constexpr int kThreads = 320;
+
+// shared memory carve-up
+constexpr size_t kOffRing = 0;                                         // [2 groups][kRing][kBoxBytes]
+constexpr size_t kOffB = kOffRing + 2 * kRing * kBoxBytes;            // [kNumB][2 (hi, lo)][kBMat]
+constexpr size_t kOffBar = kOffB + (size_t)kNumB * 2 * kBMat;         // barriers
+constexpr size_t kSmemBytes = kOffBar + 256;
+
+// TMEM columns of one group (the second group sits 256 columns further)
+constexpr uint32_t kColAccA = 0, kColAccB = 32, kColAccX = 64;
+constexpr uint32_t kColAH1 = 96, kColAL1 = 120, kColAH2 = 144, kColAL2 = 168, kColPH = 192, kColPL = 216;
+
+// tcgen05 instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N = 32, M = 128
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
+
+__device__ __forceinline__ uint32_t rna_tf32(float x)
+{
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo)
+{
+    hi = rna_tf32(x);
+    lo = rna_tf32(x - __uint_as_float(hi));
+}
+
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 8-row x 16-byte core matrices,
+// SBO = 128 B between 8-row groups, LBO = kN * 16 B between the two 16-byte K chunks of one K = 8 step.
+__device__ __forceinline__ uint64_t b_desc(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);
+    d |= (uint64_t)(((kN * 16) >> 4) & 0x3FFFu) << 16;      // leading byte offset (K direction)
+    d |= (uint64_t)((128 >> 4) & 0x3FFFu) << 32;             // stride byte offset (N direction)
+    d |= 1ull << 46;                                         // descriptor version (Blackwell)
+    return d;                                                // base offset 0, layout type 0 = SWIZZLE_NONE
+}
+
+__device__ __forceinline__ void mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t"
+        "}\n"
+        :: "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(kIdesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t *bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, 128;" :: "r"(1 + g) : "memory"); }
+
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" :: "r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float &a, float &b, float &c, float &d)
+{
+    uint32_t r0, r1, r2, r3;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr) : "memory");
+    a = __uint_as_float(r0);
+    b = __uint_as_float(r1);
+    c = __uint_as_float(r2);
+    d = __uint_as_float(r3);
+}
+
+__device__ __forceinline__ void tma_box(void *smem_dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void st_global_v8(float *p, const float *v)
+{
+    asm volatile("st.global.cs.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 :: "l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
+}
+
+// One matrix into the canonical K-major layout, split into hi and lo:  B[n][k] at chunk (k / 4), row n, word (k % 4).
+// transpose == false: B[n][k] = src[n * 20 + k] (branch matrix P[kout][l]);  true: B[n][k] = src[k * 20 + n] (EV[k][l]).
+__device__ __forceinline__ void stage_b(unsigned char *smem_b, int m, const float *__restrict__ src, bool transpose, int tid, int nthreads)
+{
+    float *hi = reinterpret_cast<float *>(smem_b + (size_t)(2 * m) * kBMat);
+    float *lo = reinterpret_cast<float *>(smem_b + (size_t)(2 * m + 1) * kBMat);
+    for (int idx = tid; idx < kK * kN; idx += nthreads) {
+        const int n = idx / kK, k = idx - n * kK;
+        float v = 0.0f;
+        if (n < kS && k < kS) v = __ldg(src + (transpose ? k * kS + n : n * kS + k));
+        uint32_t h, l;
+        split_tf32(v, h, l);
+        const int word = (k >> 2) * (kN * 4) + n * 4 + (k & 3);
+        hi[word] = __uint_as_float(h);
+        lo[word] = __uint_as_float(l);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
+                  const float *__restrict__ ev, const float *__restrict__ pl, const float *__restrict__ pr,
+                  float *__restrict__ x3, unsigned char *__restrict__ scaler, const int *__restrict__ wgt, size_t n,
+                  unsigned long long *__restrict__ scaler_sum, const int *__restrict__ cnt1, const int *__restrict__ cnt2,
+                  int *__restrict__ cnt3)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char *ring = smem + kOffRing;
+    unsigned char *smem_b = smem + kOffB;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kOffBar);
+    uint64_t *full = bars;                    // [2][kRing]
+    uint64_t *empty = bars + 2 * kRing;       // [2][kRing]
+    uint64_t *mma_ab = bars + 4 * kRing;      // [2]
+    uint64_t *mma_x = mma_ab + 2;             // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mma_x + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t n_tiles = (n + kTile - 1) / kTile;
+
+    // ---- prologue: barriers, TMEM allocation, the nine matrices split and laid out for the tensor core ----
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2 * kRing; ++i) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], 4);           // one arrive per worker warp of the group
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&mma_ab[i], 1);
+            mbar_init(&mma_x[i], 1);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int j = 0; j < 4; ++j) {
+        stage_b(smem_b, j, pl + j * kS * kS, false, threadIdx.x, kThreads);
+        stage_b(smem_b, 4 + j, pr + j * kS * kS, false, threadIdx.x, kThreads);
+    }
+    stage_b(smem_b, 8, ev, true, threadIdx.x, kThreads);
+    fence_proxy_async_smem();                  // the matrices were written through the generic proxy; the MMA reads them through the async proxy
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    unsigned long long my_sum = 0;
+
+    if (warp >= 8) {
+        // ===== producers: one lane per group =====
+        if (lane == 0) {
+            const int g = warp - 8;
+            unsigned char *gring = ring + (size_t)g * kRing * kBoxBytes;
+            uint32_t slot = 0, phase = 0;
+            for (size_t tile = (size_t)blockIdx.x * 2 + g; tile < n_tiles; tile += (size_t)gridDim.x * 2) {
+                const int row0 = (int)(tile * kTile);
+                for (int c = 0; c < 4; ++c)
+                    for (int child = 0; child < 2; ++child) {
+                        mbar_wait(&empty[g * kRing + slot], phase ^ 1u);
+                        mbar_arrive_expect_tx(&full[g * kRing + slot], kBoxBytes);
+                        tma_box(gring + (size_t)slot * kBoxBytes, child ? &map2 : &map1, c * kS, row0, &full[g * kRing + slot]);
+                        if (++slot == kRing) {
+                            slot = 0;
+                            phase ^= 1u;
+                        }
+                    }
+            }
+        }
+    } else {
+        // ===== worker groups =====
+        const int g = warp >> 2;
+        const int t = threadIdx.x & 127;                                  // site row of the tile = TMEM lane
+        const unsigned char *gring = ring + (size_t)g * kRing * kBoxBytes;
+        const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)g * 256u;    // this warp's lane quarter, this group's columns
+        const uint32_t tcol = tmem_base + (uint32_t)g * 256u;                                             // lane 0: MMA operand addresses
+        const uint32_t b_base = smem_u32(smem_b);
+
+        // K padding columns 20..23 of the six A regions: zero once (the matching B rows are zero too, but TMEM starts
+        // out with arbitrary bits and 0 x NaN would poison the sums)
+        tmem_st4(trow + kColAH1 + 20, 0u, 0u, 0u, 0u);
+        tmem_st4(trow + kColAL1 + 20, 0u, 0u, 0u, 0u);
+        tmem_st4(trow + kColAH2 + 20, 0u, 0u, 0u, 0u);
+        tmem_st4(trow + kColAL2 + 20, 0u, 0u, 0u, 0u);
+        tmem_st4(trow + kColPH + 20, 0u, 0u, 0u, 0u);
+        tmem_st4(trow + kColPL + 20, 0u, 0u, 0u, 0u);
+        tc_wait_st();
+
+        uint32_t slot = 0, phase = 0, ph_ab = 0, ph_x = 0;
+        for (size_t tile = (size_t)blockIdx.x * 2 + g; tile < n_tiles; tile += (size_t)gridDim.x * 2) {
+            float out[4][kS];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                // --- both children of this category: ring -> registers -> hi/lo -> TMEM ---
+#pragma unroll
+                for (int child = 0; child < 2; ++child) {
+                    mbar_wait(&full[g * kRing + slot], phase);
+                    const float4 *row = reinterpret_cast<const float4 *>(gring + (size_t)slot * kBoxBytes + (size_t)t * (kS * 4));
+                    float4 v[5];
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) v[q] = row[q];
+                    fence_proxy_async_smem();                               // order this lane's reads before the refill (async proxy)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[g * kRing + slot]);
+                    if (++slot == kRing) {
+                        slot = 0;
+                        phase ^= 1u;
+                    }
+                    const uint32_t ch = child ? kColAH2 : kColAH1, cl = child ? kColAL2 : kColAL1;
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) {
+                        uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+                        split_tf32(v[q].x, h0, l0);
+                        split_tf32(v[q].y, h1, l1);
+                        split_tf32(v[q].z, h2, l2);
+                        split_tf32(v[q].w, h3, l3);
+                        tmem_st4(trow + ch + 4 * q, h0, h1, h2, h3);
+                        tmem_st4(trow + cl + 4 * q, l0, l1, l2, l3);
+                    }
+                }
+                tc_wait_st();
+                tc_fence_before();
+                group_sync(g);
+                if (t == 0) {
+                    tc_fence_after();
+                    // a = x1 . P_left[c]^T  and  b = x2 . P_right[c]^T : hi.hi + lo.hi + hi.lo, three K = 8 steps each
+#pragma unroll
+                    for (int child = 0; child < 2; ++child) {
+                        const uint32_t acc = tcol + (child ? kColAccB : kColAccA);
+                        const uint32_t ah = tcol + (child ? kColAH2 : kColAH1), al = tcol + (child ? kColAL2 : kColAL1);
+                        const uint32_t bh = b_base + (uint32_t)(2 * ((child ? 4 : 0) + c)) * kBMat, bl = bh + kBMat;
+#pragma unroll
+                        for (int ks = 0; ks < 3; ++ks) mma_ts(acc, ah + 8 * ks, b_desc(bh + ks * 2 * kN * 16), ks > 0);
+#pragma unroll
+                        for (int ks = 0; ks < 3; ++ks) mma_ts(acc, al + 8 * ks, b_desc(bh + ks * 2 * kN * 16), 1u);
+#pragma unroll
+                        for (int ks = 0; ks < 3; ++ks) mma_ts(acc, ah + 8 * ks, b_desc(bl + ks * 2 * kN * 16), 1u);
+                    }
+                    mma_commit(&mma_ab[g]);
+                }
+                mbar_wait(&mma_ab[g], ph_ab);
+                ph_ab ^= 1u;
+                tc_fence_after();
+                // --- p = a * b, split, back to TMEM as the A operand of the EV product ---
+                {
+                    float a[kS], b[kS];
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) {
+                        tmem_ld4(trow + kColAccA + 4 * q, a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
+                        tmem_ld4(trow + kColAccB + 4 * q, b[4 * q], b[4 * q + 1], b[4 * q + 2], b[4 * q + 3]);
+                    }
+                    tc_wait_ld();
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) {
+                        uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+                        split_tf32(a[4 * q] * b[4 * q], h0, l0);
+                        split_tf32(a[4 * q + 1] * b[4 * q + 1], h1, l1);
+                        split_tf32(a[4 * q + 2] * b[4 * q + 2], h2, l2);
+                        split_tf32(a[4 * q + 3] * b[4 * q + 3], h3, l3);
+                        tmem_st4(trow + kColPH + 4 * q, h0, h1, h2, h3);
+                        tmem_st4(trow + kColPL + 4 * q, l0, l1, l2, l3);
+                    }
+                }
+                tc_wait_st();
+                tc_fence_before();
+                group_sync(g);
+                if (t == 0) {
+                    tc_fence_after();
+                    const uint32_t acc = tcol + kColAccX, ph = tcol + kColPH, pw = tcol + kColPL;
+                    const uint32_t bh = b_base + (uint32_t)(2 * 8) * kBMat, bl = bh + kBMat;
+#pragma unroll
+                    for (int ks = 0; ks < 3; ++ks) mma_ts(acc, ph + 8 * ks, b_desc(bh + ks * 2 * kN * 16), ks > 0);
+#pragma unroll
+                    for (int ks = 0; ks < 3; ++ks) mma_ts(acc, pw + 8 * ks, b_desc(bh + ks * 2 * kN * 16), 1u);
+#pragma unroll
+                    for (int ks = 0; ks < 3; ++ks) mma_ts(acc, ph + 8 * ks, b_desc(bl + ks * 2 * kN * 16), 1u);
+                    mma_commit(&mma_x[g]);
+                }
+                mbar_wait(&mma_x[g], ph_x);
+                ph_x ^= 1u;
+                tc_fence_after();
+#pragma unroll
+                for (int q = 0; q < 5; ++q) tmem_ld4(trow + kColAccX + 4 * q, out[c][4 * q], out[c][4 * q + 1], out[c][4 * q + 2], out[c][4 * q + 3]);
+                tc_wait_ld();
+            }
+            // --- the site's 80 results: threshold test, rescale, store ---
+            const size_t site = tile * kTile + (size_t)t;
+            bool small = true;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int l = 0; l < kS; ++l) small = small && (fabsf(out[c][l]) < kMinLikelihood);
+            if (site < n) {
+                if (small) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+#pragma unroll
+                        for (int l = 0; l < kS; ++l) out[c][l] = __fmul_rn(out[c][l], kTwoToThe32);
+                }
+                float *dst = x3 + site * kSite;
+                const float *flat = &out[0][0];
+#pragma unroll
+                for (int i = 0; i < kSite / 8; ++i) st_global_v8(dst + 8 * i, flat + 8 * i);
+                if (scaler) scaler[site] = small ? 1 : 0;
+                if (cnt3) cnt3[site] = (cnt1 ? __ldg(cnt1 + site) : 0) + (cnt2 ? __ldg(cnt2 + site) : 0) + (small ? 1 : 0);
+                if (small) my_sum += wgt ? (unsigned long long)(long long)wgt[site] : 1ull;
+            }
+        }
+    }
+    if (scaler_sum) block_add_u64<kThreads>(my_sum, scaler_sum);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// CLV as a 2-D tensor {80 floats, n sites}, row pitch 320 B; box = one category of 128 sites
+static bool make_map(CUtensorMap *map, const float *x, size_t n)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)kSite, (cuuint64_t)n};
+    const cuuint64_t strides[1] = {(cuuint64_t)kSite * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)kS, (cuuint32_t)kTile};
+    const cuuint32_t elem[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(x), dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace tc
+
+int launch_newview_aa_tc(const float *x1, const float *x2, float *x3, unsigned char *scaler, const float *ev, const float *pl,
+                         const float *pr, const int *wgt, size_t n, unsigned long long *scaler_sum, int flags, cudaStream_t stream,
+                         const int *cnt1, const int *cnt2, int *cnt3)
+{
+    if (n == 0) return PLF_OK;
+    if (n >= (1ull << 31)) return PLF_ERR_INVALID;                     // TMA coordinates are 32-bit
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+        return PLF_ERR_CUDA;
+    CUtensorMap m1, m2;
+    if (!tc::make_map(&m1, x1, n) || !tc::make_map(&m2, x2, n)) return PLF_ERR_CUDA;
+    if (cudaFuncSetAttribute(tc::plf_newview_aa_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes) != cudaSuccess)
+        return PLF_ERR_CUDA;
+    const size_t tiles = (n + tc::kTile - 1) / tc::kTile;
+    size_t grid = (tiles + 1) / 2;
+    if (grid > (size_t)sms) grid = sms;
+    if (flags & kAaSingleCta) grid = 1;
+    tc::plf_newview_aa_tc<<<(int)grid, tc::kThreads, tc::kSmemBytes, stream>>>(m1, m2, ev, pl, pr, x3, scaler, wgt, n, scaler_sum, cnt1, cnt2,
+                                                                              cnt3);
+    count_launches(1);
+    return cudaGetLastError() == cudaSuccess ? PLF_OK : PLF_ERR_CUDA;
+}
+
+int aa_tc_kernel_info(int *regs, int *block_threads, size_t *smem, int *tile_sites)
+{
+    cudaFuncAttributes attr;
+    if (cudaFuncGetAttributes(&attr, tc::plf_newview_aa_tc) != cudaSuccess) return PLF_ERR_CUDA;
+    if (regs) *regs = attr.numRegs;
+    if (block_threads) *block_threads = tc::kThreads;
+    if (smem) *smem = tc::kSmemBytes;
+    if (tile_sites) *tile_sites = tc::kTile;
+    return PLF_OK;
+}
+
+}  // namespace plf

@@ -49,6 +49,12 @@ int launch_newview_aa(const float *x1, const float *x2, float *x3, unsigned char
                       int math, int variant, int threads, int flags, cudaStream_t stream, const int *cnt1 = nullptr,
                       const int *cnt2 = nullptr, int *cnt3 = nullptr);
 constexpr int kAaSingleCta = 1 << 16;     // launch flag of launch_newview_aa: one block (stress-test hook); low bits = kernel flags
+// the tensor-core (tcgen05 / TMEM, 3xTF32) 20-state kernel of plf_protein_tc.cu: tolerance mode only
+int launch_newview_aa_tc(const float *x1, const float *x2, float *x3, unsigned char *scaler, const float *ev, const float *pl,
+                         const float *pr, const int *wgt, size_t n, unsigned long long *scaler_sum, int flags, cudaStream_t stream,
+                         const int *cnt1 = nullptr, const int *cnt2 = nullptr, int *cnt3 = nullptr);
+int aa_tc_kernel_info(int *regs, int *block_threads, size_t *smem, int *tile_sites);
+constexpr int kAaVariantTensorCore = 9;   // opts->variant of the 20-state entry points: the tcgen05 kernel (PLF_MATH_FMA only)
 int aa_kernel_info(int math, int variant, int threads, int *regs, int *block_threads, size_t *smem, int *tile_sites);
 int launch_generate_states(int states, float *x1, float *x2, size_t first_site, size_t n, uint64_t seed, cudaStream_t stream);
 void generate_states_host(int states, float *x1, float *x2, size_t first_site, size_t n, uint64_t seed);
