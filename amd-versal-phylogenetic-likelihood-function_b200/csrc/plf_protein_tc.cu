@@ -47,13 +47,13 @@ constexpr int kN = 32;                       // MMA N (>= 20, multiple of 16 for
 constexpr int kK = 24;                       // padded K (three K = 8 steps)
 constexpr int kBMat = (kK / 4) * kN * 16;    // one B matrix in canonical K-major layout: 6 chunks x 32 rows x 16 B = 3072 B
 constexpr int kNumB = 9;                     // P_left[4], P_right[4], EV
-constexpr int kThreads = 320;
+constexpr int kThreads = 384;               // 8 worker warps, 2 producer warps, 2 MMA-issuer warps
 
 // shared memory carve-up
 constexpr size_t kOffRing = 0;                                         // [2 groups][kRing][kBoxBytes]
 constexpr size_t kOffB = kOffRing + 2 * kRing * kBoxBytes;            // [kNumB][2 (hi, lo)][kBMat]
 constexpr size_t kOffBar = kOffB + (size_t)kNumB * 2 * kBMat;         // barriers
-constexpr size_t kSmemBytes = kOffBar + 256;
+constexpr size_t kSmemBytes = kOffBar + 512;          // 34 mbarriers + the TMEM base address
 
 // TMEM columns of one group (the second group sits 256 columns further)
 constexpr uint32_t kColAccA = 0, kColAccB = 32, kColAccX = 64;
@@ -72,6 +72,15 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo)
 {
     hi = rna_tf32(x);
     lo = rna_tf32(x - __uint_as_float(hi));
+}
+// The split of the DATA path: hi = x truncated to tf32 (one LOP3), lo = x - hi (exact, <= 13 significant bits; the
+// tensor core reads its leading 11).  cvt.rna.tf32.f32 is emulated on sm_100a (about five ALU instructions: ncu
+// counted 2000 of the first version's 3300 instructions per tile and warp in it), and the two roundings to nearest buy
+// nothing here: |x - (hi + tf32(lo))| <= 2^-21 |x| either way, against the 1e-5 tolerance of this mode.
+__device__ __forceinline__ void split_trunc(float x, uint32_t &hi, uint32_t &lo)
+{
+    hi = __float_as_uint(x) & 0xFFFFE000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
 }
 
 // K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): 8-row x 16-byte core matrices,
@@ -120,6 +129,26 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float &a, float &b, flo
     d = __uint_as_float(r3);
 }
 
+// 20 consecutive columns of this thread's lane: one x16 and one x4 instruction
+__device__ __forceinline__ void tmem_st20(uint32_t taddr, const uint32_t (&v)[20])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+                 :: "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+                    "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+    tmem_st4(taddr + 16, v[16], v[17], v[18], v[19]);
+}
+__device__ __forceinline__ void tmem_ld20(uint32_t taddr, float (&f)[20])
+{
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                   "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(r[i]);
+    tmem_ld4(taddr + 16, f[16], f[17], f[18], f[19]);
+}
+
 __device__ __forceinline__ void tma_box(void *smem_dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar)
 {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
@@ -155,7 +184,7 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
                   const float *__restrict__ ev, const float *__restrict__ pl, const float *__restrict__ pr,
                   float *__restrict__ x3, unsigned char *__restrict__ scaler, const int *__restrict__ wgt, size_t n,
                   unsigned long long *__restrict__ scaler_sum, const int *__restrict__ cnt1, const int *__restrict__ cnt2,
-                  int *__restrict__ cnt3)
+                  int *__restrict__ cnt3, int flags)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *ring = smem + kOffRing;
@@ -163,9 +192,12 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + kOffBar);
     uint64_t *full = bars;                    // [2][kRing]
     uint64_t *empty = bars + 2 * kRing;       // [2][kRing]
-    uint64_t *mma_ab = bars + 4 * kRing;      // [2]
-    uint64_t *mma_x = mma_ab + 2;             // [2]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mma_x + 2);
+    uint64_t *mma_ab = bars + 4 * kRing;      // [2]  tensor core -> workers: a and b are in TMEM
+    uint64_t *mma_x = mma_ab + 2;             // [2]  tensor core -> workers: x3 is in TMEM
+    uint64_t *rdy_a = mma_x + 2;              // [2]  workers -> issuer: x1 operand is in TMEM (4 warp arrivals)
+    uint64_t *rdy_b = rdy_a + 2;              // [2]  workers -> issuer: x2 operand is in TMEM
+    uint64_t *rdy_p = rdy_b + 2;              // [2]  workers -> issuer: p operand is in TMEM
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(rdy_p + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t n_tiles = (n + kTile - 1) / kTile;
@@ -179,6 +211,9 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
         for (int i = 0; i < 2; ++i) {
             mbar_init(&mma_ab[i], 1);
             mbar_init(&mma_x[i], 1);
+            mbar_init(&rdy_a[i], 4);
+            mbar_init(&rdy_b[i], 4);
+            mbar_init(&rdy_p[i], 4);
         }
         mbar_fence_init();
     }
@@ -199,7 +234,57 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
 
     unsigned long long my_sum = 0;
 
-    if (warp >= 8) {
+    if (warp >= 10) {
+        // ===== MMA issuers: one lane per group.  tcgen05.mma is issued by a single thread; a dedicated one keeps the
+        // ~25 descriptor/issue instructions per MMA (108 MMAs per tile) off the workers' critical path. =====
+        if (lane == 0) {
+            const int g = warp - 10;
+            const uint32_t tcol = tmem_base + (uint32_t)g * 256u;
+            const uint32_t b_base = smem_u32(smem_b);
+            const size_t first = (size_t)blockIdx.x * 2 + g, stride = (size_t)gridDim.x * 2;
+            const size_t my_tiles = first < n_tiles ? (n_tiles - first + stride - 1) / stride : 0;
+            uint32_t ph = 0;                                   // all three ready barriers complete once per step
+            auto branch = [&](int child, int c) {              // a = x1 . P_left[c]^T  or  b = x2 . P_right[c]^T
+                const uint32_t acc = tcol + (child ? kColAccB : kColAccA);
+                const uint32_t ah = tcol + (child ? kColAH2 : kColAH1), al = tcol + (child ? kColAL2 : kColAL1);
+                const uint32_t bh = b_base + (uint32_t)(2 * ((child ? 4 : 0) + c)) * kBMat, bl = bh + kBMat;
+#pragma unroll
+                for (int ks = 0; ks < 3; ++ks) mma_ts(acc, ah + 8 * ks, b_desc(bh + ks * 2 * kN * 16), ks > 0);
+#pragma unroll
+                for (int ks = 0; ks < 3; ++ks) mma_ts(acc, al + 8 * ks, b_desc(bh + ks * 2 * kN * 16), 1u);
+#pragma unroll
+                for (int ks = 0; ks < 3; ++ks) mma_ts(acc, ah + 8 * ks, b_desc(bl + ks * 2 * kN * 16), 1u);
+            };
+            // the workers' order: ab(0); then per step s: x(s), ab(s + 1)
+            const size_t steps = my_tiles * 4;
+            for (size_t sidx = 0; sidx <= steps; ++sidx) {
+                if (sidx > 0) {                                // x(sidx - 1) = p . EV
+                    mbar_wait(&rdy_p[g], ph ^ 1u);             // completed in the PREVIOUS step's phase
+                    tc_fence_after();
+                    const uint32_t acc = tcol + kColAccX, phh = tcol + kColPH, pw = tcol + kColPL;
+                    const uint32_t bh = b_base + (uint32_t)(2 * 8) * kBMat, bl = bh + kBMat;
+#pragma unroll
+                    for (int ks = 0; ks < 3; ++ks) mma_ts(acc, phh + 8 * ks, b_desc(bh + ks * 2 * kN * 16), ks > 0);
+#pragma unroll
+                    for (int ks = 0; ks < 3; ++ks) mma_ts(acc, pw + 8 * ks, b_desc(bh + ks * 2 * kN * 16), 1u);
+#pragma unroll
+                    for (int ks = 0; ks < 3; ++ks) mma_ts(acc, phh + 8 * ks, b_desc(bl + ks * 2 * kN * 16), 1u);
+                    mma_commit(&mma_x[g]);
+                }
+                if (sidx < steps) {                            // ab(sidx)
+                    const int c = (int)(sidx & 3);
+                    mbar_wait(&rdy_a[g], ph);
+                    tc_fence_after();
+                    branch(0, c);
+                    mbar_wait(&rdy_b[g], ph);
+                    tc_fence_after();
+                    branch(1, c);
+                    mma_commit(&mma_ab[g]);
+                    ph ^= 1u;
+                }
+            }
+        }
+    } else if (warp >= 8) {
         // ===== producers: one lane per group =====
         if (lane == 0) {
             const int g = warp - 8;
@@ -225,8 +310,6 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
         const int t = threadIdx.x & 127;                                  // site row of the tile = TMEM lane
         const unsigned char *gring = ring + (size_t)g * kRing * kBoxBytes;
         const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)g * 256u;    // this warp's lane quarter, this group's columns
-        const uint32_t tcol = tmem_base + (uint32_t)g * 256u;                                             // lane 0: MMA operand addresses
-        const uint32_t b_base = smem_u32(smem_b);
 
         // K padding columns 20..23 of the six A regions: zero once (the matching B rows are zero too, but TMEM starts
         // out with arbitrary bits and 0 x NaN would poison the sums)
@@ -239,100 +322,85 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
         tc_wait_st();
 
         uint32_t slot = 0, phase = 0, ph_ab = 0, ph_x = 0;
-        for (size_t tile = (size_t)blockIdx.x * 2 + g; tile < n_tiles; tile += (size_t)gridDim.x * 2) {
+
+        // convert: both children of the NEXT (tile, category) in ring order: ring -> registers -> hi/lo -> TMEM, then the
+        // 18 branch MMAs  a = x1 . P_left[c]^T,  b = x2 . P_right[c]^T  (hi.hi + lo.hi + hi.lo, three K = 8 steps each)
+        auto convert = [&]() {
+#pragma unroll
+            for (int child = 0; child < 2; ++child) {
+                mbar_wait(&full[g * kRing + slot], phase);
+                const float4 *row = reinterpret_cast<const float4 *>(gring + (size_t)slot * kBoxBytes + (size_t)t * (kS * 4));
+                float4 v[5];
+#pragma unroll
+                for (int q = 0; q < 5; ++q) v[q] = row[q];
+                uint32_t hi[kS], lo[kS];
+#pragma unroll
+                for (int q = 0; q < 5; ++q) {
+                    split_trunc(v[q].x, hi[4 * q], lo[4 * q]);
+                    split_trunc(v[q].y, hi[4 * q + 1], lo[4 * q + 1]);
+                    split_trunc(v[q].z, hi[4 * q + 2], lo[4 * q + 2]);
+                    split_trunc(v[q].w, hi[4 * q + 3], lo[4 * q + 3]);
+                }
+                // hand the slot back: every lane's reads are complete once their values have been used (the XOR below
+                // depends on all of them), or, with the fenced release, ordered by fence.proxy.async
+                unsigned dep = 0;
+#pragma unroll
+                for (int q = 0; q < 5; ++q) dep ^= hi[4 * q];
+                if (flags & kFlagFencedRelease) fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    if (dep == 0x9E3779B9u) fence_proxy_async_smem();
+                    mbar_arrive(&empty[g * kRing + slot]);
+                }
+                if (++slot == kRing) {
+                    slot = 0;
+                    phase ^= 1u;
+                }
+                tmem_st20(trow + (child ? kColAH2 : kColAH1), hi);
+                tmem_st20(trow + (child ? kColAL2 : kColAL1), lo);
+                // this warp's quarter of the operand is in TMEM: tell the issuer (it starts the nine MMAs of this child
+                // when all four warps have arrived, while the workers convert the other child)
+                tc_wait_st();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(child ? &rdy_b[g] : &rdy_a[g]);
+            }
+        };
+        // finish_ab: p = a * b in registers, split, back to TMEM as the A operand of the 9 EV MMAs
+        auto finish_ab = [&]() {
+            mbar_wait(&mma_ab[g], ph_ab);
+            ph_ab ^= 1u;
+            tc_fence_after();
+            float a[kS], b[kS];
+            tmem_ld20(trow + kColAccA, a);
+            tmem_ld20(trow + kColAccB, b);
+            tc_wait_ld();
+            uint32_t hi[kS], lo[kS];
+#pragma unroll
+            for (int k = 0; k < kS; ++k) split_trunc(a[k] * b[k], hi[k], lo[k]);
+            tmem_st20(trow + kColPH, hi);
+            tmem_st20(trow + kColPL, lo);
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&rdy_p[g]);
+        };
+
+        // Software pipeline over the (tile, category) steps of this group: the EV product of step s runs on the tensor
+        // core while the CUDA cores convert the operands of step s + 1, and the branch products of step s + 1 run while
+        // the results of step s are read back -- so of the two MMA round trips per step only a part of one is exposed.
+        const size_t first = (size_t)blockIdx.x * 2 + g, stride = (size_t)gridDim.x * 2;
+        if (first < n_tiles) convert();
+        for (size_t tile = first; tile < n_tiles; tile += stride) {
             float out[4][kS];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                // --- both children of this category: ring -> registers -> hi/lo -> TMEM ---
-#pragma unroll
-                for (int child = 0; child < 2; ++child) {
-                    mbar_wait(&full[g * kRing + slot], phase);
-                    const float4 *row = reinterpret_cast<const float4 *>(gring + (size_t)slot * kBoxBytes + (size_t)t * (kS * 4));
-                    float4 v[5];
-#pragma unroll
-                    for (int q = 0; q < 5; ++q) v[q] = row[q];
-                    fence_proxy_async_smem();                               // order this lane's reads before the refill (async proxy)
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&empty[g * kRing + slot]);
-                    if (++slot == kRing) {
-                        slot = 0;
-                        phase ^= 1u;
-                    }
-                    const uint32_t ch = child ? kColAH2 : kColAH1, cl = child ? kColAL2 : kColAL1;
-#pragma unroll
-                    for (int q = 0; q < 5; ++q) {
-                        uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
-                        split_tf32(v[q].x, h0, l0);
-                        split_tf32(v[q].y, h1, l1);
-                        split_tf32(v[q].z, h2, l2);
-                        split_tf32(v[q].w, h3, l3);
-                        tmem_st4(trow + ch + 4 * q, h0, h1, h2, h3);
-                        tmem_st4(trow + cl + 4 * q, l0, l1, l2, l3);
-                    }
-                }
-                tc_wait_st();
-                tc_fence_before();
-                group_sync(g);
-                if (t == 0) {
-                    tc_fence_after();
-                    // a = x1 . P_left[c]^T  and  b = x2 . P_right[c]^T : hi.hi + lo.hi + hi.lo, three K = 8 steps each
-#pragma unroll
-                    for (int child = 0; child < 2; ++child) {
-                        const uint32_t acc = tcol + (child ? kColAccB : kColAccA);
-                        const uint32_t ah = tcol + (child ? kColAH2 : kColAH1), al = tcol + (child ? kColAL2 : kColAL1);
-                        const uint32_t bh = b_base + (uint32_t)(2 * ((child ? 4 : 0) + c)) * kBMat, bl = bh + kBMat;
-#pragma unroll
-                        for (int ks = 0; ks < 3; ++ks) mma_ts(acc, ah + 8 * ks, b_desc(bh + ks * 2 * kN * 16), ks > 0);
-#pragma unroll
-                        for (int ks = 0; ks < 3; ++ks) mma_ts(acc, al + 8 * ks, b_desc(bh + ks * 2 * kN * 16), 1u);
-#pragma unroll
-                        for (int ks = 0; ks < 3; ++ks) mma_ts(acc, ah + 8 * ks, b_desc(bl + ks * 2 * kN * 16), 1u);
-                    }
-                    mma_commit(&mma_ab[g]);
-                }
-                mbar_wait(&mma_ab[g], ph_ab);
-                ph_ab ^= 1u;
-                tc_fence_after();
-                // --- p = a * b, split, back to TMEM as the A operand of the EV product ---
-                {
-                    float a[kS], b[kS];
-#pragma unroll
-                    for (int q = 0; q < 5; ++q) {
-                        tmem_ld4(trow + kColAccA + 4 * q, a[4 * q], a[4 * q + 1], a[4 * q + 2], a[4 * q + 3]);
-                        tmem_ld4(trow + kColAccB + 4 * q, b[4 * q], b[4 * q + 1], b[4 * q + 2], b[4 * q + 3]);
-                    }
-                    tc_wait_ld();
-#pragma unroll
-                    for (int q = 0; q < 5; ++q) {
-                        uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
-                        split_tf32(a[4 * q] * b[4 * q], h0, l0);
-                        split_tf32(a[4 * q + 1] * b[4 * q + 1], h1, l1);
-                        split_tf32(a[4 * q + 2] * b[4 * q + 2], h2, l2);
-                        split_tf32(a[4 * q + 3] * b[4 * q + 3], h3, l3);
-                        tmem_st4(trow + kColPH + 4 * q, h0, h1, h2, h3);
-                        tmem_st4(trow + kColPL + 4 * q, l0, l1, l2, l3);
-                    }
-                }
-                tc_wait_st();
-                tc_fence_before();
-                group_sync(g);
-                if (t == 0) {
-                    tc_fence_after();
-                    const uint32_t acc = tcol + kColAccX, ph = tcol + kColPH, pw = tcol + kColPL;
-                    const uint32_t bh = b_base + (uint32_t)(2 * 8) * kBMat, bl = bh + kBMat;
-#pragma unroll
-                    for (int ks = 0; ks < 3; ++ks) mma_ts(acc, ph + 8 * ks, b_desc(bh + ks * 2 * kN * 16), ks > 0);
-#pragma unroll
-                    for (int ks = 0; ks < 3; ++ks) mma_ts(acc, pw + 8 * ks, b_desc(bh + ks * 2 * kN * 16), 1u);
-#pragma unroll
-                    for (int ks = 0; ks < 3; ++ks) mma_ts(acc, ph + 8 * ks, b_desc(bl + ks * 2 * kN * 16), 1u);
-                    mma_commit(&mma_x[g]);
-                }
+                finish_ab();
+                if (c < 3 || tile + stride < n_tiles) convert();
                 mbar_wait(&mma_x[g], ph_x);
                 ph_x ^= 1u;
                 tc_fence_after();
-#pragma unroll
-                for (int q = 0; q < 5; ++q) tmem_ld4(trow + kColAccX + 4 * q, out[c][4 * q], out[c][4 * q + 1], out[c][4 * q + 2], out[c][4 * q + 3]);
+                tmem_ld20(trow + kColAccX, out[c]);
                 tc_wait_ld();
             }
             // --- the site's 80 results: threshold test, rescale, store ---
@@ -418,7 +486,7 @@ int launch_newview_aa_tc(const float *x1, const float *x2, float *x3, unsigned c
     if (grid > (size_t)sms) grid = sms;
     if (flags & kAaSingleCta) grid = 1;
     tc::plf_newview_aa_tc<<<(int)grid, tc::kThreads, tc::kSmemBytes, stream>>>(m1, m2, ev, pl, pr, x3, scaler, wgt, n, scaler_sum, cnt1, cnt2,
-                                                                              cnt3);
+                                                                              cnt3, flags & kFlagFencedRelease);
     count_launches(1);
     return cudaGetLastError() == cudaSuccess ? PLF_OK : PLF_ERR_CUDA;
 }

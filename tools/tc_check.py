@@ -56,8 +56,10 @@ def main():
     sc = torch.empty(n, dtype=torch.uint8, device=dev)
     dsum = torch.zeros(1, dtype=torch.int64, device=dev)
     pkg.generate_states_device(20, x1.data_ptr(), x2.data_ptr(), 0, n, 42, stream)
-    for label, math, variant in (("tcgen05 3xTF32", 1, 9), ("cuda-core fma", 1, 0), ("cuda-core strict", 0, 0)):
-        opts = pkg.make_opts(math, variant, 0)
+    for label, math, variant, fl in (("tcgen05 3xTF32 (fenced release)", 1, 9, pkg.LAUNCH_FENCED_RELEASE),
+                                     ("tcgen05 3xTF32 (dependency release)", 1, 9, pkg.LAUNCH_DEP_RELEASE),
+                                     ("cuda-core fma", 1, 0, 0), ("cuda-core strict", 0, 0, 0)):
+        opts = pkg.make_opts(math, variant, 0, 0, 0, fl)
         a = (20, x1.data_ptr(), x2.data_ptr(), x3.data_ptr(), sc.data_ptr(), ev, left, right, None, n, dsum.data_ptr(), opts, stream)
         dsum.zero_()
         for _ in range(2):
