@@ -347,8 +347,8 @@ AaSel aa_select(int math, int variant, int threads)
 
 int aa_kernel_info(int math, int variant, int threads, int *regs, int *block_threads, size_t *smem, int *tile_sites)
 {
-    if (variant == kAaVariantTensorCore)
-        return math == PLF_MATH_FMA && (threads == 0 || threads == 320) ? aa_tc_kernel_info(regs, block_threads, smem, tile_sites)
+    if (variant == kAaVariantTensorCore || (variant == 0 && threads == 0 && math == PLF_MATH_FMA))      // FMA default for long calls
+        return math == PLF_MATH_FMA && (threads == 0 || threads == 384) ? aa_tc_kernel_info(regs, block_threads, smem, tile_sites)
                                                                         : PLF_ERR_INVALID;
     const AaSel k = aa_select(math, variant, threads);
     if (!k.fn) return PLF_ERR_INVALID;
@@ -369,8 +369,10 @@ int launch_newview_aa(const float *x1, const float *x2, float *x3, unsigned char
                       int *cnt3)
 {
     // variant 9: the tensor-core kernel.  3xTF32 is fp32-class but not the reference's rounding sequence: FMA mode only.
-    if (variant == kAaVariantTensorCore) {
-        if (math != PLF_MATH_FMA || (threads != 0 && threads != 320)) return PLF_ERR_INVALID;
+    // It is also what variant 0 means in FMA mode from kAaTensorCoreMinSites sites on (5.4 against 4.7 G sites/s for the
+    // CUDA-core FMA kernel on B200); shorter calls keep the CUDA-core kernel, whose prologue is lighter.
+    if (variant == kAaVariantTensorCore || (variant == 0 && threads == 0 && math == PLF_MATH_FMA && n >= kAaTensorCoreMinSites)) {
+        if (math != PLF_MATH_FMA || (threads != 0 && threads != 384)) return PLF_ERR_INVALID;
         return launch_newview_aa_tc(x1, x2, x3, scaler, ev, pl, pr, wgt, n, scaler_sum, flags, stream, cnt1, cnt2, cnt3);
     }
     const AaSel k = aa_select(math, variant, threads);

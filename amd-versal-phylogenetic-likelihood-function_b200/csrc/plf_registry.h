@@ -54,6 +54,7 @@ int launch_newview_aa_tc(const float *x1, const float *x2, float *x3, unsigned c
                          const float *pr, const int *wgt, size_t n, unsigned long long *scaler_sum, int flags, cudaStream_t stream,
                          const int *cnt1 = nullptr, const int *cnt2 = nullptr, int *cnt3 = nullptr);
 int aa_tc_kernel_info(int *regs, int *block_threads, size_t *smem, int *tile_sites);
+constexpr size_t kAaTensorCoreMinSites = 16384;   // FMA-mode calls at least this long default to the tensor-core kernel
 constexpr int kAaVariantTensorCore = 9;   // opts->variant of the 20-state entry points: the tcgen05 kernel (PLF_MATH_FMA only)
 int aa_kernel_info(int math, int variant, int threads, int *regs, int *block_threads, size_t *smem, int *tile_sites);
 int launch_generate_states(int states, float *x1, float *x2, size_t first_site, size_t n, uint64_t seed, cudaStream_t stream);

@@ -652,14 +652,20 @@ def side_protein(pkg, torch, peak, reps=5, n=2 << 20):
     """STATES=protein: the 20-state newview, strict and FMA, device-resident CLVs."""
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import protein_bench
-    res = protein_bench.measure(pkg, torch, n, reps, shapes=[(0, 0)], maths=(0, 1), verbose=False)
+    res = protein_bench.measure(pkg, torch, n, reps, shapes=[(0, 0), (4, 256)], maths=(0, 1), verbose=False)
     out = {"sites": n, "bytes_per_site": res["bytes_per_site"], "muladd_per_site": res["muladd_per_site"]}
+    label = {("strict", 0): "strict", ("fma", 0): "fma", ("fma", 4): "fma_cuda_cores"}
     for row in res["rows"]:
+        key = label.get((row["math"], row["variant"]))
+        if key is None:
+            continue
         assert row["ok"], "20-state run failed its self-checks"
-        out[row["math"]] = {"value": row["gsites"] * 1e9, "unit": "sites/s", "ms_per_launch": row["ms_mean"],
-                            "tmuladd_per_s": row["tmuladd_per_s"], "kernel": {k: row[k] for k in ("regs", "threads", "smem_bytes")},
-                            "roofline": _roofline(res["bytes_per_site"] * n, row["ms_mean"], peak,
-                                                  "on the HBM / fp32 ridge: 961 B and 4800 multiply-adds per site")}
+        out[key] = {"value": row["gsites"] * 1e9, "unit": "sites/s", "ms_per_launch": row["ms_mean"],
+                    "tmuladd_per_s": row["tmuladd_per_s"], "kernel": {k: row[k] for k in ("regs", "threads", "smem_bytes")},
+                    "roofline": _roofline(res["bytes_per_site"] * n, row["ms_mean"], peak,
+                                          "on the HBM / fp32 ridge: 961 B and 4800 multiply-adds per site")}
+    out["fma"]["kernel"]["path"] = "tcgen05.mma kind::tf32, 3xTF32 split, TMEM accumulators, TMA operand boxes (csrc/plf_protein_tc.cu)"
+    out["fma_cuda_cores"]["kernel"]["path"] = "FFMA2 register tile (csrc/plf_protein.cu, variant 4 x 256 threads)"
     torch.cuda.empty_cache()
     return out
 

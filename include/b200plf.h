@@ -320,7 +320,10 @@ int plf_tree_evaluate_root(plf_tree *tree, const float *diag, double *lnl);
  * before the call returns, and the call can be captured into a CUDA graph.  (The instance API of a 20-state context,
  * plf_ctx_create_states, keeps the matrices in its device buffers and uploads nothing per launch.)  A site rescales when all 4*S entries are below 2^-32.  S = 4 runs the DNA
  * kernel of plf_newview_device.  For S = 20, opts->variant is the number of sites per lane of the register tile
- * (1, 2 or 4; threads_per_block 512 / 256,384 / 128,256); 0 = the fastest measured shape for the math mode.   */
+ * (1, 2 or 4; threads_per_block 512 / 256,384 / 128,256), or 9 = the TENSOR-CORE kernel (tcgen05.mma kind::tf32 with the
+ * 3xTF32 split, fp32 accumulators in tensor memory, operands by TMA; PLF_MATH_FMA only -- tensor cores cannot reproduce
+ * the reference's rounding sequence, so PLF_MATH_STRICT never uses them); 0 = the fastest measured kernel for the math
+ * mode: the register-tile kernel in strict mode, the tensor-core kernel in FMA mode for calls of >= 16384 sites.      */
 int plf_newview_states_device(int states, const float *x1, const float *x2, float *x3,
                               unsigned char *scaler, const float *ev, const float *p_left,
                               const float *p_right, const int *wgt, size_t n,
