@@ -809,7 +809,43 @@ struct BatchOp {
     const unsigned char *tip1;
     const unsigned char *tip2;
     const float *tipvec;  // [16][4], shared by all ops of a launch; NULL when no op has a compressed tip
+    // Tip-tip nodes (both children compressed tips): the parent CLV of a site depends only on (code1, code2), so the
+    // whole newview -- branch products, a.b, EV product, threshold test, x 2^32 -- is tabulated ONCE per op for the 256
+    // code pairs by plf_tiptip_tables (16 KB per op, with the functions of the per-site path: same bits) and a site then
+    // costs one L1-resident 128-bit table read per category instead of ~45 instructions.  RAxML tabulates the two branch
+    // products for this case; with 4-bit codes the whole product fits.  NULL for every other kind of node.
+    const float4 *tiptab;          // [256 code pairs][4 categories]: the final x3 of the pair, already rescaled if it rescales
+    const unsigned char *tipflag;  // [256]: 1 when the pair rescales
 };
+
+// One block of 256 threads per op of the tree; blocks of ops without a tip-tip table return at once.
+template <class M>
+__global__ void __launch_bounds__(256)
+plf_tiptip_tables(const BatchOp *__restrict__ ops, int n_ops)
+{
+    const int op = blockIdx.x;
+    if (op >= n_ops) return;
+    const BatchOp o = ops[op];
+    if (!o.tiptab) return;
+    const int c1 = threadIdx.x >> 4, c2 = threadIdx.x & 15;
+    const float4 *tv = reinterpret_cast<const float4 *>(o.tipvec);
+    const float4 t1 = __ldg(tv + c1), t2 = __ldg(tv + c2);
+    float4 r[4];
+    bool small = true;
+#pragma unroll
+    for (int cat = 0; cat < 4; ++cat) {
+        CatConst c;
+        load_cat_const(c, o.ev, o.pl, o.pr, cat, 0);
+        small = category_finish<M>(c, category_branch<M>(c.L, t1), category_branch<M>(c.R, t2), r[cat]) && small;
+    }
+    float4 *tab = const_cast<float4 *>(o.tiptab) + threadIdx.x * 4;
+#pragma unroll
+    for (int cat = 0; cat < 4; ++cat) {
+        if (small) rescale(r[cat]);
+        tab[cat] = r[cat];
+    }
+    const_cast<unsigned char *>(o.tipflag)[threadIdx.x] = small ? 1 : 0;
+}
 
 template <int U, int WARPS, int DEPTH>
 constexpr size_t batch_smem_bytes()
@@ -970,6 +1006,37 @@ plf_newview_batch(const BatchOp *__restrict__ ops, int n_ops, size_t n,
             // The rest of the stage, compiled once per (child 1 is a tip, child 2 is a tip): o.tip1 / o.tip2 are
             // warp-uniform run-time values, and left as such the compiler predicates both sides -- every dense stage
             // then also executes the tip path's byte and table reads, and the other way round.
+            // tip-tip node with a table: codes -> table rows -> stores; no arithmetic, no vote
+            auto tiptip_body = [&]() {
+                const uint32_t code_off = slot * STAGE + warp * TILE + site_in_row;
+                float4 r[U];
+                unsigned dep = g;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const unsigned pair = ((k1s[code_off + 8 * u] & 15u) << 4) | (k2s[code_off + 8 * u] & 15u);
+                    dep ^= pair << (u & 7);
+                    r[u] = __ldg(o.tiptab + pair * 4 + cat);
+                }
+                unsigned my_pair = 0;
+                if (lane_live) my_pair = ((k1s[slot * STAGE + warp * TILE + lane] & 15u) << 4) | (k2s[slot * STAGE + warp * TILE + lane] & 15u);
+                dep ^= my_pair << 8;
+                release_slot(&empty[slot], lane, dep, flags);
+                float4 *out = o.x3 + s0 * 4 + lane;
+                if (complete) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) st_stream(out + 32 * u, r[u]);
+                } else {
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (s0 + 8 * u + site_in_row < n) st_stream(out + 32 * u, r[u]);
+                }
+                if (lane_live) {
+                    const bool scaled = __ldg(o.tipflag + my_pair) != 0;
+                    if (o.scaler) o.scaler[s_lane] = scaled ? 1 : 0;
+                    if (o.cnt3) o.cnt3[s_lane] = scaled ? 1 : 0;           // tips carry no counts
+                    if (scaled) my_sum += wgt ? (unsigned long long)(long long)wgt[s_lane] : 1ull;
+                }
+            };
             auto stage_body = [&](auto tip1_c, auto tip2_c) {
                 constexpr bool TIP1 = decltype(tip1_c)::value, TIP2 = decltype(tip2_c)::value;
                 float4 a[U], b[U], r[U];
@@ -1038,7 +1105,8 @@ plf_newview_batch(const BatchOp *__restrict__ ops, int n_ops, size_t n,
             using yes = cuda_true;
             using no = cuda_false;
             if (o.tip1) {
-                if (o.tip2) stage_body(yes{}, yes{});
+                if (o.tip2 && o.tiptab) tiptip_body();
+                else if (o.tip2) stage_body(yes{}, yes{});
                 else stage_body(yes{}, no{});
             } else {
                 if (o.tip2) stage_body(no{}, yes{});

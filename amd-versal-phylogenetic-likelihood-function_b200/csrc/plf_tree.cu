@@ -43,6 +43,9 @@ struct plf_tree {
     float *d_mats = nullptr;                   // EV[S^2] | P_left[n_inner][4S^2] | P_right[n_inner][4S^2] | tipvec[16][4] (DNA)
     int *d_wgt = nullptr;
     bool use_wgt = false;
+    float *d_tiptab = nullptr;                 // codes trees: [n_tiptip][256][16] tabulated newviews of the tip-tip nodes
+    unsigned char *d_tipflag = nullptr;        //              [n_tiptip][256] rescale flags
+    unsigned n_tiptip = 0;
     plf::BatchOp *d_ops = nullptr;             // all ops, level after level
     std::vector<size_t> level_op_offset;
     unsigned long long *d_sum = nullptr, *h_sum = nullptr;
@@ -254,6 +257,11 @@ int build_graph(plf_tree *t)
     TREE_CUDA(t, cudaStreamBeginCapture(t->stream, cudaStreamCaptureModeThreadLocal));
     cudaError_t e = cudaMemsetAsync(t->d_sum, 0, sizeof(unsigned long long), t->stream);
     int rc = PLF_OK;
+    if (e == cudaSuccess && t->n_tiptip) {          // the matrices may have changed since the last traversal: re-tabulate
+        if (t->math == PLF_MATH_FMA) plf::plf_tiptip_tables<plf::MathFma><<<(int)t->n_inner, 256, 0, t->stream>>>(t->d_ops, (int)t->n_inner);
+        else plf::plf_tiptip_tables<plf::MathStrict><<<(int)t->n_inner, 256, 0, t->stream>>>(t->d_ops, (int)t->n_inner);
+        e = cudaGetLastError();
+    }
     for (size_t l = 0; l < t->levels.size() && e == cudaSuccess && rc == PLF_OK; ++l) rc = launch_level(t, k, l, t->stream);
     if (e == cudaSuccess && rc == PLF_OK)
         e = cudaMemcpyAsync(t->h_sum, t->d_sum, sizeof(unsigned long long), cudaMemcpyDeviceToHost, t->stream);
@@ -398,6 +406,22 @@ int plf_tree_create_states(plf_tree **out, int device, unsigned n_tips, const in
     }
     *t->h_sum = 0;
 
+    // tip-tip nodes of a codes tree get a 256-pair table each (plf_tiptip_tables fills them at the start of a traversal)
+    if (tip_format == PLF_TIPS_CODES && !getenv("PLF_NO_TIPTIP_TABLES")) {
+        for (unsigned k = 0; k < n_inner; ++k) t->n_tiptip += (left[k] < (int)n_tips && right[k] < (int)n_tips);
+        if (t->n_tiptip) {
+            e = cudaMalloc(&t->d_tiptab, (size_t)t->n_tiptip * 256 * 16 * sizeof(float));
+            if (e == cudaSuccess) e = cudaMalloc(&t->d_tipflag, (size_t)t->n_tiptip * 256);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                tfail(nullptr, PLF_ERR_NOMEM, "tip-tip table allocation failed: %s", cudaGetErrorString(e));
+                plf_tree_destroy(t);
+                return PLF_ERR_NOMEM;
+            }
+        }
+    }
+    unsigned next_tab = 0;
+
     // op descriptors, level after level
     std::vector<plf::BatchOp> ops;
     ops.reserve(n_inner);
@@ -415,6 +439,13 @@ int plf_tree_create_states(plf_tree **out, int device, unsigned n_tips, const in
             o.tip1 = node_codes(t, t->left[k]);
             o.tip2 = node_codes(t, t->right[k]);
             o.tipvec = tip_format == PLF_TIPS_CODES ? tipvec_ptr(t) : nullptr;
+            o.tiptab = nullptr;
+            o.tipflag = nullptr;
+            if (t->d_tiptab && o.tip1 && o.tip2) {
+                o.tiptab = reinterpret_cast<const float4 *>(t->d_tiptab + (size_t)next_tab * 256 * 16);
+                o.tipflag = t->d_tipflag + (size_t)next_tab * 256;
+                ++next_tab;
+            }
             o.ev = t->d_mats;
             o.pl = node_pl(t, (unsigned)k);
             o.pr = node_pr(t, (unsigned)k);
@@ -444,6 +475,8 @@ int plf_tree_destroy(plf_tree *t)
     cudaFree(t->d_mats);
     cudaFree(t->d_wgt);
     cudaFree(t->d_ops);
+    cudaFree(t->d_tiptab);
+    cudaFree(t->d_tipflag);
     cudaFree(t->d_sum);
     cudaFree(t->d_lnl);
     cudaFree(t->d_work);
@@ -560,7 +593,7 @@ int plf_tree_run_async(plf_tree *t)
     TREE_CUDA(t, cudaEventRecord(t->ev0, t->stream));
     TREE_CUDA(t, cudaGraphLaunch(t->exec, t->stream));
     TREE_CUDA(t, cudaEventRecord(t->ev1, t->stream));
-    plf::count_launches(t->states == 4 ? t->levels.size() : (size_t)t->n_inner);
+    plf::count_launches((t->states == 4 ? t->levels.size() : (size_t)t->n_inner) + (t->n_tiptip ? 1 : 0));
     t->ran = true;
     return PLF_OK;
 }

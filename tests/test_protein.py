@@ -251,7 +251,9 @@ def test_protein_rejects_bad_arguments(pkg, gpu):
         pkg.newview_states_device(S, d.data_ptr(), d.data_ptr(), d.data_ptr(), None, ev[:16], left, right, None, 8, None, None, st)
     info = pkg.states_kernel_info(S)
     assert info["tile_sites"] == 16 and info["threads"] == 384 and info["smem_bytes"] <= 227 * 1024
-    info = pkg.states_kernel_info(S, pkg.MATH_FMA)
+    info = pkg.states_kernel_info(S, pkg.MATH_FMA)                  # FMA default for long calls: the tensor-core kernel
+    assert info["tile_sites"] == 128 and info["threads"] == 384 and info["regs"] <= 170
+    info = pkg.states_kernel_info(S, pkg.MATH_FMA, 4, 256)          # the CUDA-core FMA register tile
     assert info["tile_sites"] == 32 and info["threads"] == 256 and info["regs"] <= 255
 
 
