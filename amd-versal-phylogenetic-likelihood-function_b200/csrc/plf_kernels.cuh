@@ -622,8 +622,9 @@ constexpr size_t tma_smem_bytes()
 // (`work[0]`), publishes it to its consumers through shared memory together with the stage's
 // data, and a sentinel index ends the loop.  The first DEPTH stages of a CTA are dealt statically and
 // two counter fetches are kept in flight, so neither the ramp of a launch nor its steady state waits
-// for an atomic round trip.  The last CTA to finish (`work[1]` counts them) zeroes both words: the
-// pair is clean for its next user without a memset.
+// for an atomic round trip.  The last PRODUCER to run out of work (`work[1]` counts them, as soon as a
+// producer has consumed its last fetch -- not behind a barrier at the end of the kernel) zeroes both
+// words: the pair is clean for its next user without a memset.
 // ---------------------------------------------------------------------------------------------
 template <class M, int U, int WARPS, int DEPTH, int MINB>
 __global__ void __launch_bounds__((WARPS + 1) * 32, MINB)
@@ -703,9 +704,17 @@ plf_newview_tma_dyn(const float4 *__restrict__ x1, const float4 *__restrict__ x2
                     phase ^= 1u;
                 }
             }
-            // every fetch this producer issued has returned before the CTA reports itself finished: the last
-            // CTA zeroes the pair, and a straggling atomic would leave it dirty for the next launch
+            // Every fetch this producer issued has returned (the empty asm consumes both values), so this CTA is
+            // done with the counter: report it NOW, while the consumers still work on the last ring stages, instead
+            // of behind a block barrier at the very end of the kernel (an atomic round trip on every CTA's tail).
+            // The last producer out zeroes the pair: clean for its next user without a memset.
             asm volatile("" :: "l"(next_a), "l"(next_b));
+            const unsigned long long finished = atomicAdd(work + 1, 1ull);
+            if (finished == gridDim.x - 1) {
+                work[0] = 0ull;
+                work[1] = 0ull;
+                __threadfence();
+            }
         }
     } else {
         // ===== consumers =====
@@ -760,15 +769,6 @@ plf_newview_tma_dyn(const float4 *__restrict__ x1, const float4 *__restrict__ x2
         }
     }
     if (scaler_sum) block_add_u64<THREADS>(my_sum, scaler_sum);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned long long finished = atomicAdd(work + 1, 1ull);
-        if (finished == gridDim.x - 1) {          // last CTA out: leave the pair clean for its next user
-            work[0] = 0ull;
-            work[1] = 0ull;
-            __threadfence();
-        }
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -957,6 +957,14 @@ plf_newview_batch(const BatchOp *__restrict__ ops, int n_ops, size_t n,
             mbar_wait(&empty[slot], phase ^ 1u);          // out of work: tell the consumers and stop
             stage_of[slot] = kDone;
             mbar_arrive(&full[slot]);
+            if (work) {                                   // every fetched chunk index has been consumed: done with the counter
+                const unsigned long long finished = atomicAdd(work + 1, 1ull);
+                if (finished == gridDim.x - 1) {          // last producer out: leave the pair clean for the next level
+                    work[0] = 0ull;
+                    work[1] = 0ull;
+                    __threadfence();
+                }
+            }
         }
     } else {
         // ===== consumers =====
@@ -1119,17 +1127,6 @@ plf_newview_batch(const BatchOp *__restrict__ ops, int n_ops, size_t n,
         }
     }
     if (scaler_sum) block_add_u64<THREADS>(my_sum, scaler_sum);
-    if (work) {
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const unsigned long long finished = atomicAdd(work + 1, 1ull);
-            if (finished == gridDim.x - 1) {      // last CTA out: leave the pair clean for the next level
-                work[0] = 0ull;
-                work[1] = 0ull;
-                __threadfence();
-            }
-        }
-    }
 }
 
 // ---------------------------------------------------------------------------------------------
