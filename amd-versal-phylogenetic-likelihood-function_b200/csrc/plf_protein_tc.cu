@@ -7,7 +7,7 @@
 //
 //        3xTF32:   A.B  ~=  A_hi.B_hi + A_lo.B_hi + A_hi.B_lo,     x_hi = rna_tf32(x), x_lo = rna_tf32(x - x_hi)
 //
-// on tcgen05.mma (kind::tf32, M = 128 sites, N = 32 >= 20, K = 24 >= 20 in three K = 8 steps), fp32 accumulation in
+// on tcgen05.mma (kind::tf32, M = 128 sites, N = 24 >= 20, K = 24 >= 20 in three K = 8 steps), fp32 accumulation in
 // TMEM.  Each operand keeps 22 significant bits, the dropped lo.lo term is 2^-22 relative: fp32-class accuracy, but
 // NOT the reference's rounding sequence -- bit-exactness is impossible on tensor cores, so this kernel exists for
 // PLF_MATH_FMA only (<= 1e-5 relative, the tests state it); PLF_MATH_STRICT keeps the FMUL2/FADD kernel.
@@ -42,10 +42,11 @@ constexpr int kS = 20;                       // states
 constexpr int kSite = 80;                    // floats per site
 constexpr int kTile = 128;                   // sites per tile = MMA M = TMEM lanes
 constexpr int kBoxBytes = kS * kTile * 4;    // one (category, child) box: 10 240 B
-constexpr int kRing = 6;                     // boxes per group ring
-constexpr int kN = 32;                       // MMA N (>= 20, multiple of 16 for M = 128)
+constexpr int kRing = 5;                     // boxes per group ring (2.5 steps ahead)
+constexpr int kN = 24;                       // MMA N (>= 20).  N = 24 with M = 128 is legal at cta_group::1 (PTX shape table: steps
+                                             // of 8; CUTLASS's static asserts want N % 16 == 0) and keeps the nine matrices at 41 KB
 constexpr int kK = 24;                       // padded K (three K = 8 steps)
-constexpr int kBMat = (kK / 4) * kN * 16;    // one B matrix in canonical K-major layout: 6 chunks x 32 rows x 16 B = 3072 B
+constexpr int kBMat = (kK / 4) * kN * 16;    // one B matrix in canonical K-major layout: 6 chunks x 24 rows x 16 B = 2304 B
 constexpr int kNumB = 9;                     // P_left[4], P_right[4], EV
 constexpr int kThreads = 384;               // 8 worker warps, 2 producer warps, 2 MMA-issuer warps
 
@@ -53,13 +54,14 @@ constexpr int kThreads = 384;               // 8 worker warps, 2 producer warps,
 constexpr size_t kOffRing = 0;                                         // [2 groups][kRing][kBoxBytes]
 constexpr size_t kOffB = kOffRing + 2 * kRing * kBoxBytes;            // [kNumB][2 (hi, lo)][kBMat]
 constexpr size_t kOffBar = kOffB + (size_t)kNumB * 2 * kBMat;         // barriers
-constexpr size_t kSmemBytes = kOffBar + 512;          // 34 mbarriers + the TMEM base address
+constexpr size_t kOffOut = kOffBar + 512;             // after 34 mbarriers + the TMEM base address
+constexpr size_t kSmemBytes = kOffOut + 2 * 4 * kBoxBytes;   // output staging: [2 groups][4 categories] boxes of {20 floats x 128 sites}
 
 // TMEM columns of one group (the second group sits 256 columns further)
 constexpr uint32_t kColAccA = 0, kColAccB = 32, kColAccX = 64;
 constexpr uint32_t kColAH1 = 96, kColAL1 = 120, kColAH2 = 144, kColAL2 = 168, kColPH = 192, kColPL = 216;
 
-// tcgen05 instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N = 32, M = 128
+// tcgen05 instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N = 24, M = 128
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
 
 __device__ __forceinline__ uint32_t rna_tf32(float x)
@@ -155,6 +157,17 @@ __device__ __forceinline__ void tma_box(void *smem_dst, const CUtensorMap *map, 
                  :: "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
 
+// shared -> global tensor copy of one {20 floats x 128 sites} box (SASS UTMASTG), bulk async-group of the issuing thread;
+// rows past the end of the tensor are clipped by the TMA unit
+__device__ __forceinline__ void tma_store_box(const CUtensorMap *map, int c0, int c1, const void *smem_src)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                 :: "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(smem_src)) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 __device__ __forceinline__ void st_global_v8(float *p, const float *v)
 {
     asm volatile("st.global.cs.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
@@ -181,7 +194,7 @@ __device__ __forceinline__ void stage_b(unsigned char *smem_b, int m, const floa
 
 __global__ void __launch_bounds__(kThreads, 1)
 plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
-                  const float *__restrict__ ev, const float *__restrict__ pl, const float *__restrict__ pr,
+                  const __grid_constant__ CUtensorMap map3, const float *__restrict__ ev, const float *__restrict__ pl, const float *__restrict__ pr,
                   float *__restrict__ x3, unsigned char *__restrict__ scaler, const int *__restrict__ wgt, size_t n,
                   unsigned long long *__restrict__ scaler_sum, const int *__restrict__ cnt1, const int *__restrict__ cnt2,
                   int *__restrict__ cnt3, int flags)
@@ -410,22 +423,43 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
             for (int c = 0; c < 4; ++c)
 #pragma unroll
                 for (int l = 0; l < kS; ++l) small = small && (fabsf(out[c][l]) < kMinLikelihood);
-            if (site < n) {
-                if (small) {
+            if (small) {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c)
+                for (int c = 0; c < 4; ++c)
 #pragma unroll
-                        for (int l = 0; l < kS; ++l) out[c][l] = __fmul_rn(out[c][l], kTwoToThe32);
+                    for (int l = 0; l < kS; ++l) out[c][l] = __fmul_rn(out[c][l], kTwoToThe32);
+            }
+            // Store.  A site's 320 bytes are contiguous in x3, but the lanes of a warp are 320 B apart: direct 256-bit
+            // stores are 32 sector requests per instruction, 1280 per tile and group, and cost ~1900 of the ~6800 cycles
+            // per tile (clock64 trace, profiles/r02_protein_tc.md).  Instead every thread writes its row into four
+            // {20 floats x 128 sites} staging boxes -- the layout of the input boxes, row pitch 80 B, conflict-free -- and
+            // one thread hands them to the TMA unit (tensor stores, SASS UTMASTG): asynchronous, whole rows, rows past the
+            // end of the site range clipped by the unit.
+            {
+                unsigned char *stage = smem + kOffOut + (size_t)g * 4 * kBoxBytes;
+                if (t == 0) bulk_wait_read_all();              // the previous tile's stores have read the staging boxes
+                group_sync(g);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float4 *dst = reinterpret_cast<float4 *>(stage + (size_t)c * kBoxBytes + (size_t)t * (kS * 4));
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) dst[q] = make_float4(out[c][4 * q], out[c][4 * q + 1], out[c][4 * q + 2], out[c][4 * q + 3]);
                 }
-                float *dst = x3 + site * kSite;
-                const float *flat = &out[0][0];
+                fence_proxy_async_smem();                      // generic-proxy writes -> visible to the TMA unit
+                group_sync(g);
+                if (t == 0) {
 #pragma unroll
-                for (int i = 0; i < kSite / 8; ++i) st_global_v8(dst + 8 * i, flat + 8 * i);
+                    for (int c = 0; c < 4; ++c) tma_store_box(&map3, c * kS, (int)(tile * kTile), stage + (size_t)c * kBoxBytes);
+                    bulk_commit();
+                }
+            }
+            if (site < n) {
                 if (scaler) scaler[site] = small ? 1 : 0;
                 if (cnt3) cnt3[site] = (cnt1 ? __ldg(cnt1 + site) : 0) + (cnt2 ? __ldg(cnt2 + site) : 0) + (small ? 1 : 0);
                 if (small) my_sum += wgt ? (unsigned long long)(long long)wgt[site] : 1ull;
             }
         }
+        if (t == 0) bulk_wait_all();                           // every tensor store of this group has completed
     }
     if (scaler_sum) block_add_u64<kThreads>(my_sum, scaler_sum);
     tc_fence_before();
@@ -477,15 +511,15 @@ int launch_newview_aa_tc(const float *x1, const float *x2, float *x3, unsigned c
     int dev = 0, sms = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
         return PLF_ERR_CUDA;
-    CUtensorMap m1, m2;
-    if (!tc::make_map(&m1, x1, n) || !tc::make_map(&m2, x2, n)) return PLF_ERR_CUDA;
+    CUtensorMap m1, m2, m3;
+    if (!tc::make_map(&m1, x1, n) || !tc::make_map(&m2, x2, n) || !tc::make_map(&m3, x3, n)) return PLF_ERR_CUDA;
     if (cudaFuncSetAttribute(tc::plf_newview_aa_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes) != cudaSuccess)
         return PLF_ERR_CUDA;
     const size_t tiles = (n + tc::kTile - 1) / tc::kTile;
     size_t grid = (tiles + 1) / 2;
     if (grid > (size_t)sms) grid = sms;
     if (flags & kAaSingleCta) grid = 1;
-    tc::plf_newview_aa_tc<<<(int)grid, tc::kThreads, tc::kSmemBytes, stream>>>(m1, m2, ev, pl, pr, x3, scaler, wgt, n, scaler_sum, cnt1, cnt2,
+    tc::plf_newview_aa_tc<<<(int)grid, tc::kThreads, tc::kSmemBytes, stream>>>(m1, m2, m3, ev, pl, pr, x3, scaler, wgt, n, scaler_sum, cnt1, cnt2,
                                                                               cnt3, flags & kFlagFencedRelease);
     count_launches(1);
     return cudaGetLastError() == cudaSuccess ? PLF_OK : PLF_ERR_CUDA;
