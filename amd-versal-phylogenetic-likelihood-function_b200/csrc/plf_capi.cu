@@ -270,6 +270,15 @@ int work_pair(plf_ctx *ctx, cudaStream_t stream, unsigned long long **out)
 // Ring-slot release mechanism of the bulk-copy kernels (plf_kernels.cuh, mbar_release_slot*): the fenced release is
 // the default of the DRAM-bound kernels; PLF_SAFE_RELEASE=1 forces it everywhere (also the tree kernel), =0 forces the
 // data-dependency release everywhere, so a field failure can be bisected without a rebuild.
+// For the 20-state dispatcher, which picks the kernel (and with it the family default) itself: the caller's explicit
+// choice, or plf::kAaReleaseUnset.
+int release_request(const plf_launch_opts *opts)
+{
+    if (opts && (opts->flags & PLF_LAUNCH_FENCED_RELEASE)) return plf::kFlagFencedRelease;
+    if (opts && (opts->flags & PLF_LAUNCH_DEP_RELEASE)) return 0;
+    return plf::kAaReleaseUnset;
+}
+
 int release_flag(const plf_launch_opts *opts, bool default_fenced)
 {
     if (opts && (opts->flags & PLF_LAUNCH_FENCED_RELEASE)) return plf::kFlagFencedRelease;
@@ -423,7 +432,7 @@ int launch_states(plf_ctx *ctx, const float *x1, const float *x2, float *x3, uns
                   const plf_launch_opts *opts, cudaStream_t stream)
 {
     const int math = opts ? opts->math_mode : PLF_MATH_STRICT;
-    int rc = plf::launch_newview_aa(x1, x2, x3, scaler, ev, pl, pr, wgt, n, sum, math, 0, 0, release_flag(opts, true), stream);
+    int rc = plf::launch_newview_aa(x1, x2, x3, scaler, ev, pl, pr, wgt, n, sum, math, 0, 0, release_request(opts), stream);
     if (rc != PLF_OK) return fail(ctx, rc, "20-state newview launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     return PLF_OK;
 }
@@ -1216,7 +1225,7 @@ int plf_newview_states_device(int states, const float *x1, const float *x2, floa
         return launch_newview(nullptr, x1, x2, x3, scaler, sc->mats, sc->mats + 16, sc->mats + 80, wgt, n, scaler_sum, opts, st);
     }
     if (opts && opts->ev_per_category) return fail(nullptr, PLF_ERR_INVALID, "ev_per_category is a DNA gen-mode option");
-    const int aa_flags = release_flag(opts, true) | ((opts && (opts->flags & PLF_LAUNCH_SINGLE_CTA)) ? plf::kAaSingleCta : 0);
+    const int aa_flags = release_request(opts) | ((opts && (opts->flags & PLF_LAUNCH_SINGLE_CTA)) ? plf::kAaSingleCta : 0);
     // HOST matrices: by value into the stream's staging record (as for S = 4), then the kernel reads device memory
     plf::StreamScratch *sc = nullptr;
     int rc = plf::stream_scratch(st, &sc);

@@ -373,8 +373,12 @@ int launch_newview_aa(const float *x1, const float *x2, float *x3, unsigned char
     // CUDA-core FMA kernel on B200); shorter calls keep the CUDA-core kernel, whose prologue is lighter.
     if (variant == kAaVariantTensorCore || (variant == 0 && threads == 0 && math == PLF_MATH_FMA && n >= kAaTensorCoreMinSites)) {
         if (math != PLF_MATH_FMA || (threads != 0 && threads != 384)) return PLF_ERR_INVALID;
+        // slot release: the tensor-core kernel is not DRAM-bound and the fence costs it 3 % (5.70 against 5.88 G sites/s),
+        // so its own default is the data-dependency release; PLF_SAFE_RELEASE / plf_set_release_mode / opts->flags override
+        if (flags & kAaReleaseUnset) flags = (flags & ~(kAaReleaseUnset | kFlagFencedRelease)) | (fenced_release(false) ? kFlagFencedRelease : 0);
         return launch_newview_aa_tc(x1, x2, x3, scaler, ev, pl, pr, wgt, n, scaler_sum, flags, stream, cnt1, cnt2, cnt3);
     }
+    if (flags & kAaReleaseUnset) flags = (flags & ~(kAaReleaseUnset | kFlagFencedRelease)) | (fenced_release(true) ? kFlagFencedRelease : 0);
     const AaSel k = aa_select(math, variant, threads);
     if (!k.fn) return PLF_ERR_INVALID;
     int dev = 0, sms = 0;

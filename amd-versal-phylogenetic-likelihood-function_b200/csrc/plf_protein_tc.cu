@@ -34,6 +34,10 @@
 
 #include <cuda.h>
 
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
 namespace plf {
 
 namespace tc {
@@ -192,12 +196,13 @@ __device__ __forceinline__ void stage_b(unsigned char *smem_b, int m, const floa
     }
 }
 
+template <bool TRACE>
 __global__ void __launch_bounds__(kThreads, 1)
 plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
                   const __grid_constant__ CUtensorMap map3, const float *__restrict__ ev, const float *__restrict__ pl, const float *__restrict__ pr,
                   float *__restrict__ x3, unsigned char *__restrict__ scaler, const int *__restrict__ wgt, size_t n,
                   unsigned long long *__restrict__ scaler_sum, const int *__restrict__ cnt1, const int *__restrict__ cnt2,
-                  int *__restrict__ cnt3, int flags)
+                  int *__restrict__ cnt3, int flags, long long *__restrict__ trace)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char *ring = smem + kOffRing;
@@ -335,13 +340,26 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
         tc_wait_st();
 
         uint32_t slot = 0, phase = 0, ph_ab = 0, ph_x = 0;
+        // PLF_TC_TRACE (debug): clock64 stamps of one thread (block 0, group 0, row 0) at the hand-off points of every step
+        const bool tracing = TRACE && trace && blockIdx.x == 0 && threadIdx.x == 0;
+        long long *tp = trace;
+        auto stamp = [&](int id) {
+            if constexpr (TRACE) {
+                if (tracing && tp < trace + 16 * 4096) {
+                    *tp++ = (long long)id;
+                    *tp++ = clock64();
+                }
+            }
+        };
 
         // convert: both children of the NEXT (tile, category) in ring order: ring -> registers -> hi/lo -> TMEM, then the
         // 18 branch MMAs  a = x1 . P_left[c]^T,  b = x2 . P_right[c]^T  (hi.hi + lo.hi + hi.lo, three K = 8 steps each)
         auto convert = [&]() {
 #pragma unroll
             for (int child = 0; child < 2; ++child) {
+                stamp(child ? 3 : 1);
                 mbar_wait(&full[g * kRing + slot], phase);
+                stamp(child ? 4 : 2);
                 const float4 *row = reinterpret_cast<const float4 *>(gring + (size_t)slot * kBoxBytes + (size_t)t * (kS * 4));
                 float4 v[5];
 #pragma unroll
@@ -377,17 +395,21 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(child ? &rdy_b[g] : &rdy_a[g]);
+                stamp(child ? 6 : 5);
             }
         };
         // finish_ab: p = a * b in registers, split, back to TMEM as the A operand of the 9 EV MMAs
         auto finish_ab = [&]() {
+            stamp(7);
             mbar_wait(&mma_ab[g], ph_ab);
+            stamp(8);
             ph_ab ^= 1u;
             tc_fence_after();
             float a[kS], b[kS];
             tmem_ld20(trow + kColAccA, a);
             tmem_ld20(trow + kColAccB, b);
             tc_wait_ld();
+            stamp(9);
             uint32_t hi[kS], lo[kS];
 #pragma unroll
             for (int k = 0; k < kS; ++k) split_trunc(a[k] * b[k], hi[k], lo[k]);
@@ -397,6 +419,7 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&rdy_p[g]);
+            stamp(10);
         };
 
         // Software pipeline over the (tile, category) steps of this group: the EV product of step s runs on the tensor
@@ -406,23 +429,28 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
         if (first < n_tiles) convert();
         for (size_t tile = first; tile < n_tiles; tile += stride) {
             float out[4][kS];
+            // running maximum of |x3| over the site's 80 results, as integer maxima of the magnitude bits in four
+            // independent chains (a NaN or Inf has larger magnitude bits than any finite value, so "all 80 below 2^-32"
+            // keeps the reference's meaning); folded in category by category while the tensor core works on the next step
+            uint32_t mx[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 finish_ab();
                 if (c < 3 || tile + stride < n_tiles) convert();
+                stamp(11);
                 mbar_wait(&mma_x[g], ph_x);
+                stamp(12);
                 ph_x ^= 1u;
                 tc_fence_after();
                 tmem_ld20(trow + kColAccX, out[c]);
                 tc_wait_ld();
+#pragma unroll
+                for (int l = 0; l < kS; ++l) mx[l & 3] = max(mx[l & 3], __float_as_uint(out[c][l]) & 0x7FFFFFFFu);
+                stamp(13);
             }
             // --- the site's 80 results: threshold test, rescale, store ---
             const size_t site = tile * kTile + (size_t)t;
-            bool small = true;
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-#pragma unroll
-                for (int l = 0; l < kS; ++l) small = small && (fabsf(out[c][l]) < kMinLikelihood);
+            const bool small = max(max(mx[0], mx[1]), max(mx[2], mx[3])) < 0x2F800000u;      // bits of 2^-32
             if (small) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
@@ -437,16 +465,22 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
             // end of the site range clipped by the unit.
             {
                 unsigned char *stage = smem + kOffOut + (size_t)g * 4 * kBoxBytes;
+                stamp(15);
                 if (t == 0) bulk_wait_read_all();              // the previous tile's stores have read the staging boxes
+                stamp(16);
                 group_sync(g);
+                stamp(17);
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     float4 *dst = reinterpret_cast<float4 *>(stage + (size_t)c * kBoxBytes + (size_t)t * (kS * 4));
 #pragma unroll
                     for (int q = 0; q < 5; ++q) dst[q] = make_float4(out[c][4 * q], out[c][4 * q + 1], out[c][4 * q + 2], out[c][4 * q + 3]);
                 }
+                stamp(18);
                 fence_proxy_async_smem();                      // generic-proxy writes -> visible to the TMA unit
+                stamp(19);
                 group_sync(g);
+                stamp(20);
                 if (t == 0) {
 #pragma unroll
                     for (int c = 0; c < 4; ++c) tma_store_box(&map3, c * kS, (int)(tile * kTile), stage + (size_t)c * kBoxBytes);
@@ -458,6 +492,7 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
                 if (cnt3) cnt3[site] = (cnt1 ? __ldg(cnt1 + site) : 0) + (cnt2 ? __ldg(cnt2 + site) : 0) + (small ? 1 : 0);
                 if (small) my_sum += wgt ? (unsigned long long)(long long)wgt[site] : 1ull;
             }
+            stamp(14);
         }
         if (t == 0) bulk_wait_all();                           // every tensor store of this group has completed
     }
@@ -513,22 +548,43 @@ int launch_newview_aa_tc(const float *x1, const float *x2, float *x3, unsigned c
         return PLF_ERR_CUDA;
     CUtensorMap m1, m2, m3;
     if (!tc::make_map(&m1, x1, n) || !tc::make_map(&m2, x2, n) || !tc::make_map(&m3, x3, n)) return PLF_ERR_CUDA;
-    if (cudaFuncSetAttribute(tc::plf_newview_aa_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes) != cudaSuccess)
+    const char *trace_path = getenv("PLF_TC_TRACE");
+    auto kernel = trace_path ? tc::plf_newview_aa_tc<true> : tc::plf_newview_aa_tc<false>;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes) != cudaSuccess)
         return PLF_ERR_CUDA;
     const size_t tiles = (n + tc::kTile - 1) / tc::kTile;
     size_t grid = (tiles + 1) / 2;
     if (grid > (size_t)sms) grid = sms;
     if (flags & kAaSingleCta) grid = 1;
-    tc::plf_newview_aa_tc<<<(int)grid, tc::kThreads, tc::kSmemBytes, stream>>>(m1, m2, m3, ev, pl, pr, x3, scaler, wgt, n, scaler_sum, cnt1, cnt2,
-                                                                              cnt3, flags & kFlagFencedRelease);
+    // PLF_TC_TRACE=<file> (debug): clock64 stamps of one worker thread at the hand-off points of its steps, dumped as text
+    // (every stamp costs the traced warp ~140 cycles: read the SHARES after subtracting that, tools/tc_trace.py)
+    long long *d_trace = nullptr;
+    constexpr size_t kTraceWords = 16 * 4096;
+    if (trace_path) {
+        if (cudaMalloc(&d_trace, kTraceWords * sizeof(long long)) != cudaSuccess) return PLF_ERR_NOMEM;
+        cudaMemsetAsync(d_trace, 0, kTraceWords * sizeof(long long), stream);
+    }
+    kernel<<<(int)grid, tc::kThreads, tc::kSmemBytes, stream>>>(m1, m2, m3, ev, pl, pr, x3, scaler, wgt, n, scaler_sum, cnt1, cnt2,
+                                                                              cnt3, flags & kFlagFencedRelease, d_trace);
     count_launches(1);
-    return cudaGetLastError() == cudaSuccess ? PLF_OK : PLF_ERR_CUDA;
+    const bool ok = cudaGetLastError() == cudaSuccess;
+    if (d_trace) {
+        std::vector<long long> h(kTraceWords);
+        cudaStreamSynchronize(stream);
+        cudaMemcpy(h.data(), d_trace, kTraceWords * sizeof(long long), cudaMemcpyDeviceToHost);
+        cudaFree(d_trace);
+        if (FILE *f = fopen(trace_path, "w")) {
+            for (size_t i = 0; i + 1 < kTraceWords && h[i] != 0; i += 2) fprintf(f, "%lld %lld\n", h[i], h[i + 1]);
+            fclose(f);
+        }
+    }
+    return ok ? PLF_OK : PLF_ERR_CUDA;
 }
 
 int aa_tc_kernel_info(int *regs, int *block_threads, size_t *smem, int *tile_sites)
 {
     cudaFuncAttributes attr;
-    if (cudaFuncGetAttributes(&attr, tc::plf_newview_aa_tc) != cudaSuccess) return PLF_ERR_CUDA;
+    if (cudaFuncGetAttributes(&attr, tc::plf_newview_aa_tc<false>) != cudaSuccess) return PLF_ERR_CUDA;
     if (regs) *regs = attr.numRegs;
     if (block_threads) *block_threads = tc::kThreads;
     if (smem) *smem = tc::kSmemBytes;

@@ -48,6 +48,7 @@ int launch_newview_aa(const float *x1, const float *x2, float *x3, unsigned char
                       const float *pl, const float *pr, const int *wgt, size_t n, unsigned long long *scaler_sum,
                       int math, int variant, int threads, int flags, cudaStream_t stream, const int *cnt1 = nullptr,
                       const int *cnt2 = nullptr, int *cnt3 = nullptr);
+constexpr int kAaReleaseUnset = 1 << 17;  // launch flag of launch_newview_aa: no explicit slot-release choice, use the kernel's own default
 constexpr int kAaSingleCta = 1 << 16;     // launch flag of launch_newview_aa: one block (stress-test hook); low bits = kernel flags
 // the tensor-core (tcgen05 / TMEM, 3xTF32) 20-state kernel of plf_protein_tc.cu: tolerance mode only
 int launch_newview_aa_tc(const float *x1, const float *x2, float *x3, unsigned char *scaler, const float *ev, const float *pl,

@@ -209,7 +209,7 @@ int build_graph_states(plf_tree *t)
     TREE_CUDA(t, cudaStreamBeginCapture(t->stream, cudaStreamCaptureModeThreadLocal));
     cudaError_t e = cudaMemsetAsync(t->d_sum, 0, sizeof(unsigned long long), t->stream);
     int rc = PLF_OK;
-    const int flags = plf::fenced_release(true) ? plf::kFlagFencedRelease : 0;
+    const int flags = plf::kAaReleaseUnset;          // every kernel's own default, or the process-wide override
     for (size_t l = 0; l < t->levels.size() && e == cudaSuccess && rc == PLF_OK; ++l)
         for (int k : t->levels[l]) {
             rc = plf::launch_newview_aa(node_clv(t, t->left[k]), node_clv(t, t->right[k]), node_clv(t, (int)t->n_tips + k), nullptr,

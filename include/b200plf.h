@@ -182,7 +182,7 @@ typedef struct plf_launch_opts {
 /* plf_launch_opts.flags.  The ring kernels hand a shared-memory slot back to the bulk-copy engine either behind
  * fence.proxy.async (FENCED: the release as the PTX memory model words it; default of the DRAM-bound kernels) or
  * behind a data dependency on the loaded registers (DEP: no fence; default of the tree kernel, whose compressed-tip
- * levels the fence slows down).  The environment variable PLF_SAFE_RELEASE=1 / =0 forces one of them for every
+ * levels the fence slows down, and of the tensor-core 20-state kernel, which it costs 3 %).  The environment variable PLF_SAFE_RELEASE=1 / =0 forces one of them for every
  * kernel of the process, so a suspected slot race can be bisected in the field without a rebuild.               */
 typedef enum plf_launch_flags {
     PLF_LAUNCH_NO_PDL = 1,          /* do not launch with programmatic stream serialization            */
