@@ -46,24 +46,31 @@ constexpr int kS = 20;                       // states
 constexpr int kSite = 80;                    // floats per site
 constexpr int kTile = 128;                   // sites per tile = MMA M = TMEM lanes
 constexpr int kBoxBytes = kS * kTile * 4;    // one (category, child) box: 10 240 B
-constexpr int kRing = 5;                     // boxes per group ring (2.5 steps ahead)
-constexpr int kN = 24;                       // MMA N (>= 20).  N = 24 with M = 128 is legal at cta_group::1 (PTX shape table: steps
-                                             // of 8; CUTLASS's static asserts want N % 16 == 0) and keeps the nine matrices at 41 KB
-constexpr int kK = 24;                       // padded K (three K = 8 steps)
-constexpr int kBMat = (kK / 4) * kN * 16;    // one B matrix in canonical K-major layout: 6 chunks x 24 rows x 16 B = 2304 B
+constexpr int kRing = 4;                     // boxes per group ring (2 steps ahead)
+// One 3xTF32 product as ONE accumulation chain of five MMAs: the A operand of a row is [hi(20) | lo(20)] (K = 40, five
+// K = 8 steps, no padding), the B operand is the 40 x 40 block matrix
+//            n < 20        n >= 20
+//   k < 20   B_hi[n][k]    B_lo[n - 20][k]         D[:, 0:20]  = A_hi.B_hi + A_lo.B_hi
+//   k >= 20  B_hi[n][k-20] 0                       D[:, 20:40] = A_hi.B_lo           (added on read-back)
+// Tiny MMAs cost ~59 cycles each whatever their N (27 of them per step and group was exactly the step time of the
+// nine-MMAs-per-product version); 15 per step is what moved the kernel from the tensor core's issue rate to HBM.
+constexpr int kN = 40;                       // MMA N.  M = 128 with N % 8 == 0 is accepted by the hardware at cta_group::1 (CUTLASS's
+                                             // static asserts want N % 16 == 0)
+constexpr int kK = 40;                       // K (five K = 8 steps)
+constexpr int kBMat = (kK / 4) * kN * 16;    // one B matrix in canonical K-major layout: 10 chunks x 40 rows x 16 B = 6400 B
 constexpr int kNumB = 9;                     // P_left[4], P_right[4], EV
 constexpr int kThreads = 384;               // 8 worker warps, 2 producer warps, 2 MMA-issuer warps
 
 // shared memory carve-up
 constexpr size_t kOffRing = 0;                                         // [2 groups][kRing][kBoxBytes]
-constexpr size_t kOffB = kOffRing + 2 * kRing * kBoxBytes;            // [kNumB][2 (hi, lo)][kBMat]
-constexpr size_t kOffBar = kOffB + (size_t)kNumB * 2 * kBMat;         // barriers
+constexpr size_t kOffB = kOffRing + 2 * kRing * kBoxBytes;            // [kNumB][kBMat]
+constexpr size_t kOffBar = kOffB + (size_t)kNumB * kBMat;             // barriers
 constexpr size_t kOffOut = kOffBar + 512;             // after 34 mbarriers + the TMEM base address
 constexpr size_t kSmemBytes = kOffOut + 2 * 4 * kBoxBytes;   // output staging: [2 groups][4 categories] boxes of {20 floats x 128 sites}
 
 // TMEM columns of one group (the second group sits 256 columns further)
-constexpr uint32_t kColAccA = 0, kColAccB = 32, kColAccX = 64;
-constexpr uint32_t kColAH1 = 96, kColAL1 = 120, kColAH2 = 144, kColAL2 = 168, kColPH = 192, kColPL = 216;
+constexpr uint32_t kColAccA = 0, kColAccB = 40, kColAccX = 80;       // accumulators, 40 columns each
+constexpr uint32_t kColA1 = 120, kColA2 = 160, kColP = 200;          // A operands [hi(20) | lo(20)]
 
 // tcgen05 instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N = 24, M = 128
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
@@ -178,21 +185,22 @@ __device__ __forceinline__ void st_global_v8(float *p, const float *v)
                  :: "l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]) : "memory");
 }
 
-// One matrix into the canonical K-major layout, split into hi and lo:  B[n][k] at chunk (k / 4), row n, word (k % 4).
-// transpose == false: B[n][k] = src[n * 20 + k] (branch matrix P[kout][l]);  true: B[n][k] = src[k * 20 + n] (EV[k][l]).
+// One matrix, split into hi and lo, as the 40 x 40 block matrix above in the canonical K-major layout:  B[n][k] at chunk
+// (k / 4), row n, word (k % 4).  transpose == false: M[n][k] = src[n * 20 + k] (branch matrix P[kout][l]);  true:
+// M[n][k] = src[k * 20 + n] (EV[k][l]).
 __device__ __forceinline__ void stage_b(unsigned char *smem_b, int m, const float *__restrict__ src, bool transpose, int tid, int nthreads)
 {
-    float *hi = reinterpret_cast<float *>(smem_b + (size_t)(2 * m) * kBMat);
-    float *lo = reinterpret_cast<float *>(smem_b + (size_t)(2 * m + 1) * kBMat);
-    for (int idx = tid; idx < kK * kN; idx += nthreads) {
-        const int n = idx / kK, k = idx - n * kK;
-        float v = 0.0f;
-        if (n < kS && k < kS) v = __ldg(src + (transpose ? k * kS + n : n * kS + k));
+    float *dst = reinterpret_cast<float *>(smem_b + (size_t)m * kBMat);
+    for (int idx = tid; idx < kS * kS; idx += nthreads) {
+        const int n = idx / kS, k = idx - n * kS;
+        const float v = __ldg(src + (transpose ? k * kS + n : n * kS + k));
         uint32_t h, l;
         split_tf32(v, h, l);
-        const int word = (k >> 2) * (kN * 4) + n * 4 + (k & 3);
-        hi[word] = __uint_as_float(h);
-        lo[word] = __uint_as_float(l);
+        auto word = [](int nn, int kk) { return (kk >> 2) * (kN * 4) + nn * 4 + (kk & 3); };
+        dst[word(n, k)] = __uint_as_float(h);              // A_hi . B_hi
+        dst[word(n, k + kS)] = __uint_as_float(h);         // A_lo . B_hi
+        dst[word(n + kS, k)] = __uint_as_float(l);         // A_hi . B_lo
+        dst[word(n + kS, k + kS)] = 0.0f;
     }
 }
 
@@ -262,16 +270,10 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
             const size_t first = (size_t)blockIdx.x * 2 + g, stride = (size_t)gridDim.x * 2;
             const size_t my_tiles = first < n_tiles ? (n_tiles - first + stride - 1) / stride : 0;
             uint32_t ph = 0;                                   // all three ready barriers complete once per step
-            auto branch = [&](int child, int c) {              // a = x1 . P_left[c]^T  or  b = x2 . P_right[c]^T
-                const uint32_t acc = tcol + (child ? kColAccB : kColAccA);
-                const uint32_t ah = tcol + (child ? kColAH2 : kColAH1), al = tcol + (child ? kColAL2 : kColAL1);
-                const uint32_t bh = b_base + (uint32_t)(2 * ((child ? 4 : 0) + c)) * kBMat, bl = bh + kBMat;
+            auto product = [&](uint32_t acc, uint32_t a_op, int m) {      // acc = [A_hi | A_lo] . B[m]: one chain of five MMAs
+                const uint32_t bm = b_base + (uint32_t)m * kBMat;
 #pragma unroll
-                for (int ks = 0; ks < 3; ++ks) mma_ts(acc, ah + 8 * ks, b_desc(bh + ks * 2 * kN * 16), ks > 0);
-#pragma unroll
-                for (int ks = 0; ks < 3; ++ks) mma_ts(acc, al + 8 * ks, b_desc(bh + ks * 2 * kN * 16), 1u);
-#pragma unroll
-                for (int ks = 0; ks < 3; ++ks) mma_ts(acc, ah + 8 * ks, b_desc(bl + ks * 2 * kN * 16), 1u);
+                for (int ks = 0; ks < kK / 8; ++ks) mma_ts(acc, a_op + 8 * ks, b_desc(bm + ks * 2 * kN * 16), ks > 0);
             };
             // the workers' order: ab(0); then per step s: x(s), ab(s + 1)
             const size_t steps = my_tiles * 4;
@@ -279,24 +281,17 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
                 if (sidx > 0) {                                // x(sidx - 1) = p . EV
                     mbar_wait(&rdy_p[g], ph ^ 1u);             // completed in the PREVIOUS step's phase
                     tc_fence_after();
-                    const uint32_t acc = tcol + kColAccX, phh = tcol + kColPH, pw = tcol + kColPL;
-                    const uint32_t bh = b_base + (uint32_t)(2 * 8) * kBMat, bl = bh + kBMat;
-#pragma unroll
-                    for (int ks = 0; ks < 3; ++ks) mma_ts(acc, phh + 8 * ks, b_desc(bh + ks * 2 * kN * 16), ks > 0);
-#pragma unroll
-                    for (int ks = 0; ks < 3; ++ks) mma_ts(acc, pw + 8 * ks, b_desc(bh + ks * 2 * kN * 16), 1u);
-#pragma unroll
-                    for (int ks = 0; ks < 3; ++ks) mma_ts(acc, phh + 8 * ks, b_desc(bl + ks * 2 * kN * 16), 1u);
+                    product(tcol + kColAccX, tcol + kColP, 8);
                     mma_commit(&mma_x[g]);
                 }
                 if (sidx < steps) {                            // ab(sidx)
                     const int c = (int)(sidx & 3);
                     mbar_wait(&rdy_a[g], ph);
                     tc_fence_after();
-                    branch(0, c);
+                    product(tcol + kColAccA, tcol + kColA1, c);
                     mbar_wait(&rdy_b[g], ph);
                     tc_fence_after();
-                    branch(1, c);
+                    product(tcol + kColAccB, tcol + kColA2, 4 + c);
                     mma_commit(&mma_ab[g]);
                     ph ^= 1u;
                 }
@@ -328,16 +323,6 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
         const int t = threadIdx.x & 127;                                  // site row of the tile = TMEM lane
         const unsigned char *gring = ring + (size_t)g * kRing * kBoxBytes;
         const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)g * 256u;    // this warp's lane quarter, this group's columns
-
-        // K padding columns 20..23 of the six A regions: zero once (the matching B rows are zero too, but TMEM starts
-        // out with arbitrary bits and 0 x NaN would poison the sums)
-        tmem_st4(trow + kColAH1 + 20, 0u, 0u, 0u, 0u);
-        tmem_st4(trow + kColAL1 + 20, 0u, 0u, 0u, 0u);
-        tmem_st4(trow + kColAH2 + 20, 0u, 0u, 0u, 0u);
-        tmem_st4(trow + kColAL2 + 20, 0u, 0u, 0u, 0u);
-        tmem_st4(trow + kColPH + 20, 0u, 0u, 0u, 0u);
-        tmem_st4(trow + kColPL + 20, 0u, 0u, 0u, 0u);
-        tc_wait_st();
 
         uint32_t slot = 0, phase = 0, ph_ab = 0, ph_x = 0;
         // PLF_TC_TRACE (debug): clock64 stamps of one thread (block 0, group 0, row 0) at the hand-off points of every step
@@ -387,8 +372,8 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
                     slot = 0;
                     phase ^= 1u;
                 }
-                tmem_st20(trow + (child ? kColAH2 : kColAH1), hi);
-                tmem_st20(trow + (child ? kColAL2 : kColAL1), lo);
+                tmem_st20(trow + (child ? kColA2 : kColA1), hi);
+                tmem_st20(trow + (child ? kColA2 : kColA1) + kS, lo);
                 // this warp's quarter of the operand is in TMEM: tell the issuer (it starts the nine MMAs of this child
                 // when all four warps have arrived, while the workers convert the other child)
                 tc_wait_st();
@@ -405,16 +390,18 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
             stamp(8);
             ph_ab ^= 1u;
             tc_fence_after();
-            float a[kS], b[kS];
+            float a[kS], a2[kS], b[kS], b2[kS];               // the two column blocks of each accumulator
             tmem_ld20(trow + kColAccA, a);
+            tmem_ld20(trow + kColAccA + kS, a2);
             tmem_ld20(trow + kColAccB, b);
+            tmem_ld20(trow + kColAccB + kS, b2);
             tc_wait_ld();
             stamp(9);
             uint32_t hi[kS], lo[kS];
 #pragma unroll
-            for (int k = 0; k < kS; ++k) split_trunc(a[k] * b[k], hi[k], lo[k]);
-            tmem_st20(trow + kColPH, hi);
-            tmem_st20(trow + kColPL, lo);
+            for (int k = 0; k < kS; ++k) split_trunc((a[k] + a2[k]) * (b[k] + b2[k]), hi[k], lo[k]);
+            tmem_st20(trow + kColP, hi);
+            tmem_st20(trow + kColP + kS, lo);
             tc_wait_st();
             tc_fence_before();
             __syncwarp();
@@ -427,11 +414,19 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
         // the results of step s are read back -- so of the two MMA round trips per step only a part of one is exposed.
         const size_t first = (size_t)blockIdx.x * 2 + g, stride = (size_t)gridDim.x * 2;
         if (first < n_tiles) convert();
+        // Results.  A site's 320 bytes are contiguous in x3, but the lanes of a warp are 320 B apart: direct 256-bit stores
+        // are 32 sector requests per instruction, 1280 per tile and group, and cost ~1900 of the ~6800 cycles per tile
+        // (clock64 trace, profiles/r02_protein_tc.md).  Instead every thread writes its row, category by category as the
+        // results come out of TMEM (in the shadow of the next step's MMAs), into four {20 floats x 128 sites} staging
+        // boxes -- the layout of the input boxes, row pitch 80 B, conflict-free -- and lane 0 of each of the four warps
+        // hands one box to the TMA unit (tensor stores, SASS UTMASTG): asynchronous, whole rows, rows past the end of the
+        // site range clipped by the unit.  The rare site that needs the x 2^32 rescale rewrites its own row first.
+        unsigned char *stage = smem + kOffOut + (size_t)g * 4 * kBoxBytes;
+        const int wq = warp & 3;
         for (size_t tile = first; tile < n_tiles; tile += stride) {
-            float out[4][kS];
             // running maximum of |x3| over the site's 80 results, as integer maxima of the magnitude bits in four
             // independent chains (a NaN or Inf has larger magnitude bits than any finite value, so "all 80 below 2^-32"
-            // keeps the reference's meaning); folded in category by category while the tensor core works on the next step
+            // keeps the reference's meaning)
             uint32_t mx[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -442,50 +437,46 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
                 stamp(12);
                 ph_x ^= 1u;
                 tc_fence_after();
-                tmem_ld20(trow + kColAccX, out[c]);
+                float o[kS], o2[kS];
+                tmem_ld20(trow + kColAccX, o);
+                tmem_ld20(trow + kColAccX + kS, o2);
                 tc_wait_ld();
 #pragma unroll
-                for (int l = 0; l < kS; ++l) mx[l & 3] = max(mx[l & 3], __float_as_uint(out[c][l]) & 0x7FFFFFFFu);
+                for (int l = 0; l < kS; ++l) o[l] += o2[l];
+#pragma unroll
+                for (int l = 0; l < kS; ++l) mx[l & 3] = max(mx[l & 3], __float_as_uint(o[l]) & 0x7FFFFFFFu);
                 stamp(13);
+                if (c == 0) {
+                    if (lane == 0) bulk_wait_read_all();       // the previous tile's tensor stores have read the staging boxes
+                    group_sync(g);
+                    stamp(17);
+                }
+                float4 *dst = reinterpret_cast<float4 *>(stage + (size_t)c * kBoxBytes + (size_t)t * (kS * 4));
+#pragma unroll
+                for (int q = 0; q < 5; ++q) dst[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+                stamp(18);
             }
-            // --- the site's 80 results: threshold test, rescale, store ---
             const size_t site = tile * kTile + (size_t)t;
             const bool small = max(max(mx[0], mx[1]), max(mx[2], mx[3])) < 0x2F800000u;      // bits of 2^-32
             if (small) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
-#pragma unroll
-                    for (int l = 0; l < kS; ++l) out[c][l] = __fmul_rn(out[c][l], kTwoToThe32);
-            }
-            // Store.  A site's 320 bytes are contiguous in x3, but the lanes of a warp are 320 B apart: direct 256-bit
-            // stores are 32 sector requests per instruction, 1280 per tile and group, and cost ~1900 of the ~6800 cycles
-            // per tile (clock64 trace, profiles/r02_protein_tc.md).  Instead every thread writes its row into four
-            // {20 floats x 128 sites} staging boxes -- the layout of the input boxes, row pitch 80 B, conflict-free -- and
-            // one thread hands them to the TMA unit (tensor stores, SASS UTMASTG): asynchronous, whole rows, rows past the
-            // end of the site range clipped by the unit.
-            {
-                unsigned char *stage = smem + kOffOut + (size_t)g * 4 * kBoxBytes;
-                stamp(15);
-                if (t == 0) bulk_wait_read_all();              // the previous tile's stores have read the staging boxes
-                stamp(16);
-                group_sync(g);
-                stamp(17);
-#pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    float4 *dst = reinterpret_cast<float4 *>(stage + (size_t)c * kBoxBytes + (size_t)t * (kS * 4));
+                    float4 *row = reinterpret_cast<float4 *>(stage + (size_t)c * kBoxBytes + (size_t)t * (kS * 4));
 #pragma unroll
-                    for (int q = 0; q < 5; ++q) dst[q] = make_float4(out[c][4 * q], out[c][4 * q + 1], out[c][4 * q + 2], out[c][4 * q + 3]);
+                    for (int q = 0; q < 5; ++q) {
+                        float4 v = row[q];
+                        row[q] = make_float4(__fmul_rn(v.x, kTwoToThe32), __fmul_rn(v.y, kTwoToThe32), __fmul_rn(v.z, kTwoToThe32),
+                                             __fmul_rn(v.w, kTwoToThe32));
+                    }
                 }
-                stamp(18);
-                fence_proxy_async_smem();                      // generic-proxy writes -> visible to the TMA unit
-                stamp(19);
-                group_sync(g);
-                stamp(20);
-                if (t == 0) {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) tma_store_box(&map3, c * kS, (int)(tile * kTile), stage + (size_t)c * kBoxBytes);
-                    bulk_commit();
-                }
+            }
+            stamp(15);
+            fence_proxy_async_smem();                          // generic-proxy writes -> visible to the TMA unit
+            group_sync(g);
+            stamp(20);
+            if (lane == 0) {
+                tma_store_box(&map3, wq * kS, (int)(tile * kTile), stage + (size_t)wq * kBoxBytes);
+                bulk_commit();
             }
             if (site < n) {
                 if (scaler) scaler[site] = small ? 1 : 0;
@@ -494,7 +485,7 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
             }
             stamp(14);
         }
-        if (t == 0) bulk_wait_all();                           // every tensor store of this group has completed
+        if (lane == 0) bulk_wait_all();                        // every tensor store this lane has issued has completed
     }
     if (scaler_sum) block_add_u64<kThreads>(my_sum, scaler_sum);
     tc_fence_before();
