@@ -3,31 +3,37 @@
 // The 20-state path (the reference's STATES knob) is the one place in scope with a real
 // contraction: per rate category and child, [sites x 20] . [20 x 20], and once more for the EV back-transform
 // (app/src/plf.cpp:29-50 with 4 -> 20 states).  The CUDA-core kernel of plf_protein.cu is bound by shared-memory
-// operand bandwidth and the fp32 pipe (4.97 G sites/s = 0.73 of the HBM copy peak).  Here the three products run as
+// operand bandwidth and the fp32 pipe (4.7 G sites/s in FMA mode).  Here the three products run as
 //
-//        3xTF32:   A.B  ~=  A_hi.B_hi + A_lo.B_hi + A_hi.B_lo,     x_hi = rna_tf32(x), x_lo = rna_tf32(x - x_hi)
+//        3xTF32:   A.B  ~=  A_hi.B_hi + A_lo.B_hi + A_hi.B_lo,     x_hi = x truncated to tf32, x_lo = x - x_hi
 //
-// on tcgen05.mma (kind::tf32, M = 128 sites, N = 24 >= 20, K = 24 >= 20 in three K = 8 steps), fp32 accumulation in
-// TMEM.  Each operand keeps 22 significant bits, the dropped lo.lo term is 2^-22 relative: fp32-class accuracy, but
-// NOT the reference's rounding sequence -- bit-exactness is impossible on tensor cores, so this kernel exists for
-// PLF_MATH_FMA only (<= 1e-5 relative, the tests state it); PLF_MATH_STRICT keeps the FMUL2/FADD kernel.
+// on tcgen05.mma (kind::tf32, M = 128 sites, fp32 accumulation in TMEM), each product as ONE accumulation chain of
+// five MMAs (see kN below).  Each operand keeps 22 significant bits, the dropped lo.lo term is 2^-22 relative:
+// fp32-class accuracy (worst observed 2e-6), but NOT the reference's rounding sequence -- bit-exactness is impossible
+// on tensor cores, so this kernel exists for PLF_MATH_FMA only (<= 1e-5 relative, the tests state it);
+// PLF_MATH_STRICT keeps the FMUL2/FADD kernel.
 //
-// Shape (one CTA per SM, 320 threads):
+// Shape (one CTA per SM, 384 threads):
 //   warps 0-3 / 4-7   two WORKER GROUPS of 128 threads; thread t of a group owns site row t of the group's current
-//                     128-site tile = TMEM lane t.  A group is a self-contained sequential pipeline (convert -> MMA ->
-//                     product -> MMA -> read back); the two groups work on alternating tiles, so one group's CUDA-core
-//                     phases overlap the other's tensor-core phases.
+//                     128-site tile = TMEM lane t.  A group is a software-pipelined sequence over (tile, category)
+//                     steps (convert -> MMA -> product -> MMA -> read back); the two groups work on alternating tiles,
+//                     so one group's CUDA-core phases overlap the other's tensor-core phases.
 //   warps 8 / 9       one PRODUCER lane per group: TMA tensor copies (cp.async.bulk.tensor.2d, SASS UTMALDG) of
 //                     {20 floats x 128 sites} boxes -- one (category, child) operand, 10 KB, row pitch 80 B, which makes
-//                     the row-per-lane LDS.128 reads conflict-free -- into a 6-box ring per group (120 KB in flight per
-//                     SM).  Rows past the end of the site range are zero-filled by the TMA unit.
-//   A operands        never touch shared memory again: a worker splits its row into hi/lo in registers and writes both
-//                     to TMEM (tcgen05.st); the MMAs take A from TMEM and B (the constant matrices, pre-split, K-major
-//                     no-swizzle canonical layout, 54 KB) from shared memory.
-//   per category      a = x1.P_l^T, b = x2.P_r^T (18 MMAs) -> tcgen05.ld -> p = a*b in registers, split, tcgen05.st ->
-//                     x3 = p.EV (9 MMAs) -> tcgen05.ld into registers; after the fourth category the thread holds its
-//                     site's 80 results: threshold test, x 2^32, 256-bit stores, scaler byte, scaler count.
-// TMEM: 512 columns = 2 groups x (3 accumulators x 32 + 6 A-operand regions x 24).
+//                     the row-per-lane LDS.128 reads conflict-free -- into a 4-box ring per group.  Rows past the end
+//                     of the site range are zero-filled by the TMA unit.
+//   warps 10 / 11     one MMA-ISSUER lane per group: waits for the workers' "operand is in TMEM" mbarriers, issues the
+//                     five MMAs of a product, commits to the mbarrier the workers wait on.
+//   A operands        never touch shared memory again: a worker splits its row into hi/lo in registers and writes
+//                     [hi(20) | lo(20)] to TMEM (tcgen05.st); the MMAs take A from TMEM and B (the nine constant
+//                     matrices, pre-split, 40 x 40 blocks in the K-major no-swizzle canonical layout, 56 KB) from
+//                     shared memory.
+//   per category      a = x1.P_l^T, b = x2.P_r^T (10 MMAs) -> tcgen05.ld -> p = a*b in registers, split, tcgen05.st ->
+//                     x3 = p.EV (5 MMAs) -> tcgen05.ld into registers; after the fourth category the thread holds its
+//                     site's 80 results: threshold test, x 2^32, staging boxes, TMA tensor stores (SASS UTMASTG),
+//                     scaler byte, scaler count.
+// TMEM: 512 columns = 2 groups x (3 accumulators x 40 + 3 A-operand regions x 40) (+ 16 unused per group).
+// How it got here (3.3 -> 6.3 G sites/s) and what bounds it now: profiles/r02_protein_tc.md.
 #include "../../include/b200plf.h"
 #include "plf_kernels.cuh"
 #include "plf_registry.h"
@@ -46,7 +52,10 @@ constexpr int kS = 20;                       // states
 constexpr int kSite = 80;                    // floats per site
 constexpr int kTile = 128;                   // sites per tile = MMA M = TMEM lanes
 constexpr int kBoxBytes = kS * kTile * 4;    // one (category, child) box: 10 240 B
-constexpr int kRing = 4;                     // boxes per group ring (2 steps ahead)
+#ifndef PLF_TC_RING
+#define PLF_TC_RING 4
+#endif
+constexpr int kRing = PLF_TC_RING;           // boxes per group ring (4 = 2 steps ahead)
 // One 3xTF32 product as ONE accumulation chain of five MMAs: the A operand of a row is [hi(20) | lo(20)] (K = 40, five
 // K = 8 steps, no padding), the B operand is the 40 x 40 block matrix
 //            n < 20        n >= 20
@@ -59,6 +68,7 @@ constexpr int kN = 40;                       // MMA N.  M = 128 with N % 8 == 0 
 constexpr int kK = 40;                       // K (five K = 8 steps)
 constexpr int kBMat = (kK / 4) * kN * 16;    // one B matrix in canonical K-major layout: 10 chunks x 40 rows x 16 B = 6400 B
 constexpr int kNumB = 9;                     // P_left[4], P_right[4], EV
+constexpr int kTraceCols = 12;               // PLF_TC_TRACE: counters per worker warp
 constexpr int kThreads = 384;               // 8 worker warps, 2 producer warps, 2 MMA-issuer warps
 
 // shared memory carve-up
@@ -325,15 +335,31 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
         const uint32_t trow = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)g * 256u;    // this warp's lane quarter, this group's columns
 
         uint32_t slot = 0, phase = 0, ph_ab = 0, ph_x = 0;
-        // PLF_TC_TRACE (debug): clock64 stamps of one thread (block 0, group 0, row 0) at the hand-off points of every step
-        const bool tracing = TRACE && trace && blockIdx.x == 0 && threadIdx.x == 0;
-        long long *tp = trace;
-        auto stamp = [&](int id) {
+        // PLF_TC_TRACE (debug build of the kernel): every worker thread adds up the cycles it spends in each kind of wait;
+        // lane 0 of every worker warp writes its eight counters at the end (tools/tc_trace.py).  Unlike per-event stamps
+        // this costs two clock reads per wait and perturbs nothing else.
+        uint32_t wacc[kTraceCols] = {};
+        const uint32_t t_begin = TRACE ? (uint32_t)clock() : 0u;
+        auto wait_on = [&](int kind, uint64_t *bar, uint32_t parity) {
             if constexpr (TRACE) {
-                if (tracing && tp < trace + 16 * 4096) {
-                    *tp++ = (long long)id;
-                    *tp++ = clock64();
-                }
+                const uint32_t t0 = (uint32_t)clock();
+                mbar_wait(bar, parity);
+                wacc[kind] += (uint32_t)clock() - t0;
+            } else {
+                mbar_wait(bar, parity);
+            }
+        };
+        auto seg_begin = [&]() -> uint32_t { return TRACE ? (uint32_t)clock() : 0u; };
+        auto seg_end = [&](int kind, uint32_t t0) {
+            if constexpr (TRACE) wacc[kind] += (uint32_t)clock() - t0;
+        };
+        auto sync_on = [&](int kind) {
+            if constexpr (TRACE) {
+                const uint32_t t0 = (uint32_t)clock();
+                group_sync(g);
+                wacc[kind] += (uint32_t)clock() - t0;
+            } else {
+                group_sync(g);
             }
         };
 
@@ -342,9 +368,7 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
         auto convert = [&]() {
 #pragma unroll
             for (int child = 0; child < 2; ++child) {
-                stamp(child ? 3 : 1);
-                mbar_wait(&full[g * kRing + slot], phase);
-                stamp(child ? 4 : 2);
+                wait_on(child, &full[g * kRing + slot], phase);
                 const float4 *row = reinterpret_cast<const float4 *>(gring + (size_t)slot * kBoxBytes + (size_t)t * (kS * 4));
                 float4 v[5];
 #pragma unroll
@@ -380,14 +404,11 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(child ? &rdy_b[g] : &rdy_a[g]);
-                stamp(child ? 6 : 5);
             }
         };
         // finish_ab: p = a * b in registers, split, back to TMEM as the A operand of the 9 EV MMAs
         auto finish_ab = [&]() {
-            stamp(7);
-            mbar_wait(&mma_ab[g], ph_ab);
-            stamp(8);
+            wait_on(2, &mma_ab[g], ph_ab);
             ph_ab ^= 1u;
             tc_fence_after();
             float a[kS], a2[kS], b[kS], b2[kS];               // the two column blocks of each accumulator
@@ -396,7 +417,6 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
             tmem_ld20(trow + kColAccB, b);
             tmem_ld20(trow + kColAccB + kS, b2);
             tc_wait_ld();
-            stamp(9);
             uint32_t hi[kS], lo[kS];
 #pragma unroll
             for (int k = 0; k < kS; ++k) split_trunc((a[k] + a2[k]) * (b[k] + b2[k]), hi[k], lo[k]);
@@ -406,7 +426,6 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&rdy_p[g]);
-            stamp(10);
         };
 
         // Software pipeline over the (tile, category) steps of this group: the EV product of step s runs on the tensor
@@ -415,12 +434,12 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
         const size_t first = (size_t)blockIdx.x * 2 + g, stride = (size_t)gridDim.x * 2;
         if (first < n_tiles) convert();
         // Results.  A site's 320 bytes are contiguous in x3, but the lanes of a warp are 320 B apart: direct 256-bit stores
-        // are 32 sector requests per instruction, 1280 per tile and group, and cost ~1900 of the ~6800 cycles per tile
-        // (clock64 trace, profiles/r02_protein_tc.md).  Instead every thread writes its row, category by category as the
+        // are 32 sector requests per instruction, 1280 per tile and group, and were a quarter of the time of the version that
+        // used them (profiles/r02_protein_tc.md).  Instead every thread writes its row, category by category as the
         // results come out of TMEM (in the shadow of the next step's MMAs), into four {20 floats x 128 sites} staging
         // boxes -- the layout of the input boxes, row pitch 80 B, conflict-free -- and lane 0 of each of the four warps
         // hands one box to the TMA unit (tensor stores, SASS UTMASTG): asynchronous, whole rows, rows past the end of the
-        // site range clipped by the unit.  The rare site that needs the x 2^32 rescale rewrites its own row first.
+        // site range clipped by the unit.  A site that needs the x 2^32 rescale rewrites its rows from its registers.
         unsigned char *stage = smem + kOffOut + (size_t)g * 4 * kBoxBytes;
         const int wq = warp & 3;
         for (size_t tile = first; tile < n_tiles; tile += stride) {
@@ -428,52 +447,58 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
             // independent chains (a NaN or Inf has larger magnitude bits than any finite value, so "all 80 below 2^-32"
             // keeps the reference's meaning)
             uint32_t mx[4] = {0u, 0u, 0u, 0u};
+            float out[4][kS];
+            auto put_row = [&](int c, float f) {               // this thread's row of category c, times f, into staging box c
+                float4 *dst = reinterpret_cast<float4 *>(stage + (size_t)c * kBoxBytes + (size_t)t * (kS * 4));
+#pragma unroll
+                for (int q = 0; q < 5; ++q)
+                    dst[q] = make_float4(__fmul_rn(out[c][4 * q], f), __fmul_rn(out[c][4 * q + 1], f), __fmul_rn(out[c][4 * q + 2], f),
+                                         __fmul_rn(out[c][4 * q + 3], f));
+            };
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
+                uint32_t ts = seg_begin();
                 finish_ab();
+                seg_end(9, ts);
+                ts = seg_begin();
                 if (c < 3 || tile + stride < n_tiles) convert();
-                stamp(11);
-                mbar_wait(&mma_x[g], ph_x);
-                stamp(12);
+                seg_end(8, ts);
+                ts = seg_begin();
+                wait_on(3, &mma_x[g], ph_x);
                 ph_x ^= 1u;
                 tc_fence_after();
-                float o[kS], o2[kS];
-                tmem_ld20(trow + kColAccX, o);
+                float o2[kS];
+                tmem_ld20(trow + kColAccX, out[c]);
                 tmem_ld20(trow + kColAccX + kS, o2);
                 tc_wait_ld();
 #pragma unroll
-                for (int l = 0; l < kS; ++l) o[l] += o2[l];
-#pragma unroll
-                for (int l = 0; l < kS; ++l) mx[l & 3] = max(mx[l & 3], __float_as_uint(o[l]) & 0x7FFFFFFFu);
-                stamp(13);
-                if (c == 0) {
-                    if (lane == 0) bulk_wait_read_all();       // the previous tile's tensor stores have read the staging boxes
-                    group_sync(g);
-                    stamp(17);
+                for (int l = 0; l < kS; ++l) {
+                    out[c][l] += o2[l];
+                    mx[l & 3] = max(mx[l & 3], __float_as_uint(out[c][l]) & 0x7FFFFFFFu);
                 }
-                float4 *dst = reinterpret_cast<float4 *>(stage + (size_t)c * kBoxBytes + (size_t)t * (kS * 4));
-#pragma unroll
-                for (int q = 0; q < 5; ++q) dst[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
-                stamp(18);
+                // staging runs one category behind: the previous tile's tensor stores have had a whole step more to read
+                // the boxes before this tile's first write
+                if (c == 1) {
+                    const uint32_t tr = seg_begin();
+                    if (lane == 0) bulk_wait_read_all();
+                    if constexpr (TRACE) __syncwarp();
+                    seg_end(4, tr);
+                    sync_on(4);
+                }
+                if (c >= 1) put_row(c - 1, 1.0f);
+                seg_end(10, ts);
             }
+            const uint32_t te = seg_begin();
             const size_t site = tile * kTile + (size_t)t;
             const bool small = max(max(mx[0], mx[1]), max(mx[2], mx[3])) < 0x2F800000u;      // bits of 2^-32
-            if (small) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    float4 *row = reinterpret_cast<float4 *>(stage + (size_t)c * kBoxBytes + (size_t)t * (kS * 4));
-#pragma unroll
-                    for (int q = 0; q < 5; ++q) {
-                        float4 v = row[q];
-                        row[q] = make_float4(__fmul_rn(v.x, kTwoToThe32), __fmul_rn(v.y, kTwoToThe32), __fmul_rn(v.z, kTwoToThe32),
-                                             __fmul_rn(v.w, kTwoToThe32));
-                    }
-                }
+            put_row(3, small ? kTwoToThe32 : 1.0f);
+            if (small) {                                       // the rows already staged, again, from the registers
+                put_row(0, kTwoToThe32);
+                put_row(1, kTwoToThe32);
+                put_row(2, kTwoToThe32);
             }
-            stamp(15);
             fence_proxy_async_smem();                          // generic-proxy writes -> visible to the TMA unit
-            group_sync(g);
-            stamp(20);
+            sync_on(5);
             if (lane == 0) {
                 tma_store_box(&map3, wq * kS, (int)(tile * kTile), stage + (size_t)wq * kBoxBytes);
                 bulk_commit();
@@ -483,9 +508,16 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
                 if (cnt3) cnt3[site] = (cnt1 ? __ldg(cnt1 + site) : 0) + (cnt2 ? __ldg(cnt2 + site) : 0) + (small ? 1 : 0);
                 if (small) my_sum += wgt ? (unsigned long long)(long long)wgt[site] : 1ull;
             }
-            stamp(14);
+            seg_end(11, te);
         }
         if (lane == 0) bulk_wait_all();                        // every tensor store this lane has issued has completed
+        if constexpr (TRACE) {
+            if (trace && lane == 0) {
+                wacc[6] = (uint32_t)clock() - t_begin;
+                wacc[7] = (uint32_t)((n_tiles > first ? (n_tiles - first + stride - 1) / stride : 0));
+                for (int k = 0; k < kTraceCols; ++k) trace[((size_t)blockIdx.x * 8 + warp) * kTraceCols + k] = (long long)wacc[k];
+            }
+        }
     }
     if (scaler_sum) block_add_u64<kThreads>(my_sum, scaler_sum);
     tc_fence_before();
@@ -547,10 +579,10 @@ int launch_newview_aa_tc(const float *x1, const float *x2, float *x3, unsigned c
     size_t grid = (tiles + 1) / 2;
     if (grid > (size_t)sms) grid = sms;
     if (flags & kAaSingleCta) grid = 1;
-    // PLF_TC_TRACE=<file> (debug): clock64 stamps of one worker thread at the hand-off points of its steps, dumped as text
-    // (every stamp costs the traced warp ~140 cycles: read the SHARES after subtracting that, tools/tc_trace.py)
+    // PLF_TC_TRACE=<file> (debug): per worker warp, the cycles spent in each kind of wait, dumped as text:
+    //   block warp  x1_box x2_box mma_ab mma_x staging_free staged total tiles | segments: convert finish_ab results tile_end
     long long *d_trace = nullptr;
-    constexpr size_t kTraceWords = 16 * 4096;
+    const size_t kTraceWords = grid * 8 * tc::kTraceCols;
     if (trace_path) {
         if (cudaMalloc(&d_trace, kTraceWords * sizeof(long long)) != cudaSuccess) return PLF_ERR_NOMEM;
         cudaMemsetAsync(d_trace, 0, kTraceWords * sizeof(long long), stream);
@@ -565,7 +597,11 @@ int launch_newview_aa_tc(const float *x1, const float *x2, float *x3, unsigned c
         cudaMemcpy(h.data(), d_trace, kTraceWords * sizeof(long long), cudaMemcpyDeviceToHost);
         cudaFree(d_trace);
         if (FILE *f = fopen(trace_path, "w")) {
-            for (size_t i = 0; i + 1 < kTraceWords && h[i] != 0; i += 2) fprintf(f, "%lld %lld\n", h[i], h[i + 1]);
+            for (size_t w = 0; w < grid * 8; ++w) {
+                fprintf(f, "%zu %zu", w / 8, w % 8);
+                for (int k = 0; k < tc::kTraceCols; ++k) fprintf(f, " %lld", h[w * tc::kTraceCols + k]);
+                fprintf(f, "\n");
+            }
             fclose(f);
         }
     }

@@ -1,12 +1,36 @@
-import sys,collections
-ev=[tuple(map(int,l.split())) for l in open(sys.argv[1]) if l.strip()]
-names={1:"x1 wait start",2:"x1 data ready",3:"x2 wait start",4:"x2 data ready",5:"arrive a",6:"arrive b",7:"ab wait start",8:"ab ready",9:"a,b loaded",10:"arrive p",11:"x wait start",12:"x ready",13:"out loaded",14:"output stored",15:"threshold done",16:"stores read",17:"group sync 1",18:"staged",19:"fenced",20:"group sync 2"}
-# durations between consecutive stamps, aggregated by (prev,cur)
-agg=collections.defaultdict(list)
-for (i0,t0),(i1,t1) in zip(ev,ev[1:]):
-    agg[(i0,i1)].append(t1-t0)
-tot=ev[-1][1]-ev[0][1]
-print("stamps",len(ev),"total clk",tot)
-for k,v in sorted(agg.items(), key=lambda kv:-sum(kv[1])):
-    v2=v[len(v)//10:]  # skip warm-up
-    print(f"{names[k[0]]:16s} -> {names[k[1]]:16s} n={len(v):5d} mean={sum(v2)/len(v2):8.1f} share={100*sum(v)/tot:5.1f}%")
+"""Read a PLF_TC_TRACE dump of the tcgen05 20-state kernel (debug build selected by the environment variable): per worker
+warp, the cycles spent in each kind of wait and in each segment of a step over the whole launch.
+
+    PLF_TC_TRACE=trace.txt python tools/tc_check.py time ; python tools/tc_trace.py trace.txt
+
+Prints, per (tile, category) step and averaged over all worker warps of all CTAs, where a worker's time goes.
+"""
+import sys
+
+import numpy as np
+
+WAITS = ["x1 box (TMA)", "x2 box (TMA)", "branch MMAs (mma_ab)", "EV MMAs (mma_x)", "staging free (+ sync)", "staged sync"]
+# segment -> the waits that happen inside it
+SEGMENTS = [("convert x1, x2 of the next step", 8, (0, 1)), ("finish_ab: p = a*b", 9, (2,)), ("results of this category", 10, (3, 4)),
+            ("tile end (rescale, stores)", 11, (5,))]
+
+
+def main():
+    rows = np.loadtxt(sys.argv[1], dtype=np.int64)
+    rows = rows[rows[:, 9] > 0]
+    steps = rows[:, 9] * 4
+    total = rows[:, 8] / steps
+    print(f"{len(rows)} worker warps, {int(rows[:, 9].sum()) // 4} tiles; cycles per step: mean {total.mean():.0f}, "
+          f"min {total.min():.0f}, max {total.max():.0f}")
+    for k, name in enumerate(WAITS):
+        per = rows[:, 2 + k] / steps
+        print(f"  wait for {name:22s} {per.mean():7.0f}  ({100 * per.mean() / total.mean():4.1f} %)   min {per.min():6.0f} max {per.max():6.0f}")
+    if rows.shape[1] >= 14:
+        for name, col, waits in SEGMENTS:
+            seg = rows[:, 2 + col] / steps
+            inside = sum(rows[:, 2 + w] / steps for w in waits)
+            print(f"  segment {name:32s} {seg.mean():7.0f}  of which waiting {inside.mean():6.0f}, busy {seg.mean() - inside.mean():6.0f}")
+
+
+if __name__ == "__main__":
+    main()
