@@ -448,6 +448,13 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
             // keeps the reference's meaning)
             uint32_t mx[4] = {0u, 0u, 0u, 0u};
             float out[4][kS];
+            // the children's scaler counts and the site weight are needed at the end of the tile: ask for them now
+            const size_t site = tile * kTile + (size_t)t;
+            int cnt_in = 0, weight = 1;
+            if (site < n) {
+                if (cnt3) cnt_in = (cnt1 ? __ldg(cnt1 + site) : 0) + (cnt2 ? __ldg(cnt2 + site) : 0);
+                if (wgt) weight = __ldg(wgt + site);
+            }
             auto put_row = [&](int c, float f) {               // this thread's row of category c, times f, into staging box c
                 float4 *dst = reinterpret_cast<float4 *>(stage + (size_t)c * kBoxBytes + (size_t)t * (kS * 4));
 #pragma unroll
@@ -489,7 +496,6 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
                 seg_end(10, ts);
             }
             const uint32_t te = seg_begin();
-            const size_t site = tile * kTile + (size_t)t;
             const bool small = max(max(mx[0], mx[1]), max(mx[2], mx[3])) < 0x2F800000u;      // bits of 2^-32
             put_row(3, small ? kTwoToThe32 : 1.0f);
             if (small) {                                       // the rows already staged, again, from the registers
@@ -505,8 +511,8 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
             }
             if (site < n) {
                 if (scaler) scaler[site] = small ? 1 : 0;
-                if (cnt3) cnt3[site] = (cnt1 ? __ldg(cnt1 + site) : 0) + (cnt2 ? __ldg(cnt2 + site) : 0) + (small ? 1 : 0);
-                if (small) my_sum += wgt ? (unsigned long long)(long long)wgt[site] : 1ull;
+                if (cnt3) cnt3[site] = cnt_in + (small ? 1 : 0);
+                if (small) my_sum += (unsigned long long)(long long)weight;
             }
             seg_end(11, te);
         }
