@@ -1147,15 +1147,28 @@ int plf_newview_stream(plf_ctx *ctx, const float *ev, const float *p_left, const
         cudaError_t e__ = (expr);                                                                                    \
         if (e__ != cudaSuccess) return drain(fail(ctx, PLF_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__))); \
     } while (0)
+    // PLF_STREAM_TRACE=<file> (debug; there is no nsys in this image): four events per chunk on its stream -- before the
+    // H2D copies, after them, after the kernel, after the D2H copies -- written after the call as one line per chunk in
+    // ms since the first event.  tools/stream_timeline.py turns that into the three-way overlap of the pipeline.
+    const char *trace_path = getenv("PLF_STREAM_TRACE");
+    std::vector<cudaEvent_t> tev;
+    auto mark = [&](cudaStream_t st) {
+        if (!trace_path) return;
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreate(&e) == cudaSuccess) cudaEventRecord(e, st);
+        tev.push_back(e);
+    };
     size_t k = 0;
     for (size_t lo = 0; lo < n_sites; lo += chunk_sites, ++k) {
         const int b = (int)(k % K);
         cudaStream_t st = ctx->s_stream[b];
         const size_t cnt = n_sites - lo < chunk_sites ? n_sites - lo : chunk_sites;
         const size_t bytes = cnt * sf * sizeof(float);
+        mark(st);
         PLF_CUDA_DRAIN(cudaMemcpyAsync(ctx->sd_x1[b], x1 + lo * sf, bytes, cudaMemcpyHostToDevice, st));
         PLF_CUDA_DRAIN(cudaMemcpyAsync(ctx->sd_x2[b], x2 + lo * sf, bytes, cudaMemcpyHostToDevice, st));
         if (wgt) PLF_CUDA_DRAIN(cudaMemcpyAsync(ctx->sd_wgt[b], wgt + lo, cnt * sizeof(int), cudaMemcpyHostToDevice, st));
+        mark(st);
         int rc = ctx->states == 4
                      ? launch_newview(ctx, ctx->sd_x1[b], ctx->sd_x2[b], ctx->sd_x3[b], ctx->sd_sc[b], ctx->sd_mats,
                                       ctx->sd_mats + evf, ctx->sd_mats + evf + pf, wgt ? ctx->sd_wgt[b] : nullptr, cnt,
@@ -1164,11 +1177,29 @@ int plf_newview_stream(plf_ctx *ctx, const float *ev, const float *p_left, const
                                      ctx->sd_mats + evf, ctx->sd_mats + evf + pf, wgt ? ctx->sd_wgt[b] : nullptr, cnt,
                                      ctx->sd_sum, &opts, st);
         if (rc != PLF_OK) return drain(rc);
+        mark(st);
         PLF_CUDA_DRAIN(cudaMemcpyAsync(x3 + lo * sf, ctx->sd_x3[b], bytes, cudaMemcpyDeviceToHost, st));
         if (scaler) PLF_CUDA_DRAIN(cudaMemcpyAsync(scaler + lo, ctx->sd_sc[b], cnt, cudaMemcpyDeviceToHost, st));
+        mark(st);
     }
 #undef PLF_CUDA_DRAIN
     for (int b = 0; b < K; ++b) PLF_CUDA(ctx, cudaStreamSynchronize(ctx->s_stream[b]));
+    if (trace_path && !tev.empty()) {
+        if (FILE *f = fopen(trace_path, "w")) {
+            fprintf(f, "# chunk slot sites  h2d_begin h2d_end kernel_end d2h_end   (ms since the first event; chunk = %zu sites, %zu B/site in, %zu B/site out)\n",
+                    chunk_sites, 2 * sf * sizeof(float), sf * sizeof(float) + 1);
+            for (size_t c = 0; c * 4 + 3 < tev.size(); ++c) {
+                float t[4] = {0, 0, 0, 0};
+                for (int j = 0; j < 4; ++j)
+                    if (tev[0] && tev[c * 4 + j]) cudaEventElapsedTime(&t[j], tev[0], tev[c * 4 + j]);
+                const size_t lo = c * chunk_sites;
+                fprintf(f, "%zu %zu %zu  %.4f %.4f %.4f %.4f\n", c, c % K, n_sites - lo < chunk_sites ? n_sites - lo : chunk_sites, t[0], t[1], t[2], t[3]);
+            }
+            fclose(f);
+        }
+        for (cudaEvent_t e : tev)
+            if (e) cudaEventDestroy(e);
+    }
     PLF_CUDA(ctx, cudaMemcpy(ctx->sh_sum, ctx->sd_sum, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     if (increment) *increment = (long long)*ctx->sh_sum;
     return PLF_OK;
