@@ -11,7 +11,8 @@
 // five MMAs (see kN below).  Each operand keeps 22 significant bits, the dropped lo.lo term is 2^-22 relative:
 // fp32-class accuracy (worst observed 2e-6), but NOT the reference's rounding sequence -- bit-exactness is impossible
 // on tensor cores, so this kernel exists for PLF_MATH_FMA only (<= 1e-5 relative, the tests state it);
-// PLF_MATH_STRICT keeps the FMUL2/FADD kernel.
+// PLF_MATH_STRICT keeps the FMUL2/FADD kernel.  The tensor core reads fp32 denormal operands as zero (measured,
+// tools/tc_denormal_probe.py); such an entry is >= 2^94 below its own site's rescaling threshold.
 //
 // Shape (one CTA per SM, 384 threads):
 //   warps 0-3 / 4-7   two WORKER GROUPS of 128 threads; thread t of a group owns site row t of the group's current

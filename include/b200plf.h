@@ -322,7 +322,8 @@ int plf_tree_evaluate_root(plf_tree *tree, const float *diag, double *lnl);
  * kernel of plf_newview_device.  For S = 20, opts->variant is the number of sites per lane of the register tile
  * (1, 2 or 4; threads_per_block 512 / 256,384 / 128,256), or 9 = the TENSOR-CORE kernel (tcgen05.mma kind::tf32 with the
  * 3xTF32 split, fp32 accumulators in tensor memory, operands by TMA; PLF_MATH_FMA only -- tensor cores cannot reproduce
- * the reference's rounding sequence, so PLF_MATH_STRICT never uses them); 0 = the fastest measured kernel for the math
+ * the reference's rounding sequence, so PLF_MATH_STRICT never uses them; <= 1e-5 relative, measured 2e-6; fp32 DENORMAL
+ * operands read as zero there, the CUDA-core kernels keep them); 0 = the fastest measured kernel for the math
  * mode: the register-tile kernel in strict mode, the tensor-core kernel in FMA mode for calls of >= 16384 sites.      */
 int plf_newview_states_device(int states, const float *x1, const float *x2, float *x3,
                               unsigned char *scaler, const float *ev, const float *p_left,

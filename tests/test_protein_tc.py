@@ -107,3 +107,51 @@ def test_tc_tree_with_scaler_counts(pkg, coracle):
     assert same.mean() > 0.999
     rel = np.abs(root[same].astype(np.float64) - o_root[same]) / np.maximum(np.abs(o_root[same]), 1e-300)
     assert rel.max() <= 8 * REL_TOL          # error compounds over the depth of the tree
+
+
+@pytest.mark.gpu
+def test_tc_non_finite_inputs_stay_in_their_site_and_category(pkg, coracle):
+    """NaN / Inf entries in one (site, category) of a child: the tensor-core kernel's results are non-finite exactly where
+    the reference's are (that site's category), every other value stays within tolerance, and such a site is never
+    rescaled (a NaN or Inf is not below the threshold).  Rows are TMEM lanes and the operand has no K padding, so nothing
+    can leak between sites; this pins it."""
+    import torch
+    n = 1000
+    ev, left, right = matrices(7)
+    x1, x2 = pkg.generate_states_host(S, 0, n, 5)
+    x1 = x1.reshape(n, SITE).copy()
+    x2 = x2.reshape(n, SITE).copy()
+    x1[3, 1 * S + 4] = np.nan            # site 3, category 1
+    x2[130, 2 * S + 19] = np.inf         # site 130 (second tile), category 2
+    x1[255, 0] = -np.inf                 # last row of the second tile, category 0
+    x1[4] *= 1e-20                       # a small site next to a poisoned one keeps its rescale
+    o3, osc, _ = coracle.newview_states(S, x1, x2, ev, left, right)
+    g3, gsc, _ = run_states(pkg, torch, S, ev, left, right, x1, x2, math=pkg.MATH_FMA, shape=TC)
+    bad_o, bad_g = ~np.isfinite(o3), ~np.isfinite(g3)
+    assert np.array_equal(bad_o, bad_g), "non-finite results differ in position from the reference's"
+    assert bad_o.sum() == 3 * S and bad_o[3, S:2 * S].all() and bad_o[130, 2 * S:3 * S].all() and bad_o[255, :S].all()
+    ok = ~bad_o
+    rel = np.abs(g3[ok].astype(np.float64) - o3[ok]) / np.maximum(np.abs(o3[ok].astype(np.float64)), 1e-300)
+    assert rel.max() <= REL_TOL
+    assert np.array_equal(gsc, osc) and gsc[3] == 0 and gsc[130] == 0 and gsc[255] == 0 and gsc[4] == 1
+
+
+@pytest.mark.gpu
+def test_tc_denormal_operands_are_flushed_not_garbled(pkg, coracle):
+    """The tensor core reads fp32 denormals as zero (tools/tc_denormal_probe.py: the CUDA-core FMA kernel keeps them).  A
+    CLV entry that small is >= 2^94 below the rescaling threshold of its own site, so the likelihood cannot see it; what
+    this pins is that such a value becomes exactly zero -- never garbage -- and that the scaler bytes do not move."""
+    import torch
+    n = 4096
+    ev, left, right = matrices(7)
+    x1, x2 = pkg.generate_states_host(S, 0, n, 5)
+    x1 = x1.reshape(n, SITE) * np.float32(1e-30)          # 1e-30 ... 1e-42: the designed-small sites drop below FLT_MIN
+    x2 = x2.reshape(n, SITE)
+    o3, osc, _ = coracle.newview_states(S, x1, x2, ev, left, right)
+    g3, gsc, _ = run_states(pkg, torch, S, ev, left, right, x1, x2, math=pkg.MATH_FMA, shape=TC)
+    rel = np.abs(g3.astype(np.float64) - o3) / np.maximum(np.abs(o3.astype(np.float64)), 1e-300)
+    flushed = g3 == 0
+    assert ((rel <= REL_TOL) | flushed).all()
+    assert flushed.any() and (np.abs(x1[flushed.any(axis=1)]).max(axis=1) < np.finfo(np.float32).tiny).all(), \
+        "only sites whose x1 is entirely denormal may come out as zero"
+    assert np.array_equal(gsc, osc)
