@@ -2,7 +2,8 @@
 
 The write-after-read hazard of a shared-memory ring: a slot handed back to the bulk-copy engine while a warp is still
 reading it.  It shows when refills are FAST (inputs resident in L2) and one block does all the work, so these tests run
-the DNA ring kernel (plf_newview_tma_dyn, the default) and the 20-state kernel (plf_newview_aa) on ONE block
+the DNA ring kernel (plf_newview_tma_dyn, the default), the 20-state kernel (plf_newview_aa) and the tensor-core
+20-state kernel (plf_newview_aa_tc) on ONE block
 (PLF_LAUNCH_SINGLE_CTA), with freshly poisoned device memory every iteration, in BOTH release modes (fence.proxy.async
 and data dependency), and compare every bit with the oracle.  The tree kernel's twin lives in tests/test_tree.py."""
 from __future__ import annotations
@@ -72,6 +73,40 @@ def test_protein_single_block_poisoned_memory_both_release_modes(pkg, coracle, s
             torch.cuda.synchronize()
             got = g3.cpu().numpy().reshape(o3.shape)
             assert np.array_equal(bits(got), bits(o3)), (it, mode, first_mismatch(got, o3))
+            assert np.array_equal(gsc.cpu().numpy(), osc) and int(gsum.item()) == 2 * oinc
+
+
+@pytest.mark.gpu
+def test_tensor_core_kernel_single_block_poisoned_memory_both_release_modes(pkg, coracle):
+    """The tcgen05 20-state kernel's operand ring (4 boxes per group, refilled by TMA tensor copies) and its staging boxes
+    (read by TMA tensor stores): one block, L2-resident inputs, both release modes, poisoned memory; results within the
+    mode's tolerance, identical between the two release modes and from launch to launch."""
+    import torch
+    n = 20011                                                       # 157 ragged tiles of 128 sites, 19 MB: L2-resident
+    rng = np.random.RandomState(21)
+    ev, left, right = (rng.random_sample(k).astype(np.float32) for k in (400, 1600, 1600))
+    x1, x2 = pkg.generate_states_host(20, 0, n, 13)
+    o3, osc, oinc = coracle.newview_states(20, x1, x2, ev, left, right)
+    stream = torch.cuda.current_stream().cuda_stream
+    first = None
+    for it in range(10):
+        _poison(torch)
+        d1, d2 = torch.from_numpy(x1).cuda(), torch.from_numpy(x2).cuda()
+        for mode in (pkg.LAUNCH_FENCED_RELEASE, pkg.LAUNCH_DEP_RELEASE):
+            g3 = torch.full((n * 80,), float("nan"), device="cuda")
+            gsc = torch.full((n,), 7, dtype=torch.uint8, device="cuda")
+            gsum = torch.zeros(1, dtype=torch.int64, device="cuda")
+            opts = pkg.make_opts(pkg.MATH_FMA, 9, 0, 0, 0, mode | pkg.LAUNCH_SINGLE_CTA)
+            for _ in range(2):
+                pkg.newview_states_device(20, d1.data_ptr(), d2.data_ptr(), g3.data_ptr(), gsc.data_ptr(), ev, left, right,
+                                          None, n, gsum.data_ptr(), opts, stream)
+            torch.cuda.synchronize()
+            got = g3.cpu().numpy().reshape(o3.shape)
+            if first is None:
+                first = got.copy()
+                rel = np.abs(got.astype(np.float64) - o3) / np.maximum(np.abs(o3.astype(np.float64)), 1e-300)
+                assert rel.max() <= 1e-5, rel.max()
+            assert np.array_equal(bits(got), bits(first)), (it, mode, first_mismatch(got, first))
             assert np.array_equal(gsc.cpu().numpy(), osc) and int(gsum.item()) == 2 * oinc
 
 
