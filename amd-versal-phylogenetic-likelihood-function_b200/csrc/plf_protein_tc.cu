@@ -62,8 +62,8 @@ constexpr int kRing = PLF_TC_RING;           // boxes per group ring (4 = 2 step
 //            n < 20        n >= 20
 //   k < 20   B_hi[n][k]    B_lo[n - 20][k]         D[:, 0:20]  = A_hi.B_hi + A_lo.B_hi
 //   k >= 20  B_hi[n][k-20] 0                       D[:, 20:40] = A_hi.B_lo           (added on read-back)
-// Tiny MMAs cost ~59 cycles each whatever their N (27 of them per step and group was exactly the step time of the
-// nine-MMAs-per-product version); 15 per step is what moved the kernel from the tensor core's issue rate to HBM.
+// A small MMA costs its issuing thread 74 cycles whatever N <= 128 (tools/microbench_mma.cu), so the nine-MMAs-per-product
+// version spent 27 x 74 cycles per step and group on issue alone; 15 per step is what moved the kernel to the memory side.
 constexpr int kN = 40;                       // MMA N.  M = 128 with N % 8 == 0 is accepted by the hardware at cta_group::1 (CUTLASS's
                                              // static asserts want N % 16 == 0)
 constexpr int kK = 40;                       // K (five K = 8 steps)

@@ -1,0 +1,4 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+timeout 60 build/microbench_mma > gpurun_out/c36_microbench_mma.txt 2>&1; echo "rc=$?"; cat gpurun_out/c36_microbench_mma.txt
