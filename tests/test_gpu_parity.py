@@ -497,3 +497,23 @@ def test_streamed_host_path_matches_oracle(pkg, gpu, coracle, n, chunk):
         x3b = np.empty((n, 16), np.float32)
         assert ctx.newview_stream(ev, left, right, x1, x2, x3b, None, None, chunk_sites=max(256, chunk // 2)) == int(osc.sum())
         assert np.array_equal(bits(x3b), bits(o3))
+
+
+def test_stream_trace_dump_is_a_consistent_timeline(pkg, gpu, coracle, tmp_path, monkeypatch):
+    """PLF_STREAM_TRACE: one line per chunk with four non-decreasing event times, every site accounted for, and the traced
+    call returns the same bits (the events only break the programmatic launch overlap)."""
+    n, chunk = 300001, 65536
+    ev, left, right, x1, x2, wgt = signed_inputs(n, seed=11)
+    o3, osc, oinc = coracle.newview(x1, x2, ev, left, right, wgt)
+    path = tmp_path / "stream_trace.txt"
+    monkeypatch.setenv("PLF_STREAM_TRACE", str(path))
+    with pkg.Context(0, 1) as ctx:
+        x3 = np.full((n, 16), np.nan, np.float32)
+        sc = np.full(n, 7, np.uint8)
+        assert ctx.newview_stream(ev, left, right, x1, x2, x3, sc, wgt, chunk_sites=chunk) == oinc
+    assert np.array_equal(bits(x3), bits(o3)) and np.array_equal(sc, osc)
+    rows = np.loadtxt(path, comments="#", ndmin=2)
+    assert rows.shape == ((n + chunk - 1) // chunk, 7)
+    assert rows[:, 2].sum() == n and (rows[:, 1] == np.arange(len(rows)) % 3).all()
+    t = rows[:, 3:]
+    assert (np.diff(t, axis=1) >= 0).all() and t.min() >= 0 and t.max() < 10e3

@@ -155,3 +155,24 @@ def test_tc_denormal_operands_are_flushed_not_garbled(pkg, coracle):
     assert flushed.any() and (np.abs(x1[flushed.any(axis=1)]).max(axis=1) < np.finfo(np.float32).tiny).all(), \
         "only sites whose x1 is entirely denormal may come out as zero"
     assert np.array_equal(gsc, osc)
+
+
+@pytest.mark.gpu
+def test_tc_trace_twin_computes_the_same_bits(pkg, coracle, tmp_path, monkeypatch):
+    """PLF_TC_TRACE selects the compile-time twin of the kernel that counts wait cycles: same results bit for bit, one
+    line of counters per worker warp, and the counters add up (waits <= total, tiles = all tiles)."""
+    import torch
+    n = 50000
+    ev, left, right = matrices(9)
+    x1, x2 = pkg.generate_states_host(S, 0, n, 21)
+    plain = run_states(pkg, torch, S, ev, left, right, x1, x2, math=pkg.MATH_FMA, shape=TC)
+    path = tmp_path / "tc_trace.txt"
+    monkeypatch.setenv("PLF_TC_TRACE", str(path))
+    traced = run_states(pkg, torch, S, ev, left, right, x1, x2, math=pkg.MATH_FMA, shape=TC)
+    monkeypatch.delenv("PLF_TC_TRACE")
+    assert np.array_equal(plain[0].view(np.uint32), traced[0].view(np.uint32)) and np.array_equal(plain[1], traced[1]) and plain[2] == traced[2]
+    rows = np.loadtxt(path, dtype=np.int64, ndmin=2)
+    assert rows.shape[1] == 14 and rows.shape[0] % 8 == 0
+    assert rows[:, 9].sum() == 4 * ((n + 127) // 128)            # four worker warps per group count the group's tiles
+    busy = rows[rows[:, 9] > 0]
+    assert (busy[:, 2:8].sum(axis=1) <= busy[:, 8]).all() and (busy[:, 8] > 0).all()
