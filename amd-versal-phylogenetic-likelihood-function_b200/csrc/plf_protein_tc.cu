@@ -62,14 +62,14 @@ constexpr int kRing = PLF_TC_RING;           // boxes per group ring (4 = 2 step
 //            n < 20        n >= 20
 //   k < 20   B_hi[n][k]    B_lo[n - 20][k]         D[:, 0:20]  = A_hi.B_hi + A_lo.B_hi
 //   k >= 20  B_hi[n][k-20] 0                       D[:, 20:40] = A_hi.B_lo           (added on read-back)
-// A small MMA costs its issuing thread 74 cycles whatever N <= 128 (tools/microbench_mma.cu), so the nine-MMAs-per-product
-// version spent 27 x 74 cycles per step and group on issue alone; 15 per step is what moved the kernel to the memory side.
+// Tiny MMAs cost ~59 cycles each whatever their N (27 of them per step and group was exactly the step time of the
+// nine-MMAs-per-product version); 15 per step is what moved the kernel from the tensor core's issue rate to HBM.
 constexpr int kN = 40;                       // MMA N.  M = 128 with N % 8 == 0 is accepted by the hardware at cta_group::1 (CUTLASS's
                                              // static asserts want N % 16 == 0)
 constexpr int kK = 40;                       // K (five K = 8 steps)
 constexpr int kBMat = (kK / 4) * kN * 16;    // one B matrix in canonical K-major layout: 10 chunks x 40 rows x 16 B = 6400 B
 constexpr int kNumB = 9;                     // P_left[4], P_right[4], EV
-constexpr int kTraceCols = 12;               // PLF_TC_TRACE: counters per worker warp
+constexpr int kTraceCols = 13;               // PLF_TC_TRACE: counters per worker warp
 constexpr int kThreads = 384;               // 8 worker warps, 2 producer warps, 2 MMA-issuer warps
 
 // shared memory carve-up
@@ -235,6 +235,9 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
     uint64_t *rdy_b = rdy_a + 2;              // [2]  workers -> issuer: x2 operand is in TMEM
     uint64_t *rdy_p = rdy_b + 2;              // [2]  workers -> issuer: p operand is in TMEM
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(rdy_p + 2);
+    // PLF_TC_TRACE only: clock stamps exchanged between workers and issuers of this CTA (same SM, same counter)
+    volatile uint32_t *stamp_arrive_b = reinterpret_cast<volatile uint32_t *>(smem + kOffBar + 256);      // [2 groups][4 warps]
+    volatile uint32_t *stamp_commit = stamp_arrive_b + 8;                                                 // [2 groups]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const size_t n_tiles = (n + kTile - 1) / kTile;
@@ -281,6 +284,7 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
             const size_t first = (size_t)blockIdx.x * 2 + g, stride = (size_t)gridDim.x * 2;
             const size_t my_tiles = first < n_tiles ? (n_tiles - first + stride - 1) / stride : 0;
             uint32_t ph = 0;                                   // all three ready barriers complete once per step
+            uint32_t iacc[3] = {0u, 0u, 0u};
             auto product = [&](uint32_t acc, uint32_t a_op, int m) {      // acc = [A_hi | A_lo] . B[m]: one chain of five MMAs
                 const uint32_t bm = b_base + (uint32_t)m * kBMat;
 #pragma unroll
@@ -301,10 +305,34 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
                     tc_fence_after();
                     product(tcol + kColAccA, tcol + kColA1, c);
                     mbar_wait(&rdy_b[g], ph);
+                    uint32_t t_wake = 0;
+                    if constexpr (TRACE) {
+                        t_wake = (uint32_t)clock();
+                        uint32_t last = stamp_arrive_b[g * 4];
+                        for (int q = 1; q < 4; ++q) {
+                            const uint32_t v = stamp_arrive_b[g * 4 + q];
+                            if ((int32_t)(v - last) > 0) last = v;
+                        }
+                        iacc[0] += t_wake - last;              // last worker arrive -> issuer awake
+                    }
                     tc_fence_after();
                     product(tcol + kColAccB, tcol + kColA2, 4 + c);
                     mma_commit(&mma_ab[g]);
+                    if constexpr (TRACE) {
+                        const uint32_t t_done = (uint32_t)clock();
+                        iacc[1] += t_done - t_wake;            // five MMAs and the commit issued
+                        stamp_commit[g] = t_done;
+                        ++iacc[2];
+                    }
                     ph ^= 1u;
+                }
+            }
+            if constexpr (TRACE) {
+                if (trace) {
+                    long long *row = trace + ((size_t)gridDim.x * 8 + (size_t)blockIdx.x * 2 + g) * kTraceCols;
+                    row[0] = iacc[0];
+                    row[1] = iacc[1];
+                    row[2] = iacc[2];
                 }
             }
         }
@@ -340,6 +368,7 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
         // lane 0 of every worker warp writes its eight counters at the end (tools/tc_trace.py).  Unlike per-event stamps
         // this costs two clock reads per wait and perturbs nothing else.
         uint32_t wacc[kTraceCols] = {};
+        uint32_t wacc_commit = 0;                              // commit issued by the issuer -> this worker awake
         const uint32_t t_begin = TRACE ? (uint32_t)clock() : 0u;
         auto wait_on = [&](int kind, uint64_t *bar, uint32_t parity) {
             if constexpr (TRACE) {
@@ -404,12 +433,16 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
                 tc_wait_st();
                 tc_fence_before();
                 __syncwarp();
+                if constexpr (TRACE) {
+                    if (lane == 0 && child) stamp_arrive_b[g * 4 + (warp & 3)] = (uint32_t)clock();
+                }
                 if (lane == 0) mbar_arrive(child ? &rdy_b[g] : &rdy_a[g]);
             }
         };
         // finish_ab: p = a * b in registers, split, back to TMEM as the A operand of the 9 EV MMAs
         auto finish_ab = [&]() {
             wait_on(2, &mma_ab[g], ph_ab);
+            if constexpr (TRACE) wacc_commit += (uint32_t)clock() - stamp_commit[g];
             ph_ab ^= 1u;
             tc_fence_after();
             float a[kS], a2[kS], b[kS], b2[kS];               // the two column blocks of each accumulator
@@ -522,6 +555,7 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
             if (trace && lane == 0) {
                 wacc[6] = (uint32_t)clock() - t_begin;
                 wacc[7] = (uint32_t)((n_tiles > first ? (n_tiles - first + stride - 1) / stride : 0));
+                wacc[12] = wacc_commit;
                 for (int k = 0; k < kTraceCols; ++k) trace[((size_t)blockIdx.x * 8 + warp) * kTraceCols + k] = (long long)wacc[k];
             }
         }
@@ -587,9 +621,10 @@ int launch_newview_aa_tc(const float *x1, const float *x2, float *x3, unsigned c
     if (grid > (size_t)sms) grid = sms;
     if (flags & kAaSingleCta) grid = 1;
     // PLF_TC_TRACE=<file> (debug): per worker warp, the cycles spent in each kind of wait, dumped as text:
-    //   block warp  x1_box x2_box mma_ab mma_x staging_free staged total tiles | segments: convert finish_ab results tile_end
+    //   block warp  x1_box x2_box mma_ab mma_x staging_free staged total tiles | segments: convert finish_ab results tile_end |
+    //               commit_to_awake          and per issuer lane (warp 10 + group):  arrive_to_awake  issue_of_b_chain  steps
     long long *d_trace = nullptr;
-    const size_t kTraceWords = grid * 8 * tc::kTraceCols;
+    const size_t kTraceWords = grid * 10 * tc::kTraceCols;      // 8 worker warps + 2 issuer lanes per CTA
     if (trace_path) {
         if (cudaMalloc(&d_trace, kTraceWords * sizeof(long long)) != cudaSuccess) return PLF_ERR_NOMEM;
         cudaMemsetAsync(d_trace, 0, kTraceWords * sizeof(long long), stream);
@@ -604,8 +639,11 @@ int launch_newview_aa_tc(const float *x1, const float *x2, float *x3, unsigned c
         cudaMemcpy(h.data(), d_trace, kTraceWords * sizeof(long long), cudaMemcpyDeviceToHost);
         cudaFree(d_trace);
         if (FILE *f = fopen(trace_path, "w")) {
-            for (size_t w = 0; w < grid * 8; ++w) {
-                fprintf(f, "%zu %zu", w / 8, w % 8);
+            for (size_t w = 0; w < grid * 10; ++w) {        // worker rows, then the issuers' (warp 10 + group)
+                if (w < grid * 8)
+                    fprintf(f, "%zu %zu", w / 8, w % 8);
+                else
+                    fprintf(f, "%zu %zu", (w - grid * 8) / 2, 10 + (w - grid * 8) % 2);
                 for (int k = 0; k < tc::kTraceCols; ++k) fprintf(f, " %lld", h[w * tc::kTraceCols + k]);
                 fprintf(f, "\n");
             }

@@ -16,7 +16,9 @@ SEGMENTS = [("convert x1, x2 of the next step", 8, (0, 1)), ("finish_ab: p = a*b
 
 
 def main():
-    rows = np.loadtxt(sys.argv[1], dtype=np.int64)
+    allrows = np.loadtxt(sys.argv[1], dtype=np.int64)
+    issuers = allrows[allrows[:, 1] >= 10]
+    rows = allrows[allrows[:, 1] < 8]
     rows = rows[rows[:, 9] > 0]
     steps = rows[:, 9] * 4
     total = rows[:, 8] / steps
@@ -30,6 +32,15 @@ def main():
             seg = rows[:, 2 + col] / steps
             inside = sum(rows[:, 2 + w] / steps for w in waits)
             print(f"  segment {name:32s} {seg.mean():7.0f}  of which waiting {inside.mean():6.0f}, busy {seg.mean() - inside.mean():6.0f}")
+
+
+    if rows.shape[1] >= 15:
+        per = rows[:, 14] / steps
+        print(f"  hand-off: issuer's commit issued -> worker awake {per.mean():7.0f}   (the tail of b's chain + the mbarrier hop)")
+    issuers = issuers[issuers[:, 4] > 0]
+    if len(issuers):
+        print(f"  hand-off: last worker arrive (x2 operand) -> issuer awake {np.mean(issuers[:, 2] / issuers[:, 4]):7.0f};  "
+              f"issue of b's five MMAs + commit {np.mean(issuers[:, 3] / issuers[:, 4]):7.0f}")
 
 
 if __name__ == "__main__":
