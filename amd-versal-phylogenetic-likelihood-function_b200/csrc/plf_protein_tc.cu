@@ -23,16 +23,17 @@
 //                     {20 floats x 128 sites} boxes -- one (category, child) operand, 10 KB, row pitch 80 B, which makes
 //                     the row-per-lane LDS.128 reads conflict-free -- into a 4-box ring per group.  Rows past the end
 //                     of the site range are zero-filled by the TMA unit.
-//   warps 10 / 11     one MMA-ISSUER lane per group: waits for the workers' "operand is in TMEM" mbarriers, issues the
-//                     five MMAs of a product, commits to the mbarrier the workers wait on.
+//   warps 10 / 11     one MMA-ISSUER warp per group: waits (converged) for the workers' "operand is in TMEM" mbarriers, an
+//                     elected lane issues the five MMAs of a product back to back and commits to the mbarrier the
+//                     workers wait on.
 //   A operands        never touch shared memory again: a worker splits its row into hi/lo in registers and writes
 //                     [hi(20) | lo(20)] to TMEM (tcgen05.st); the MMAs take A from TMEM and B (the nine constant
 //                     matrices, pre-split, 40 x 40 blocks in the K-major no-swizzle canonical layout, 56 KB) from
 //                     shared memory.
 //   per category      a = x1.P_l^T, b = x2.P_r^T (10 MMAs) -> tcgen05.ld -> p = a*b in registers, split, tcgen05.st ->
 //                     x3 = p.EV (5 MMAs) -> tcgen05.ld into registers; after the fourth category the thread holds its
-//                     site's 80 results: threshold test, x 2^32, staging boxes, TMA tensor stores (SASS UTMASTG),
-//                     scaler byte, scaler count.
+//                     site's 80 results: threshold test, x 2^32, a staging row per site, one {80 x 32} TMA tensor store
+//                     per warp (SASS UTMASTG), scaler byte, scaler count.
 // TMEM: 512 columns = 2 groups x (3 accumulators x 40 + 3 A-operand regions x 40) (+ 16 unused per group).
 // How it got here (3.3 -> 6.3 G sites/s) and what bounds it now: profiles/r02_protein_tc.md.
 #include "../../include/b200plf.h"
@@ -133,11 +134,17 @@ __device__ __forceinline__ void mma_commit(uint64_t *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
+// one lane of the (converged) warp, chosen by the hardware: the predicate nvcc recognises for uniform-datapath code
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, 128;" :: "r"(1 + g) : "memory"); }
 
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
 {
@@ -275,10 +282,13 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
     unsigned long long my_sum = 0;
 
     if (warp >= 10) {
-        // ===== MMA issuers: one lane per group.  tcgen05.mma is issued by a single thread; a dedicated one keeps the
-        // ~25 descriptor/issue instructions per MMA (108 MMAs per tile) off the workers' critical path. =====
-        if (lane == 0) {
-            const int g = warp - 10;
+        // ===== MMA issuers: one warp per group.  tcgen05.mma is issued by a single thread; a dedicated warp keeps the issue
+        // (~100 cycles per MMA here, 74 at best: tools/microbench_mma.cu) off the workers' critical path.  The whole warp
+        // runs the loop and waits on the mbarriers, and one ELECTED lane issues: with warp-uniform control flow the
+        // operands live in uniform registers, where a branch on the lane number costs a broadcast loop per MMA. =====
+        {
+            const int g = __shfl_sync(0xffffffffu, warp, 0) - 10;
+            const bool leader = elect_one();
             const uint32_t tcol = tmem_base + (uint32_t)g * 256u;
             const uint32_t b_base = smem_u32(smem_b);
             const size_t first = (size_t)blockIdx.x * 2 + g, stride = (size_t)gridDim.x * 2;
@@ -296,39 +306,46 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
                 if (sidx > 0) {                                // x(sidx - 1) = p . EV
                     mbar_wait(&rdy_p[g], ph ^ 1u);             // completed in the PREVIOUS step's phase
                     tc_fence_after();
-                    product(tcol + kColAccX, tcol + kColP, 8);
-                    mma_commit(&mma_x[g]);
+                    if (leader) {
+                        product(tcol + kColAccX, tcol + kColP, 8);
+                        mma_commit(&mma_x[g]);
+                    }
+                    __syncwarp();
                 }
                 if (sidx < steps) {                            // ab(sidx)
                     const int c = (int)(sidx & 3);
                     mbar_wait(&rdy_a[g], ph);
                     tc_fence_after();
-                    product(tcol + kColAccA, tcol + kColA1, c);
+                    if (leader) product(tcol + kColAccA, tcol + kColA1, c);
+                    __syncwarp();
                     mbar_wait(&rdy_b[g], ph);
-                    uint32_t t_wake = 0;
-                    if constexpr (TRACE) {
-                        t_wake = (uint32_t)clock();
-                        uint32_t last = stamp_arrive_b[g * 4];
-                        for (int q = 1; q < 4; ++q) {
-                            const uint32_t v = stamp_arrive_b[g * 4 + q];
-                            if ((int32_t)(v - last) > 0) last = v;
-                        }
-                        iacc[0] += t_wake - last;              // last worker arrive -> issuer awake
-                    }
                     tc_fence_after();
-                    product(tcol + kColAccB, tcol + kColA2, 4 + c);
-                    mma_commit(&mma_ab[g]);
-                    if constexpr (TRACE) {
-                        const uint32_t t_done = (uint32_t)clock();
-                        iacc[1] += t_done - t_wake;            // five MMAs and the commit issued
-                        stamp_commit[g] = t_done;
-                        ++iacc[2];
+                    if (leader) {
+                        uint32_t t_wake = 0;
+                        if constexpr (TRACE) {
+                            t_wake = (uint32_t)clock();
+                            uint32_t last = stamp_arrive_b[g * 4];
+                            for (int q = 1; q < 4; ++q) {
+                                const uint32_t v = stamp_arrive_b[g * 4 + q];
+                                if ((int32_t)(v - last) > 0) last = v;
+                            }
+                            iacc[0] += t_wake - last;          // last worker arrive -> issuer awake
+                        }
+                        product(tcol + kColAccB, tcol + kColA2, 4 + c);
+                        mma_commit(&mma_ab[g]);
+                        if constexpr (TRACE) {
+                            const uint32_t t_done = (uint32_t)clock();
+                            iacc[1] += t_done - t_wake;        // five MMAs and the commit issued
+                            stamp_commit[g] = t_done;
+                            ++iacc[2];
+                        }
                     }
+                    __syncwarp();
                     ph ^= 1u;
                 }
             }
             if constexpr (TRACE) {
-                if (trace) {
+                if (trace && leader) {
                     long long *row = trace + ((size_t)gridDim.x * 8 + (size_t)blockIdx.x * 2 + g) * kTraceCols;
                     row[0] = iacc[0];
                     row[1] = iacc[1];
@@ -383,16 +400,6 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
         auto seg_end = [&](int kind, uint32_t t0) {
             if constexpr (TRACE) wacc[kind] += (uint32_t)clock() - t0;
         };
-        auto sync_on = [&](int kind) {
-            if constexpr (TRACE) {
-                const uint32_t t0 = (uint32_t)clock();
-                group_sync(g);
-                wacc[kind] += (uint32_t)clock() - t0;
-            } else {
-                group_sync(g);
-            }
-        };
-
         // convert: both children of the NEXT (tile, category) in ring order: ring -> registers -> hi/lo -> TMEM, then the
         // 18 branch MMAs  a = x1 . P_left[c]^T,  b = x2 . P_right[c]^T  (hi.hi + lo.hi + hi.lo, three K = 8 steps each)
         auto convert = [&]() {
@@ -469,13 +476,15 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
         if (first < n_tiles) convert();
         // Results.  A site's 320 bytes are contiguous in x3, but the lanes of a warp are 320 B apart: direct 256-bit stores
         // are 32 sector requests per instruction, 1280 per tile and group, and were a quarter of the time of the version that
-        // used them (profiles/r02_protein_tc.md).  Instead every thread writes its row, category by category as the
-        // results come out of TMEM (in the shadow of the next step's MMAs), into four {20 floats x 128 sites} staging
-        // boxes -- the layout of the input boxes, row pitch 80 B, conflict-free -- and lane 0 of each of the four warps
-        // hands one box to the TMA unit (tensor stores, SASS UTMASTG): asynchronous, whole rows, rows past the end of the
-        // site range clipped by the unit.  A site that needs the x 2^32 rescale rewrites its rows from its registers.
-        unsigned char *stage = smem + kOffOut + (size_t)g * 4 * kBoxBytes;
+        // used them (profiles/r02_protein_tc.md).  Instead every WARP stages its 32 sites in the global layout (32 rows of
+        // 320 B, category by category as the results come out of TMEM) and its lane 0 hands them to the TMA unit as ONE
+        // {80 floats x 32 sites} tensor store (SASS UTMASTG): asynchronous, rows past the end of the site range clipped
+        // by the unit, and no synchronisation beyond the warp.  The row-per-lane writes at a 320 B pitch are 4-way bank
+        // conflicts; they buy 32 requests of 320 B per warp and tile where category boxes {20 x 128} cost 128 of 80 B --
+        // the TMA unit takes about one request per 3.7 cycles whatever its size (tools/microbench_tma.cu), and with
+        // 80-byte rows in both directions that rate, not HBM, was the kernel's bound.
         const int wq = warp & 3;
+        unsigned char *stage = smem + kOffOut + ((size_t)g * 4 + wq) * kBoxBytes;      // this warp's 32 rows x 320 B
         for (size_t tile = first; tile < n_tiles; tile += stride) {
             // running maximum of |x3| over the site's 80 results, as integer maxima of the magnitude bits in four
             // independent chains (a NaN or Inf has larger magnitude bits than any finite value, so "all 80 below 2^-32"
@@ -489,8 +498,8 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
                 if (cnt3) cnt_in = (cnt1 ? __ldg(cnt1 + site) : 0) + (cnt2 ? __ldg(cnt2 + site) : 0);
                 if (wgt) weight = __ldg(wgt + site);
             }
-            auto put_row = [&](int c, float f) {               // this thread's row of category c, times f, into staging box c
-                float4 *dst = reinterpret_cast<float4 *>(stage + (size_t)c * kBoxBytes + (size_t)t * (kS * 4));
+            auto put_row = [&](int c, float f) {               // category c of this thread's site, times f, into its staging row
+                float4 *dst = reinterpret_cast<float4 *>(stage + (size_t)lane * (kSite * 4) + (size_t)c * (kS * 4));
 #pragma unroll
                 for (int q = 0; q < 5; ++q)
                     dst[q] = make_float4(__fmul_rn(out[c][4 * q], f), __fmul_rn(out[c][4 * q + 1], f), __fmul_rn(out[c][4 * q + 2], f),
@@ -522,9 +531,8 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
                 if (c == 1) {
                     const uint32_t tr = seg_begin();
                     if (lane == 0) bulk_wait_read_all();
-                    if constexpr (TRACE) __syncwarp();
+                    __syncwarp();
                     seg_end(4, tr);
-                    sync_on(4);
                 }
                 if (c >= 1) put_row(c - 1, 1.0f);
                 seg_end(10, ts);
@@ -538,9 +546,9 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
                 put_row(2, kTwoToThe32);
             }
             fence_proxy_async_smem();                          // generic-proxy writes -> visible to the TMA unit
-            sync_on(5);
+            __syncwarp();
             if (lane == 0) {
-                tma_store_box(&map3, wq * kS, (int)(tile * kTile), stage + (size_t)wq * kBoxBytes);
+                tma_store_box(&map3, 0, (int)(tile * kTile) + wq * 32, stage);
                 bulk_commit();
             }
             if (site < n) {
@@ -587,13 +595,13 @@ static EncodeTiledFn encode_fn()
 }
 
 // CLV as a 2-D tensor {80 floats, n sites}, row pitch 320 B; box = one category of 128 sites
-static bool make_map(CUtensorMap *map, const float *x, size_t n)
+static bool make_map(CUtensorMap *map, const float *x, size_t n, bool whole_rows = false)
 {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     const cuuint64_t dims[2] = {(cuuint64_t)kSite, (cuuint64_t)n};
     const cuuint64_t strides[1] = {(cuuint64_t)kSite * sizeof(float)};
-    const cuuint32_t box[2] = {(cuuint32_t)kS, (cuuint32_t)kTile};
+    const cuuint32_t box[2] = {(cuuint32_t)(whole_rows ? kSite : kS), (cuuint32_t)(whole_rows ? 32 : kTile)};
     const cuuint32_t elem[2] = {1, 1};
     return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(x), dims, strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -611,7 +619,7 @@ int launch_newview_aa_tc(const float *x1, const float *x2, float *x3, unsigned c
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
         return PLF_ERR_CUDA;
     CUtensorMap m1, m2, m3;
-    if (!tc::make_map(&m1, x1, n) || !tc::make_map(&m2, x2, n) || !tc::make_map(&m3, x3, n)) return PLF_ERR_CUDA;
+    if (!tc::make_map(&m1, x1, n) || !tc::make_map(&m2, x2, n) || !tc::make_map(&m3, x3, n, true)) return PLF_ERR_CUDA;
     const char *trace_path = getenv("PLF_TC_TRACE");
     auto kernel = trace_path ? tc::plf_newview_aa_tc<true> : tc::plf_newview_aa_tc<false>;
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc::kSmemBytes) != cudaSuccess)

@@ -9,7 +9,7 @@ import sys
 
 import numpy as np
 
-WAITS = ["x1 box (TMA)", "x2 box (TMA)", "branch MMAs (mma_ab)", "EV MMAs (mma_x)", "staging free (+ sync)", "staged sync"]
+WAITS = ["x1 box (TMA)", "x2 box (TMA)", "branch MMAs (mma_ab)", "EV MMAs (mma_x)", "staging rows free", "(unused)"]
 # segment -> the waits that happen inside it
 SEGMENTS = [("convert x1, x2 of the next step", 8, (0, 1)), ("finish_ab: p = a*b", 9, (2,)), ("results of this category", 10, (3, 4)),
             ("tile end (rescale, stores)", 11, (5,))]
