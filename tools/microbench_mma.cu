@@ -12,6 +12,10 @@
 // Measured on B200 (profiles/r02_microbench_mma.txt): one thread issues one MMA per 74 cycles whatever N (8 ... 128), M
 // (64, 128), operand form or dependency; N = 256 takes 131.  Chains of different warps run side by side at 74 cycles
 // each up to three warps, 85 at six (14 cycles per MMA in aggregate), and saturate at eight; lanes of one warp do not.
+// CAUTION about what the 74 cycles are: this program issues from `if (lane == 0)`, and in a branch on the lane number
+// nvcc wraps every UTCHMMA in an ELECT / R2UR.BROADCAST loop (the operands live in uniform registers).  The kernel's
+// issuer warps used the same idiom until v13; with the warp converged and elect.sync choosing the lane, five MMAs and
+// a commit take 170-230 cycles (profiles/r02_protein_tc.md).  So this measures the idiom, not the tensor core.
 // Operand contents are zeros; only the timing matters.  Build:
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o build/microbench_mma tools/microbench_mma.cu
 #include <cuda_runtime.h>
