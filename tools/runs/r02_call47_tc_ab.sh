@@ -4,7 +4,7 @@ set -u
 P=amd-versal-phylogenetic-likelihood-function_b200
 mkdir -p gpurun_out
 for round in 1 2 3; do
-  for v in v13 v15; do
+  for v in v15 v17; do
     cp $P/build/alt/lib_$v.so $P/libb200plf.so
     echo "== $v round $round"; timeout 120 python tools/tc_check.py time 2>&1 | head -2 | cut -c1-120
   done
