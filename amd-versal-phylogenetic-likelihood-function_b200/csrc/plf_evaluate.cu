@@ -21,9 +21,14 @@
 #include "plf_kernels.cuh"
 #include "plf_registry.h"
 
+#include <atomic>
+#include <cstdint>
+#include <cstdlib>
+
 namespace plf {
 
 constexpr int kEvalThreads = 256;
+constexpr size_t kEvalRingMinSites = (size_t)1 << 18;      // below ~2 stages per SM the load-use-load kernel is as fast
 
 // S states per category (4: DNA, one 128-bit load per child and element; 20: protein, five), U independent
 // (site, category) elements per thread and iteration.  diag is [category][state], 4*S floats.
@@ -136,6 +141,156 @@ plf_evaluate_kernel(const float4 *__restrict__ x1, const float4 *__restrict__ x2
     }
 }
 
+// The same sum for S = 4 with the operands fed by the bulk-copy engine through an mbarrier ring, as in the newview kernels
+// (plf_newview_tma): one producer lane keeps DEPTH stages of 768 sites (2 x 48 KB) in flight whatever the consumers are
+// doing, where the load-use-load loop above leaves the memory system idle while a warp takes its logarithms (ncu on that
+// kernel: DRAM 72 %, 9 warps per issue slot waiting on loads).  Static stage schedule (stage st belongs to block st mod
+// grid), so the summation order -- and the result -- is still a function of (n, SM count) only.
+constexpr int kRingWarps = 24, kRingU = 4, kRingDepth = 2;
+constexpr int kRingThreads = (kRingWarps + 1) * 32;
+constexpr int kRingStage = kRingWarps * 8 * kRingU;             // 768 sites per stage
+constexpr size_t kRingSmem = (size_t)kRingDepth * kRingStage * 64 * 2 + 2 * kRingDepth * sizeof(uint64_t);
+
+__global__ void __launch_bounds__(kRingThreads, 1)
+plf_evaluate_ring(const float4 *__restrict__ x1, const float4 *__restrict__ x2, const int *__restrict__ cnt1,
+                  const int *__restrict__ cnt2, const int *__restrict__ wgt, const float *__restrict__ diag, size_t n,
+                  double *__restrict__ lnl, StreamScratch *__restrict__ scratch, int flags)
+{
+    constexpr int U = kRingU, STAGE = kRingStage, STAGE_F4 = STAGE * 4, TILE = 8 * U, DEPTH = kRingDepth;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4 *s1 = reinterpret_cast<float4 *>(smem_raw);                 // [DEPTH][STAGE_F4]
+    float4 *s2 = s1 + (size_t)DEPTH * STAGE_F4;
+    uint64_t *full = reinterpret_cast<uint64_t *>(s2 + (size_t)DEPTH * STAGE_F4);
+    uint64_t *empty = full + DEPTH;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t n_stages = (n + STAGE - 1) / STAGE;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int d = 0; d < DEPTH; ++d) {
+            mbar_init(&full[d], 1);
+            mbar_init(&empty[d], kRingWarps);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    double acc = 0.0;
+    if (warp == kRingWarps) {
+        if (lane == 0) {
+            uint32_t slot = 0, phase = 0;
+            for (size_t st = blockIdx.x; st < n_stages; st += gridDim.x) {
+                mbar_wait(&empty[slot], phase ^ 1u);
+                const size_t s0 = st * STAGE, left = n - s0;
+                const uint32_t bytes = (uint32_t)(left < (size_t)STAGE ? left : (size_t)STAGE) * 64u;
+                mbar_arrive_expect_tx(&full[slot], 2u * bytes);
+                bulk_g2s(s1 + slot * STAGE_F4, x1 + s0 * 4, bytes, &full[slot]);
+                bulk_g2s(s2 + slot * STAGE_F4, x2 + s0 * 4, bytes, &full[slot]);
+                if (++slot == DEPTH) {
+                    slot = 0;
+                    phase ^= 1u;
+                }
+            }
+        }
+    } else {
+        const int cat = lane & 3;
+        const float4 dg = __ldg(reinterpret_cast<const float4 *>(diag) + cat);
+        const double log_min = -32.0 * 0.69314718055994530942;    // log(2^-32)
+        const uint32_t tile_off = warp * (TILE * 4) + lane;
+        uint32_t slot = 0, phase = 0;
+        for (size_t st = blockIdx.x; st < n_stages; st += gridDim.x) {
+            // the lane with category u finishes element u of its four: its site within the range
+            const size_t my_site = st * STAGE + (size_t)warp * TILE + (lane >> 2) + 8 * cat;
+            const bool my_live = my_site < n;
+            int c = 0, w = 1;                                     // asked for before the wait: 4 B per site each
+            if (my_live) {
+                if (cnt1) c += __ldg(cnt1 + my_site);
+                if (cnt2) c += __ldg(cnt2 + my_site);
+                if (wgt) w = __ldg(wgt + my_site);
+            }
+            const float4 *t1 = s1 + slot * STAGE_F4 + tile_off;
+            const float4 *t2 = s2 + slot * STAGE_F4 + tile_off;
+            mbar_wait(&full[slot], phase);
+            float4 a[U], b[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                a[u] = t1[32 * u];
+                b[u] = t2[32 * u];
+            }
+            unsigned dep = 0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) dep ^= __float_as_uint(a[u].x) ^ __float_as_uint(b[u].w);
+            release_slot(&empty[slot], lane, dep, flags);
+            if (++slot == DEPTH) {
+                slot = 0;
+                phase ^= 1u;
+            }
+            double mine = 0.0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                // rows past the end of the site range were not copied: whatever the slot holds there is never used
+                double t = (double)a[u].x * (double)b[u].x * (double)dg.x + (double)a[u].y * (double)b[u].y * (double)dg.y +
+                           (double)a[u].z * (double)b[u].z * (double)dg.z + (double)a[u].w * (double)b[u].w * (double)dg.w;
+                t += __shfl_xor_sync(0xffffffffu, t, 1);
+                t += __shfl_xor_sync(0xffffffffu, t, 2);
+                if (cat == u) mine = t;
+            }
+            if (my_live) acc += (double)w * (log(0.25 * fabs(mine)) + (double)c * log_min);
+        }
+    }
+    __shared__ double warp_acc[kRingThreads / 32];
+    __shared__ bool is_last;
+    auto block_sum = [&](double v) {             // fixed tree: shuffles within the warp, then across the warps
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        __syncthreads();
+        if (lane == 0) warp_acc[warp] = v;
+        __syncthreads();
+        double t = threadIdx.x < kRingThreads / 32 ? warp_acc[threadIdx.x] : 0.0;
+        if (threadIdx.x < 32) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        }
+        return t;                                // valid in thread 0
+    };
+    const double mine = block_sum(acc);
+    if (threadIdx.x == 0) {
+        scratch->partials[blockIdx.x] = mine;
+        __threadfence();
+        is_last = atomicAdd(&scratch->ticket, 1ull) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double part = 0.0;
+    for (unsigned b = threadIdx.x; b < gridDim.x; b += kRingThreads) part += __ldcg(&scratch->partials[b]);
+    const double total = block_sum(part);
+    if (threadIdx.x == 0) {
+        atomicAdd(lnl, total);                   // the launch's only addition
+        scratch->ticket = 0ull;                  // clean for the next launch on this stream
+    }
+}
+
+static int launch_evaluate_ring(const float *x1, const float *x2, const int *cnt1, const int *cnt2, const int *wgt,
+                                const float *diag, size_t n, double *lnl, cudaStream_t stream, int sms)
+{
+    static std::atomic<int> prepared[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return PLF_ERR_CUDA;
+    if (!prepared[dev].load(std::memory_order_acquire)) {
+        if (cudaFuncSetAttribute(plf_evaluate_ring, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRingSmem) != cudaSuccess)
+            return PLF_ERR_CUDA;
+        prepared[dev].store(1, std::memory_order_release);
+    }
+    size_t grid = (n + kRingStage - 1) / kRingStage;
+    if (grid > (size_t)sms) grid = sms;
+    StreamScratch *scratch = nullptr;
+    if (int rc = stream_scratch(stream, &scratch)) return rc;
+    plf_evaluate_ring<<<(int)grid, kRingThreads, kRingSmem, stream>>>(reinterpret_cast<const float4 *>(x1),
+                                                                     reinterpret_cast<const float4 *>(x2), cnt1, cnt2, wgt, diag,
+                                                                     n, lnl, scratch, fenced_release(true) ? kFlagFencedRelease : 0);
+    count_launches(1);
+    return cudaGetLastError() == cudaSuccess ? PLF_OK : PLF_ERR_CUDA;
+}
+
 template <int S, int U>
 static int launch_evaluate_t(const float *x1, const float *x2, const int *cnt1, const int *cnt2, const int *wgt,
                              const float *diag, size_t n, double *lnl, cudaStream_t stream, int sms)
@@ -161,6 +316,9 @@ int launch_evaluate(int states, const float *x1, const float *x2, const int *cnt
     if (cudaGetDevice(&dev) != cudaSuccess ||
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
         return PLF_ERR_CUDA;
+    // the ring kernel needs 16-byte aligned CLVs (bulk copies) and enough stages to fill its pipeline
+    if (states == 4 && n >= kEvalRingMinSites && (((uintptr_t)x1 | (uintptr_t)x2) & 15u) == 0 && !getenv("PLF_EVAL_NO_RING"))
+        return launch_evaluate_ring(x1, x2, cnt1, cnt2, wgt, diag, n, lnl, stream, sms);
     if (states == 4) return launch_evaluate_t<4, 4>(x1, x2, cnt1, cnt2, wgt, diag, n, lnl, stream, sms);
     if (states == 20) return launch_evaluate_t<20, 1>(x1, x2, cnt1, cnt2, wgt, diag, n, lnl, stream, sms);
     return PLF_ERR_INVALID;

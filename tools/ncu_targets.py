@@ -41,6 +41,16 @@ def main():
         torch.cuda.synchronize()
         v = lnl.cpu().numpy()
         assert v[0] == v[1] == v[2] and np.isfinite(v[0])
+        if "--time" in sys.argv:                                # events around 20 launches: G sites/s, GB/s (136 B/site)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for i in range(20):
+                pkg.evaluate_device(x1.data_ptr(), x2.data_ptr(), c1.data_ptr(), c2.data_ptr(), None, diag.data_ptr(), n,
+                                    lnl[3:].data_ptr(), stream)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 20
+            print(f"evaluate {n} sites: {ms:.4f} ms = {n / ms / 1e6:.2f} G sites/s = {136 * n / ms / 1e6:.0f} GB/s, lnL {v[0]!r}")
     elif what in ("cfg2", "cfg3"):
         n, sets, reps = ((1 << 20), 6, 40) if what == "cfg2" else ((64 << 20), 1, 3)
         x1 = [torch.empty((n, 16), device=dev) for _ in range(sets)]
