@@ -23,7 +23,8 @@ def test_evaluate_oracle_hand_case():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n", [1, 7, 8, 1000, 65537, 1 << 20])
+# from 2^18 sites on, 4-state calls take the ring-fed kernel (stages of 768 sites: all of these end in a ragged stage)
+@pytest.mark.parametrize("n", [1, 7, 8, 1000, 65537, (1 << 18) - 1, 1 << 18, 300001, 1 << 20])
 def test_evaluate_device_matches_oracle(pkg, n):
     import torch
     rng = np.random.RandomState(n)
@@ -43,6 +44,12 @@ def test_evaluate_device_matches_oracle(pkg, n):
         want = evaluate_oracle.evaluate(x1, x2, diag, c1 if use_cnt else None, c2 if use_cnt else None,
                                         wgt if use_w else None)
         assert abs(lnl.item() - want) <= REL_TOL * abs(want), (n, use_cnt, use_w, lnl.item(), want)
+        again = torch.zeros(1, dtype=torch.float64, device="cuda")           # same launch, same bits
+        pkg.evaluate_device(d[0].data_ptr(), d[1].data_ptr(), d[2].data_ptr() if use_cnt else None,
+                            d[3].data_ptr() if use_cnt else None, d[4].data_ptr() if use_w else None,
+                            d[5].data_ptr(), n, again.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert again.item() == lnl.item()
 
 
 @pytest.mark.gpu

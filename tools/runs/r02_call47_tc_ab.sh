@@ -1,5 +1,6 @@
 #!/bin/bash
-# same-box A/B of two builds of the tcgen05 kernel (build/alt), alternating
+# same-box A/B of two builds of the tcgen05 kernel, alternating.  The alternative libraries are built beforehand into
+# build/alt/lib_<name>.so (the other objects of build/ linked with an alternative plf_protein_tc.o) and are not kept.
 set -u
 P=amd-versal-phylogenetic-likelihood-function_b200
 mkdir -p gpurun_out
