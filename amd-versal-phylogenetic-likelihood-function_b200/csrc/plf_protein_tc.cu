@@ -35,7 +35,7 @@
 //                     site's 80 results: threshold test, x 2^32, a staging row per site, one {80 x 32} TMA tensor store
 //                     per warp (SASS UTMASTG), scaler byte, scaler count.
 // TMEM: 512 columns = 2 groups x (3 accumulators x 40 + 3 A-operand regions x 40) (+ 16 unused per group).
-// How it got here (3.3 -> 6.3 G sites/s) and what bounds it now: profiles/r02_protein_tc.md.
+// How it got here (3.3 -> 6.4 G sites/s) and what bounds it now: profiles/r02_protein_tc.md.
 #include "../../include/b200plf.h"
 #include "plf_kernels.cuh"
 #include "plf_registry.h"
@@ -63,8 +63,8 @@ constexpr int kRing = PLF_TC_RING;           // boxes per group ring (4 = 2 step
 //            n < 20        n >= 20
 //   k < 20   B_hi[n][k]    B_lo[n - 20][k]         D[:, 0:20]  = A_hi.B_hi + A_lo.B_hi
 //   k >= 20  B_hi[n][k-20] 0                       D[:, 20:40] = A_hi.B_lo           (added on read-back)
-// Tiny MMAs cost ~59 cycles each whatever their N (27 of them per step and group was exactly the step time of the
-// nine-MMAs-per-product version); 15 per step is what moved the kernel from the tensor core's issue rate to HBM.
+// The price of a small MMA is per instruction, not per column (N is free up to 128: tools/microbench_mma.cu), so the
+// obvious nine MMAs per product -- one per 3xTF32 term and K step -- cost nearly twice what these five do.
 constexpr int kN = 40;                       // MMA N.  M = 128 with N % 8 == 0 is accepted by the hardware at cta_group::1 (CUTLASS's
                                              // static asserts want N % 16 == 0)
 constexpr int kK = 40;                       // K (five K = 8 steps)
@@ -77,7 +77,7 @@ constexpr int kThreads = 384;               // 8 worker warps, 2 producer warps,
 constexpr size_t kOffRing = 0;                                         // [2 groups][kRing][kBoxBytes]
 constexpr size_t kOffB = kOffRing + 2 * kRing * kBoxBytes;            // [kNumB][kBMat]
 constexpr size_t kOffBar = kOffB + (size_t)kNumB * kBMat;             // barriers
-constexpr size_t kOffOut = kOffBar + 512;             // after 34 mbarriers + the TMEM base address
+constexpr size_t kOffOut = kOffBar + 512;             // after 26 mbarriers, the TMEM base address and (trace build) the clock stamps
 constexpr size_t kSmemBytes = kOffOut + 2 * 4 * kBoxBytes;   // output staging: [2 groups][4 categories] boxes of {20 floats x 128 sites}
 
 // TMEM columns of one group (the second group sits 256 columns further)
@@ -283,9 +283,10 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
 
     if (warp >= 10) {
         // ===== MMA issuers: one warp per group.  tcgen05.mma is issued by a single thread; a dedicated warp keeps the issue
-        // (~100 cycles per MMA here, 74 at best: tools/microbench_mma.cu) off the workers' critical path.  The whole warp
-        // runs the loop and waits on the mbarriers, and one ELECTED lane issues: with warp-uniform control flow the
-        // operands live in uniform registers, where a branch on the lane number costs a broadcast loop per MMA. =====
+        // off the workers' critical path.  The whole warp runs the loop and waits on the mbarriers, and one ELECTED lane
+        // issues: with warp-uniform control flow the operands live in uniform registers and the five UTCHMMA of a product
+        // sit back to back (170-230 cycles with the commit), where a branch on the lane number makes nvcc wrap every MMA
+        // in an ELECT / R2UR.BROADCAST loop (~100 cycles each: profiles/r02_protein_tc.md). =====
         {
             const int g = __shfl_sync(0xffffffffu, warp, 0) - 10;
             const bool leader = elect_one();
