@@ -9,13 +9,14 @@
 //            4 = round-robin over independent accumulators
 //   issuers  warps issuing their own chain at the same time (or lanes of ONE warp)
 //
-// Measured on B200 (profiles/r02_microbench_mma.txt): one thread issues one MMA per 74 cycles whatever N (8 ... 128), M
-// (64, 128), operand form or dependency; N = 256 takes 131.  Chains of different warps run side by side at 74 cycles
-// each up to three warps, 85 at six (14 cycles per MMA in aggregate), and saturate at eight; lanes of one warp do not.
-// CAUTION about what the 74 cycles are: this program issues from `if (lane == 0)`, and in a branch on the lane number
-// nvcc wraps every UTCHMMA in an ELECT / R2UR.BROADCAST loop (the operands live in uniform registers).  The kernel's
-// issuer warps used the same idiom until v13; with the warp converged and elect.sync choosing the lane, five MMAs and
-// a commit take 170-230 cycles (profiles/r02_protein_tc.md).  So this measures the idiom, not the tensor core.
+// Measured on B200 (profiles/r02_microbench_mma.txt):
+//   * issued by an ELECTED lane of a converged warp (what CUTLASS does, what the kernel does since v13): 20 cycles per
+//     MMA up to N = 40, then N / 2 cycles (34 at N = 64, 66 at 128, 130 at 256: 2048 multiply-adds per cycle, the tf32
+//     peak), the same for a dependent chain and for four independent accumulators; several issuing warps share that
+//     rate (20 cycles per MMA in aggregate);
+//   * issued from `if (lane == 0)`: 74 cycles per MMA whatever N <= 128, M, operand form or dependency -- nvcc wraps
+//     every UTCHMMA of such a branch in an ELECT / R2UR.BROADCAST loop because the operands live in uniform registers.
+//     Chains of different warps then overlap (37 cycles per MMA in aggregate with two, 14 with six).
 // Operand contents are zeros; only the timing matters.  Build:
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o build/microbench_mma tools/microbench_mma.cu
 #include <cuda_runtime.h>
@@ -37,7 +38,7 @@ __device__ __forceinline__ uint64_t desc(uint32_t addr, uint32_t lbo, uint32_t s
     return d;
 }
 
-template <bool SS>
+template <bool SS, bool CONVERGED>
 __global__ void __launch_bounds__(256, 1) bench(int n, int chain, int accs, int issuers, int lanes_mode, int m, long long *out)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -69,8 +70,16 @@ __global__ void __launch_bounds__(256, 1) bench(int n, int chain, int accs, int 
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     // issuer w: warp w lane 0 (lanes_mode 0) or lane w of warp 0 (lanes_mode 1); its accumulators start at column 64 * w
-    const int w = lanes_mode ? (int)threadIdx.x : (int)(threadIdx.x >> 5);
-    const bool is_issuer = lanes_mode ? (threadIdx.x < (unsigned)issuers) : ((threadIdx.x & 31) == 0 && w < issuers);
+    // CONVERGED: the whole warp w runs the loop and elect.sync picks the issuing lane (uniform control flow: the MMA's
+    // operands stay in uniform registers, no ELECT / R2UR.BROADCAST loop around every UTCHMMA)
+    const int w = CONVERGED ? __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0) : lanes_mode ? (int)threadIdx.x : (int)(threadIdx.x >> 5);
+    bool leader = true;
+    if (CONVERGED) {
+        uint32_t pred;
+        asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+        leader = pred != 0;
+    }
+    const bool is_issuer = CONVERGED ? (w < issuers) : lanes_mode ? (threadIdx.x < (unsigned)issuers) : ((threadIdx.x & 31) == 0 && w < issuers);
     if (is_issuer) {
         uint64_t &bar = bars[w];
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
@@ -84,6 +93,7 @@ __global__ void __launch_bounds__(256, 1) bench(int n, int chain, int accs, int 
             for (int i = 0; i < chain; ++i) {
                 const uint32_t d = tmem + (uint32_t)(w * 64 + (i & (accs - 1)) * 64);       // accumulators 64 columns apart (accs: power of two)
                 const uint32_t acc = i >= accs ? 1u : 0u;                  // the first MMA into each accumulator overwrites
+                if (!leader) continue;
                 if (SS) {
                     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}\n"
@@ -94,14 +104,15 @@ __global__ void __launch_bounds__(256, 1) bench(int n, int chain, int accs, int 
                                  :: "r"(d), "r"(tmem + 448u), "l"(bd), "r"(idesc), "r"(acc), "r"(0u) : "memory");
                 }
             }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&bar)) : "memory");
+            if (leader) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&bar)) : "memory");
+            if (CONVERGED) __syncwarp();
             asm volatile("{\n\t.reg .pred p;\n\tW_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra D_%=;\n\tbra W_%=;\n\tD_%=:\n\t}"
                          :: "r"(smem_u32(&bar)), "r"(phase) : "memory");
             phase ^= 1u;
             const long long t1 = clock64();
             if (t1 - t0 < best) best = t1 - t0;
         }
-        out[blockIdx.x * 8 + w] = best;
+        if (leader) out[blockIdx.x * 8 + w] = best;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -115,10 +126,12 @@ static double run(bool ss, int n, int chain, int accs, int issuers, int lanes_mo
 {
     const int smem = 8192 + 4096;
     std::vector<long long> h(sms * 8);
-    if (ss)
-        bench<true><<<sms, 256, smem>>>(n, chain, accs, issuers, lanes_mode, m, d);
+    if (lanes_mode == 2)
+        bench<false, true><<<sms, 256, smem>>>(n, chain, accs, issuers, 0, m, d);
+    else if (ss)
+        bench<true, false><<<sms, 256, smem>>>(n, chain, accs, issuers, lanes_mode, m, d);
     else
-        bench<false><<<sms, 256, smem>>>(n, chain, accs, issuers, lanes_mode, m, d);
+        bench<false, false><<<sms, 256, smem>>>(n, chain, accs, issuers, lanes_mode, m, d);
     if (cudaDeviceSynchronize() != cudaSuccess) {
         printf("launch failed: %s\n", cudaGetErrorString(cudaGetLastError()));
         exit(1);
@@ -163,6 +176,16 @@ int main()
     for (int issuers : {2, 4}) {
         const double c = run(false, 40, chain, 1, issuers, 1, 128, d, sms, &worst);
         printf("issuers %d (lanes of ONE warp)     cycles/MMA per chain %.1f   -> aggregate %.1f cycles per MMA\n", issuers, c, c / issuers);
+    }
+    printf("## the same chains issued by an ELECTED lane of a converged warp (TS, M = 128): the tensor core itself\n");
+    for (int n : {8, 40, 64, 128, 256})
+        for (int accs : {1, 4}) {
+            if (n > 64 && accs > 1) continue;
+            printf("converged  N %3d  accumulators %d  cycles/MMA %.1f\n", n, accs, run(false, n, chain, accs, 1, 2, 128, d, sms, &worst));
+        }
+    for (int issuers : {2, 4}) {
+        const double c = run(false, 40, chain, 1, issuers, 2, 128, d, sms, &worst);
+        printf("converged  issuers %d (N = 40)   cycles/MMA per chain %.1f   -> aggregate %.1f cycles per MMA\n", issuers, c, c / issuers);
     }
     return 0;
 }
