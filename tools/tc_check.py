@@ -58,8 +58,9 @@ def main():
     pkg.generate_states_device(20, x1.data_ptr(), x2.data_ptr(), 0, n, 42, stream)
     for label, math, variant, fl in (("tcgen05 3xTF32 (fenced release)", 1, 9, pkg.LAUNCH_FENCED_RELEASE),
                                      ("tcgen05 3xTF32 (dependency release)", 1, 9, pkg.LAUNCH_DEP_RELEASE),
-                                     ("cuda-core fma", 1, 0, 0), ("cuda-core strict", 0, 0, 0)):
-        opts = pkg.make_opts(math, variant, 0, 0, 0, fl)
+                                     ("FMA default (= the tcgen05 kernel at this size)", 1, 0, 0), ("cuda-core fma (variant 4, 256 threads)", 1, 4, 0),
+                                     ("cuda-core strict", 0, 0, 0)):
+        opts = pkg.make_opts(math, variant, 256 if variant == 4 else 0, 0, 0, fl)
         a = (20, x1.data_ptr(), x2.data_ptr(), x3.data_ptr(), sc.data_ptr(), ev, left, right, None, n, dsum.data_ptr(), opts, stream)
         dsum.zero_()
         for _ in range(2):
