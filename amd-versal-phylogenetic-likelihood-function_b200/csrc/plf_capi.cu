@@ -1137,8 +1137,12 @@ int plf_newview_stream(plf_ctx *ctx, const float *ev, const float *p_left, const
     opts.flags = 0;
     // A failure in the middle of the pipeline must not return while copies to or from the caller's host arrays are
     // still in flight on the other streams: drain all of them first (secondary errors of the drain are ignored).
+    std::vector<cudaEvent_t> tev;                                    // PLF_STREAM_TRACE events (below)
     auto drain = [&](int rc) {
         for (int b = 0; b < K; ++b) cudaStreamSynchronize(ctx->s_stream[b]);
+        for (cudaEvent_t e : tev)
+            if (e) cudaEventDestroy(e);
+        tev.clear();
         cudaGetLastError();
         return rc;
     };
@@ -1151,7 +1155,6 @@ int plf_newview_stream(plf_ctx *ctx, const float *ev, const float *p_left, const
     // H2D copies, after them, after the kernel, after the D2H copies -- written after the call as one line per chunk in
     // ms since the first event.  tools/stream_timeline.py turns that into the three-way overlap of the pipeline.
     const char *trace_path = getenv("PLF_STREAM_TRACE");
-    std::vector<cudaEvent_t> tev;
     auto mark = [&](cudaStream_t st) {
         if (!trace_path) return;
         cudaEvent_t e = nullptr;
