@@ -499,12 +499,34 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
                 if (cnt3) cnt_in = (cnt1 ? __ldg(cnt1 + site) : 0) + (cnt2 ? __ldg(cnt2 + site) : 0);
                 if (wgt) weight = __ldg(wgt + site);
             }
-            auto put_row = [&](int c, float f) {               // category c of this thread's site, times f, into its staging row
-                float4 *dst = reinterpret_cast<float4 *>(stage + (size_t)lane * (kSite * 4) + (size_t)c * (kS * 4));
+            // Category c of this thread's site, times f, into its staging row.  Rows are 320 B apart, so the same 16-byte
+            // chunk of eight consecutive rows falls on two bank groups (4-way conflicts).  Each pair of lanes therefore
+            // writes its five chunks in an order rotated by (lane / 2) mod 4: instruction q stores chunk (q + rot) mod 5,
+            // eight lanes hit eight bank groups (one 2-way collision in three of the five instructions).  The rotation
+            // of the values is two levels of selects -- registers cannot be indexed by the lane.
+            auto put_row = [&](int c, float f) {
+                float4 v[5];
 #pragma unroll
                 for (int q = 0; q < 5; ++q)
-                    dst[q] = make_float4(__fmul_rn(out[c][4 * q], f), __fmul_rn(out[c][4 * q + 1], f), __fmul_rn(out[c][4 * q + 2], f),
-                                         __fmul_rn(out[c][4 * q + 3], f));
+                    v[q] = make_float4(__fmul_rn(out[c][4 * q], f), __fmul_rn(out[c][4 * q + 1], f), __fmul_rn(out[c][4 * q + 2], f),
+                                       __fmul_rn(out[c][4 * q + 3], f));
+                const int rot = (lane >> 1) & 3;
+                auto sel = [](bool take_b, const float4 &a, const float4 &b) {
+                    return make_float4(take_b ? b.x : a.x, take_b ? b.y : a.y, take_b ? b.z : a.z, take_b ? b.w : a.w);
+                };
+                const bool r1 = rot & 1, r2 = rot & 2;
+                float4 w[5];
+#pragma unroll
+                for (int q = 0; q < 5; ++q) w[q] = sel(r1, v[q], v[(q + 1) % 5]);          // w[q] = v[(q + (rot & 1)) % 5]
+#pragma unroll
+                for (int q = 0; q < 5; ++q) v[q] = sel(r2, w[q], w[(q + 2) % 5]);          // v[q] = original chunk (q + rot) % 5
+                float4 *row = reinterpret_cast<float4 *>(stage + (size_t)lane * (kSite * 4) + (size_t)c * (kS * 4));
+#pragma unroll
+                for (int q = 0; q < 5; ++q) {
+                    int k = q + rot;
+                    if (k >= 5) k -= 5;
+                    row[k] = v[q];
+                }
             };
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
