@@ -84,7 +84,7 @@ constexpr size_t kSmemBytes = kOffOut + 2 * 4 * kBoxBytes;   // output staging: 
 constexpr uint32_t kColAccA = 0, kColAccB = 40, kColAccX = 80;       // accumulators, 40 columns each
 constexpr uint32_t kColA1 = 120, kColA2 = 160, kColP = 200;          // A operands [hi(20) | lo(20)]
 
-// tcgen05 instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N = 24, M = 128
+// tcgen05 instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, N = 40, M = 128
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kN >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
 
 __device__ __forceinline__ uint32_t rna_tf32(float x)
@@ -402,7 +402,7 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
             if constexpr (TRACE) wacc[kind] += (uint32_t)clock() - t0;
         };
         // convert: both children of the NEXT (tile, category) in ring order: ring -> registers -> hi/lo -> TMEM, then the
-        // 18 branch MMAs  a = x1 . P_left[c]^T,  b = x2 . P_right[c]^T  (hi.hi + lo.hi + hi.lo, three K = 8 steps each)
+        // 10 branch MMAs  a = x1 . P_left[c]^T,  b = x2 . P_right[c]^T  (one chain of five per child, see kN)
         auto convert = [&]() {
 #pragma unroll
             for (int child = 0; child < 2; ++child) {
@@ -436,7 +436,7 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
                 }
                 tmem_st20(trow + (child ? kColA2 : kColA1), hi);
                 tmem_st20(trow + (child ? kColA2 : kColA1) + kS, lo);
-                // this warp's quarter of the operand is in TMEM: tell the issuer (it starts the nine MMAs of this child
+                // this warp's quarter of the operand is in TMEM: tell the issuer (it starts the five MMAs of this child
                 // when all four warps have arrived, while the workers convert the other child)
                 tc_wait_st();
                 tc_fence_before();
@@ -447,7 +447,7 @@ plf_newview_aa_tc(const __grid_constant__ CUtensorMap map1, const __grid_constan
                 if (lane == 0) mbar_arrive(child ? &rdy_b[g] : &rdy_a[g]);
             }
         };
-        // finish_ab: p = a * b in registers, split, back to TMEM as the A operand of the 9 EV MMAs
+        // finish_ab: p = a * b in registers, split, back to TMEM as the A operand of the five EV MMAs
         auto finish_ab = [&]() {
             wait_on(2, &mma_ab[g], ph_ab);
             if constexpr (TRACE) wacc_commit += (uint32_t)clock() - stamp_commit[g];
