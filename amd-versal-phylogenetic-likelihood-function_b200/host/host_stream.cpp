@@ -68,7 +68,8 @@ int main(int argc, char *argv[])
     } catch (const std::exception &e) {
         die(e.what());
     }
-    if (cfg.n_states != 4) die("STATES=" + cfg.states + " runs through host_states.exe (this host is the DNA drop-in)");
+    const size_t S = cfg.n_states;                         // STATES knob: DNA (4) or AA (20), from the configuration name
+    const size_t SF = 4 * S;                               // floats per site
     if (cfg.input_src != PLF_INPUT_MEM) die("the streamed path reads CLVs from host memory: use an INPUT_SRC=mem configuration");
     int device = 0;
     if (plf_device_from_string(argv[2], &device) != PLF_OK) die(plf_last_error(nullptr));
@@ -82,10 +83,11 @@ int main(int argc, char *argv[])
     std::cout << "| test name:        plf streamed round trip (B200 / CUDA sm_100a)" << std::endl;
     std::cout << "| alignment sites:  " << n << "   plf calls: " << calls << "   chunk: " << (chunk ? std::to_string(chunk) : "auto")
               << std::endl;
-    std::cout << "| host CLV bytes:   " << 3.0 * n * 64 / 1e9 << " GB   device: " << name << " [" << bdf << "]" << std::endl;
+    std::cout << "| STATES:           " << cfg.states << " (" << S << " states x 4 rate categories, " << SF << " floats per site)" << std::endl;
+    std::cout << "| host CLV bytes:   " << 3.0 * n * SF * 4 / 1e9 << " GB   device: " << name << " [" << bdf << "]" << std::endl;
 
     plf_ctx *ctx = nullptr;
-    check(plf_ctx_create(&ctx, device, 1, cfg.layout, PLF_INPUT_MEM), nullptr, "plf_ctx_create");
+    check(plf_ctx_create_states(&ctx, device, 1, cfg.layout, PLF_INPUT_MEM, static_cast<int>(S)), nullptr, "plf_ctx_create_states");
     if (const char *m = std::getenv("PLF_MATH"))
         check(plf_ctx_set_math(ctx, std::strcmp(m, "fma") == 0 ? PLF_MATH_FMA : PLF_MATH_STRICT), ctx, "plf_ctx_set_math");
 
@@ -93,17 +95,19 @@ int main(int argc, char *argv[])
     const char *seed_env = std::getenv("PLF_SEED");
     std::mt19937 gen(seed_env ? static_cast<uint32_t>(std::strtoul(seed_env, nullptr, 10)) : 42u);
     std::uniform_real_distribution<> dis(0.0, 1.0);
-    float ev[16], branchleft[64], branchright[64];
-    for (float &v : ev) v = static_cast<float>(dis(gen));
-    for (int j = 0; j < 64; ++j) {
+    std::vector<float> ev_v(S * S), bl_v(4 * S * S), br_v(4 * S * S);
+    float *ev = ev_v.data(), *branchleft = bl_v.data(), *branchright = br_v.data();
+    for (float &v : ev_v) v = static_cast<float>(dis(gen));
+    for (size_t j = 0; j < 4 * S * S; ++j) {
         branchleft[j] = static_cast<float>(dis(gen));
         branchright[j] = static_cast<float>(dis(gen));
     }
-    float *x1 = pinned<float>(n * 16), *x2 = pinned<float>(n * 16), *x3 = pinned<float>(n * 16);
+    float *x1 = pinned<float>(n * SF), *x2 = pinned<float>(n * SF), *x3 = pinned<float>(n * SF);
     char *scaler = pinned<char>(n);
-    const float tiny_scale = static_cast<float>(std::pow(1.0e-12, 1));
-    for (size_t j = 0; j < n * 16; ++j) {
-        x1[j] = static_cast<float>(dis(gen) * ((j % 64 < 16) ? tiny_scale : 1.0f));
+    // every fourth site tiny on the left (host_mem.cpp:198-204); with 20 states the sums have 20 terms, hence 1e-14
+    const float tiny_scale = S == 4 ? static_cast<float>(std::pow(1.0e-12, 1)) : 1.0e-14f;
+    for (size_t j = 0; j < n * SF; ++j) {
+        x1[j] = static_cast<float>(dis(gen) * ((j % (4 * SF) < SF) ? tiny_scale : 1.0f));
         x2[j] = static_cast<float>(dis(gen));
     }
     std::vector<int> wgt(n, 1);
@@ -122,15 +126,18 @@ int main(int argc, char *argv[])
 
     int exit_code = 0;
 #if !defined(NO_CORRECTNESS_CHECK) || NO_CORRECTNESS_CHECK == 0
-    std::vector<float> cpu(n * 16);
+    std::vector<float> cpu(n * SF);
     long long inc_cpu = 0;
     const double g0 = t.elapsed_ms();
-    golden_plf(x1, x2, cpu.data(), ev, n, branchleft, branchright, wgt.data(), inc_cpu);
+    if (S == 4)
+        golden_plf(x1, x2, cpu.data(), ev, n, branchleft, branchright, wgt.data(), inc_cpu);
+    else
+        golden_plf_states(static_cast<unsigned>(S), x1, x2, cpu.data(), ev, n, branchleft, branchright, wgt.data(), inc_cpu);
     const double g1 = t.elapsed_ms();
     unsigned errors = 0;
-    for (size_t j = 0; j < n * 16 && errors < 20; ++j)
+    for (size_t j = 0; j < n * SF && errors < 20; ++j)
         if (cpu[j] != x3[j]) {
-            std::cout << "ERROR: alignment data wrong at alignment " << (j >> 4) << ", probability " << (j % 16) << ", cpu!=b200: "
+            std::cout << "ERROR: alignment data wrong at alignment " << (j / SF) << ", probability " << (j % SF) << ", cpu!=b200: "
                       << cpu[j] << "!=" << x3[j] << std::endl;
             ++errors;
         }
@@ -146,7 +153,7 @@ int main(int argc, char *argv[])
 #endif
 
     const double total_sites = static_cast<double>(n) * calls;
-    const double bytes = total_sites * 64.0;
+    const double bytes = total_sites * SF * 4.0;
     const std::string line(101, '=');
     std::cout << std::endl << line << std::endl;
     std::cout << "| Timing region                          | time (ms)  | bandwidth (MB/s) |         bandwidth (MA/s) |" << std::endl;
@@ -155,7 +162,8 @@ int main(int argc, char *argv[])
     print_row("  - fastest call:", execution_ms.min_msm(), bytes / calls, total_sites / calls);
     print_row("scaling wgt mult (host):", execution_ms.mh(), bytes, total_sites);
     std::cout << line << std::endl;
-    std::cout << "| PCIe traffic, fastest call: " << 193.0 * n / (execution_ms.min_msm() / 1e3) / 1e9 << " GB/s (128 B/site in, 65 B/site out)"
+    std::cout << "| PCIe traffic, fastest call: " << (12.0 * SF + 1.0) * n / (execution_ms.min_msm() / 1e3) / 1e9 << " GB/s (" << 8 * SF
+              << " B/site in, " << 4 * SF + 1 << " B/site out)"
               << std::endl;
 
     plf_host_free(x1);

@@ -132,6 +132,18 @@ def test_host_stream_end_to_end(hosts, sites, calls, chunk):
     assert f"scalerIncrement (last call): {(sites + 3) // 4}" in r.stdout
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("sites,calls,chunk", [(100, 1, 0), (100003, 2, 16384)])
+def test_host_stream_twenty_states(hosts, sites, calls, chunk):
+    """The same streamed round trip with an AA configuration name (STATES knob): 80-float sites, exact against the
+    host's golden loop nest."""
+    cfg = "plf_128x9AAwindow8192Comb_memAAwindowComb"
+    r = run(HOST_STREAM, *([cfg, 0, sites, calls] + ([chunk] if chunk else [])))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "Test result: Passed" in r.stdout and "20 states x 4 rate categories, 80 floats per site" in r.stdout
+    assert f"scalerIncrement (last call): {(sites + 3) // 4}" in r.stdout
+
+
 def test_host_stream_argument_errors(hosts):
     assert run(HOST_STREAM).returncode == 2
     r = run(HOST_STREAM, CFG_GEN, 0, 100, 1)
@@ -247,9 +259,8 @@ def test_host_states_argument_errors(hosts):
     assert r.returncode == 2 and "DNA or AA" in r.stderr
     r = run(HOST_STATES, "plf_128x9AAwindow8192Comb_genAAwindowComb", 0, 100, 1)
     assert r.returncode == 2 and "INPUT_SRC=mem" in r.stderr
-    for exe in (hosts[1], HOST_STREAM):                         # the gen / stream test benches are DNA only and say so
-        r = run(exe, CFG_AA, 0, 100, 1, 1)
-        assert r.returncode == 2 and ("host_states" in r.stderr or "Usage" in r.stderr)
+    r = run(hosts[1], CFG_AA, 0, 100, 1, 1)                         # the gen test bench is DNA only and says so
+    assert r.returncode == 2 and ("host_states" in r.stderr or "Usage" in r.stderr)
 
 
 @pytest.mark.gpu
