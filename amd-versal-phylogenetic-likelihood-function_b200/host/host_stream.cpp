@@ -4,7 +4,8 @@
 // (app/src/host_mem.cpp:327-382) on top of plf_newview_stream().  The host keeps the plain, unpacked
 // arrays that plf() takes (plf.h:1-5); the library cuts the site range into chunks and overlaps H2D,
 // kernel and D2H.  No packing pass, no device-memory limit on the site count.  Same stimulus recipe,
-// same exact verification against the CPU golden as host_mem.
+// same exact verification against the CPU golden as host_mem; the configuration name selects the state count
+// (...DNA...: 16-float sites, ...AA...: 80-float sites).
 //
 //   host_stream.exe <config name> <device ordinal | PCI BDF> <sites> <plf calls> [chunk sites]
 #include <cmath>
