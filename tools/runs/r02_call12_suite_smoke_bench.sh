@@ -1,4 +1,5 @@
 #!/bin/bash
+# full GPU suite, smoke, default bench, SASS census of the tensor-core object (mid-round)
 set -u
 mkdir -p gpurun_out
 timeout 1800 python -m pytest tests -m gpu -q > gpurun_out/c12_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/c12_pytest.log

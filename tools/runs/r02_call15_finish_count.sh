@@ -1,4 +1,5 @@
 #!/bin/bash
+# small-launch study after the producer-side finish count: tests, 1 Mi-site launches, 8-shape sweep
 set -u
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_tree.py tests/test_stress.py -m gpu -q -x > gpurun_out/c15_pytest.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/c15_pytest.log

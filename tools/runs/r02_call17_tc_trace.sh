@@ -1,4 +1,5 @@
 #!/bin/bash
+# the first clock64 stamp trace of the tcgen05 kernel (one traced thread)
 set -u
 mkdir -p gpurun_out
 PLF_TC_TRACE=gpurun_out/c17_tc_trace.txt timeout 120 python - <<'P'

@@ -1,4 +1,5 @@
 #!/bin/bash
+# time per launch against launch size (1 ... 64 Mi sites), four kernel shapes
 set -u
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_protein_tc.py -m gpu -q > gpurun_out/c34_pytest.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/c34_pytest.log

@@ -1,4 +1,5 @@
 #!/bin/bash
+# host program tests after host_stream.exe gained the STATES knob; one 2 M-site AA run
 set -u
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_hosts.py -m gpu -q > gpurun_out/c64_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/c64_pytest.log
